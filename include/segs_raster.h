@@ -1,0 +1,211 @@
+/*
+ * segs_raster.h — C ABI of the B200-native (sm_100a) Gaussian-splatting rasterizer,
+ * anchor-init kNN and anchor decoder that drop in behind SEGS-SLAM's L6/L7 entry points.
+ *
+ * Every entry point takes plain device pointers, sizes, a cudaStream_t (as void*) and —
+ * where the reference grows opaque byte tensors through std::function<char*(size_t)>
+ * (/root/reference/cuda_rasterizer/rasterizer.h:32-34) — C allocation callbacks.
+ * All functions return 0 on success and a non-zero status otherwise; the message of the
+ * last failure on the calling thread is returned by segs_last_error().  No torch types,
+ * no global mutable state: every call is self-contained in the buffers it is handed.
+ *
+ * Reference interface replaced by each function (file:line under /root/reference):
+ *
+ *   segs_raster_forward      CudaRasterizer::Rasterizer::forward        cuda_rasterizer/rasterizer.h:31-53,
+ *                                                                       rasterizer_impl.cu:198-336
+ *                            (called by RasterizeGaussiansCUDA,         src/rasterize_points.cu:36-114)
+ *   segs_raster_backward     CudaRasterizer::Rasterizer::backward       cuda_rasterizer/rasterizer.h:73-101,
+ *                                                                       rasterizer_impl.cu:397-490
+ *                            (called by RasterizeGaussiansBackwardCUDA, src/rasterize_points.cu:116-193)
+ *   segs_visible_filter      CudaRasterizer::Rasterizer::visible_filter cuda_rasterizer/rasterizer.h:55-71,
+ *                                                                       rasterizer_impl.cu:339-393
+ *                            (called by RasterizeGaussiansfilterCUDA,   src/rasterize_points.cu:216-276)
+ *   segs_mark_visible        CudaRasterizer::Rasterizer::markVisible    cuda_rasterizer/rasterizer.h:24-29,
+ *                                                                       rasterizer_impl.cu:141-153
+ *                            (called by markVisible,                    src/rasterize_points.cu:195-214)
+ *   segs_project             CudaRasterizer::Rasterizer::project2_image cuda_rasterizer/rasterizer.h:103-125,
+ *                                                                       rasterizer_impl.cu:494-585
+ *                            (called by RasterizeGaussiansprojectCUDA,  src/rasterize_points.cu:278-362)
+ *   segs_knn_mean_dist2      SimpleKNN::knn                             third_party/simple-knn/simple_knn.h:15-19,
+ *                                                                       simple_knn.cu:185-221
+ *                            (called by distCUDA2,                      third_party/simple-knn/spatial.cu:16-25)
+ *   segs_decode_forward /    GaussianRenderer::generate_neural_gaussians src/gaussian_renderer.cpp:214-334
+ *   segs_decode_backward     with the module shapes of GaussianModel    src/gaussian_model.cpp:62-98
+ *
+ * Matrices are 16 floats indexed m[4*col+row] exactly as the reference kernels read them
+ * (cuda_rasterizer/auxiliary.h:59-78).  An absent optional input is a null pointer
+ * (the reference passes data_ptr() of a 0-element tensor, src/gaussian_rasterizer.cpp:183-193).
+ */
+#ifndef SEGS_RASTER_H_INCLUDED
+#define SEGS_RASTER_H_INCLUDED
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SEGS_ABI_VERSION 1
+
+/* Status codes. */
+#define SEGS_OK              0
+#define SEGS_ERR_INVALID_ARG 1   /* bad pointer / size / unsupported combination            */
+#define SEGS_ERR_CUDA        2   /* a CUDA runtime call or kernel launch failed              */
+#define SEGS_ERR_ALLOC       3   /* an allocation callback returned NULL                     */
+#define SEGS_ERR_PREFILTERED 4   /* a point was culled although `prefiltered` was set
+                                    (the reference __trap()s, auxiliary.h:158-161)           */
+
+/* Grow-and-return-pointer callback: must return a device pointer to at least `bytes`
+ * bytes (>= 128-byte aligned), valid until the matching backward call has finished.
+ * Mirrors std::function<char*(size_t)> of rasterizer.h:32-34 / resizeFunctional of
+ * src/rasterize_points.cu:28-34. */
+typedef char* (*segs_alloc_fn)(void* user, size_t bytes);
+
+int         segs_version(void);
+const char* segs_last_error(void);
+
+/* ---- forward ------------------------------------------------------------------------ */
+/* Returns the number of rendered Gaussian/tile instances in *num_rendered (the int that
+ * Rasterizer::forward returns).  out_color is [3,H,W] planar, radii is [P] (may be NULL,
+ * as rasterizer.h:53). out_color and radii are fully written for P > 0. */
+int segs_raster_forward(
+    segs_alloc_fn geom_alloc,    void* geom_user,
+    segs_alloc_fn binning_alloc, void* binning_user,
+    segs_alloc_fn image_alloc,   void* image_user,
+    int P, int D, int M,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_color,
+    int* radii,
+    int* num_rendered,
+    void* stream);
+
+/* ---- backward ----------------------------------------------------------------------- */
+/* Gradient outputs are FULLY written (zeros for Gaussians that were not rendered), so the
+ * caller may hand in uninitialised memory.  dL_dconic ([P,2,2]) is optional (NULL ok): the
+ * reference only uses it internally (src/rasterize_points.cu:150,192).  dL_dmean2D is
+ * [P,3] with z = 0 (backward.cu:412).  dL_dsh may be NULL when M == 0. */
+int segs_raster_backward(
+    int P, int D, int M, int R,
+    const float* background,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* campos,
+    float tan_fovx, float tan_fovy,
+    const int* radii,
+    char* geom_buffer,
+    char* binning_buffer,
+    char* image_buffer,
+    const float* dL_dpix,
+    float* dL_dmean2D,
+    float* dL_dconic,
+    float* dL_dopacity,
+    float* dL_dcolor,
+    float* dL_dmean3D,
+    float* dL_dcov3D,
+    float* dL_dsh,
+    float* dL_dscale,
+    float* dL_drot,
+    void* stream);
+
+/* ---- anchor prefilter / frustum mark / debug projection ----------------------------- */
+/* radii[P] is fully written (0 = not visible).  Needs no scratch memory (the reference
+ * allocates — and never uses — full geometry and image buffers here). */
+int segs_visible_filter(
+    int P, int M,
+    int width, int height,
+    const float* means3D,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    int* radii,
+    void* stream);
+
+/* present[P] (1 byte each, C++ bool) = p_view.z > 0.2 (auxiliary.h:155-156). */
+int segs_mark_visible(
+    int P,
+    const float* means3D,
+    const float* viewmatrix,
+    const float* projmatrix,
+    unsigned char* present,
+    void* stream);
+
+/* Debug projection: points_image[P,2], radii[P], out_rgb[P,3] — all DEVICE pointers and
+ * fully written (zeros for culled points; out_rgb is only written by the SH path, as in
+ * the reference, and zero otherwise). */
+int segs_project(
+    int P, int D, int M,
+    int width, int height,
+    const float* means3D,
+    const float* shs,
+    const float* colors_precomp,
+    const float* opacities,
+    const float* scales,
+    float scale_modifier,
+    const float* rotations,
+    const float* cov3D_precomp,
+    const float* viewmatrix,
+    const float* projmatrix,
+    const float* cam_pos,
+    float tan_fovx, float tan_fovy,
+    int prefiltered,
+    float* out_rgb,
+    float* points_image,
+    int* radii,
+    void* stream);
+
+/* ---- anchor-init kNN ---------------------------------------------------------------- */
+/* mean_dists[P] = mean squared distance to the 3 nearest neighbours (self excluded).
+ * scratch grows one opaque device buffer (all temporaries; no cudaMalloc inside). */
+int segs_knn_mean_dist2(
+    int P,
+    const float* points,
+    float* mean_dists,
+    segs_alloc_fn scratch_alloc, void* scratch_user,
+    void* stream);
+
+/* ---- inspection of the opaque buffers (parity tests, debugging) --------------------- */
+/* Returns in *ptr / *bytes the device address and size of a named section of the
+ * buffers produced by segs_raster_forward for the given (P, R, width, height).
+ * Sections: "depths" f32[P], "tiles_touched" u32[P], "rect" u16[P,4] (x0,y0,x1,y1),
+ * "rec" f32[P,12] (x,y,hx,hy | conic.x,conic.y,conic.z,opacity | r,g,b,depth),
+ * "cov3D" f32[6,P] (planes), "depth_order" u32[P], "point_offsets" u32[P] (exclusive, in
+ * depth order), "point_list" u32[R], "tile_ids" u32[R] (sorted), "ranges" u32[T,2],
+ * "final_T" f32[N], "n_contrib" u32[N]. */
+int segs_buffer_section(
+    const char* name,
+    char* geom_buffer, char* binning_buffer, char* image_buffer,
+    int P, int R, int width, int height,
+    void** ptr, size_t* bytes);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SEGS_RASTER_H_INCLUDED */

@@ -1,0 +1,94 @@
+"""ctypes binding of the C-ABI library (include/segs_raster.h).
+
+The library is built in-tree (segs_slam_b200/libsegs_raster.so) by
+``make -C segs_slam_b200/csrc`` / ``__graft_entry__.build()``.  There is no fallback:
+if the shared object is missing, loading raises.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libsegs_raster.so")
+
+ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
+
+_f32p = C.c_void_p  # device pointers travel as plain addresses
+_i32p = C.c_void_p
+
+_PROTOTYPES = {
+    "segs_version": (C.c_int, []),
+    "segs_last_error": (C.c_char_p, []),
+    "segs_raster_forward": (
+        C.c_int,
+        [ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
+         C.c_int, C.c_int, C.c_int,
+         _f32p, C.c_int, C.c_int,
+         _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p,
+         _f32p, _f32p, _f32p,
+         C.c_float, C.c_float, C.c_int,
+         _f32p, _i32p, C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "segs_raster_backward": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_int,
+         _f32p, C.c_int, C.c_int,
+         _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p,
+         C.c_float, C.c_float, _i32p,
+         C.c_void_p, C.c_void_p, C.c_void_p,
+         _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p],
+    ),
+    "segs_visible_filter": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p,
+         C.c_float, C.c_float, C.c_int, _i32p, C.c_void_p],
+    ),
+    "segs_mark_visible": (C.c_int, [C.c_int, _f32p, _f32p, _f32p, C.c_void_p, C.c_void_p]),
+    "segs_project": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+         _f32p, _f32p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, _f32p, _f32p,
+         C.c_float, C.c_float, C.c_int, _f32p, _f32p, _i32p, C.c_void_p],
+    ),
+    "segs_knn_mean_dist2": (C.c_int, [C.c_int, _f32p, _f32p, ALLOC_FN, C.c_void_p, C.c_void_p]),
+    "segs_buffer_section": (
+        C.c_int,
+        [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,
+         C.POINTER(C.c_void_p), C.POINTER(C.c_size_t)],
+    ),
+}
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load libsegs_raster.so (once).  Raises if the CUDA extension has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} is missing: build it with `make -C segs_slam_b200/csrc` "
+                "(or __graft_entry__.build()). There is no CPU fallback."
+            )
+        lib = C.CDLL(LIB_PATH)
+        for name, (res, args) in _PROTOTYPES.items():
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def exported_symbols() -> list[str]:
+    return sorted(_PROTOTYPES)
+
+
+class SegsError(RuntimeError):
+    pass
+
+
+def check(status: int) -> None:
+    if status != 0:
+        msg = load().segs_last_error()
+        raise SegsError(f"segs status {status}: {msg.decode() if msg else ''}")

@@ -1,0 +1,313 @@
+// C-ABI entry points (include/segs_raster.h) and the opaque-buffer layout.
+//
+// Pipeline driver replacing CudaRasterizer::Rasterizer::{forward,backward,visible_filter,
+// markVisible,project2_image} (cuda_rasterizer/rasterizer_impl.cu:141-153,198-336,339-393,
+// 397-490,494-585).  Unlike the reference, every launch goes to the caller's stream, every
+// CUDA call is checked, and nothing is allocated here: all device memory comes from the
+// three allocation callbacks.
+#include <cstdarg>
+#include <cstring>
+#include <string>
+#include "common.cuh"
+
+namespace segs {
+
+// ---- error plumbing -----------------------------------------------------------------
+static thread_local char g_last_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_last_error, sizeof(g_last_error), fmt, ap);
+    va_end(ap);
+}
+
+// ---- layouts --------------------------------------------------------------------------
+GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
+    Carver c(base);
+    GeomState g;
+    g.depths = c.take<float>(P);
+    g.tiles_touched = c.take<uint32_t>(P);
+    g.rect = c.take<ushort4>(P);
+    g.rec = c.take<float4>(3 * P);
+    g.cov3D = c.take<float>(6 * P);
+    g.acc = c.take<float4>(3 * P);
+    g.clamped = c.take<uint8_t>(3 * P);
+    g.key_a = c.take<uint32_t>(P);
+    g.key_b = c.take<uint32_t>(P);
+    g.val_a = c.take<uint32_t>(P);
+    g.val_b = c.take<uint32_t>(P);
+    g.offsets = c.take<uint32_t>(P);
+    g.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(P));
+    g.global_hist = c.take<uint32_t>(RADIX_BINS);
+    g.scan_partials = c.take<uint32_t>(P / 2048 + 2);
+    g.counters = c.take<uint32_t>(8);
+    if (bytes) *bytes = c.used(base) + 128;
+    return g;
+}
+
+BinningState BinningState::carve(char* base, size_t R, size_t* bytes) {
+    Carver c(base);
+    BinningState b;
+    b.tile_a = c.take<uint32_t>(R);
+    b.tile_b = c.take<uint32_t>(R);
+    b.idx_a = c.take<uint32_t>(R);
+    b.idx_b = c.take<uint32_t>(R);
+    b.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(R));
+    b.global_hist = c.take<uint32_t>(RADIX_BINS);
+    if (bytes) *bytes = c.used(base) + 128;
+    return b;
+}
+
+ImageState ImageState::carve(char* base, size_t N, size_t T, size_t* bytes) {
+    Carver c(base);
+    ImageState s;
+    s.final_T = c.take<float>(N);
+    s.n_contrib = c.take<uint32_t>(N);
+    s.ranges = c.take<uint2>(T);
+    if (bytes) *bytes = c.used(base) + 128;
+    return s;
+}
+
+static ViewParams make_view(int width, int height, float tan_fovx, float tan_fovy, float scale_modifier) {
+    ViewParams vp;
+    vp.W = width;
+    vp.H = height;
+    vp.grid_x = (width + TILE_X - 1) / TILE_X;
+    vp.grid_y = (height + TILE_Y - 1) / TILE_Y;
+    vp.tan_fovx = tan_fovx;
+    vp.tan_fovy = tan_fovy;
+    // rasterizer_impl.cu:221-222 (float arithmetic on the host)
+    vp.focal_y = height / (2.0f * tan_fovy);
+    vp.focal_x = width / (2.0f * tan_fovx);
+    vp.scale_modifier = scale_modifier;
+    return vp;
+}
+
+// One pinned word per host thread for the num_rendered / error-flag readback.
+static uint32_t* pinned_words() {
+    static thread_local uint32_t* p = nullptr;
+    if (!p) {
+        if (cudaHostAlloc(reinterpret_cast<void**>(&p), 8 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
+            p = nullptr;
+        }
+    }
+    return p;
+}
+
+}  // namespace segs
+
+using namespace segs;
+
+extern "C" {
+
+int segs_version(void) { return SEGS_ABI_VERSION; }
+const char* segs_last_error(void) { return g_last_error; }
+
+int segs_raster_forward(
+    segs_alloc_fn geom_alloc, void* geom_user,
+    segs_alloc_fn binning_alloc, void* binning_user,
+    segs_alloc_fn image_alloc, void* image_user,
+    int P, int D, int M,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* opacities, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_color, int* radii, int* num_rendered, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (num_rendered) *num_rendered = 0;
+    if (!geom_alloc || !binning_alloc || !image_alloc) { set_error("allocation callbacks must not be NULL"); return SEGS_ERR_INVALID_ARG; }
+    if (P < 0 || width <= 0 || height <= 0) { set_error("invalid sizes P=%d W=%d H=%d", P, width, height); return SEGS_ERR_INVALID_ARG; }
+    if (!out_color || !background || !viewmatrix || !projmatrix) { set_error("NULL required pointer"); return SEGS_ERR_INVALID_ARG; }
+    const size_t N = size_t(width) * height;
+    if (P == 0) {
+        // RasterizeGaussiansCUDA (rasterize_points.cu:81): nothing runs, the image stays zero
+        SEGS_CUDA_CHECK(cudaMemsetAsync(out_color, 0, NUM_CH * N * sizeof(float), stream));
+        return SEGS_OK;
+    }
+    if (!means3D || !opacities) { set_error("means3D/opacities must not be NULL"); return SEGS_ERR_INVALID_ARG; }
+    if (!colors_precomp && !shs) {
+        // rasterizer_impl.cu:241-244 analogue: no colour source at all
+        set_error("Please provide exactly one of either SHs or precomputed colors!");
+        return SEGS_ERR_INVALID_ARG;
+    }
+    if (!cov3D_precomp && (!scales || !rotations)) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return SEGS_ERR_INVALID_ARG;
+    }
+    if (!colors_precomp && (M <= 0 || (D + 1) * (D + 1) > M || D > 3 || D < 0)) {
+        set_error("SH degree %d needs %d coefficients, got M=%d", D, (D + 1) * (D + 1), M);
+        return SEGS_ERR_INVALID_ARG;
+    }
+
+    const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
+    const size_t T = size_t(vp.grid_x) * vp.grid_y;
+    if (vp.grid_x > 65535 || vp.grid_y > 65535) { set_error("image too large"); return SEGS_ERR_INVALID_ARG; }
+
+    size_t geom_bytes = 0, img_bytes = 0, bin_bytes = 0;
+    GeomState::carve(nullptr, P, &geom_bytes);
+    char* geom_ptr = geom_alloc(geom_user, geom_bytes);
+    if (!geom_ptr) { set_error("geometry buffer allocation of %zu bytes failed", geom_bytes); return SEGS_ERR_ALLOC; }
+    GeomState g = GeomState::carve(geom_ptr, P, nullptr);
+
+    ImageState::carve(nullptr, N, T, &img_bytes);
+    char* img_ptr = image_alloc(image_user, img_bytes);
+    if (!img_ptr) { set_error("image buffer allocation of %zu bytes failed", img_bytes); return SEGS_ERR_ALLOC; }
+    ImageState img = ImageState::carve(img_ptr, N, T, nullptr);
+
+    uint32_t* host_words = pinned_words();
+    if (!host_words) { set_error("cudaHostAlloc for the readback word failed"); return SEGS_ERR_CUDA; }
+
+    SEGS_CUDA_CHECK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), stream));
+    int rc;
+    if ((rc = launch_preprocess(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
+                                colors_precomp, viewmatrix, projmatrix, cam_pos, vp, prefiltered != 0,
+                                radii, g, stream))) return rc;
+    if ((rc = launch_depth_order(P, g, stream))) return rc;
+
+    // num_rendered sizes the binning buffer, so it has to reach the host here
+    // (rasterizer_impl.cu:279-285).
+    SEGS_CUDA_CHECK(cudaMemcpyAsync(host_words, g.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    SEGS_CUDA_CHECK(cudaStreamSynchronize(stream));
+    const uint32_t R = host_words[0];
+    if (host_words[1] != 0) {
+        set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
+        return SEGS_ERR_PREFILTERED;
+    }
+    if (R > 0x7FFFFFFFu) { set_error("num_rendered %u overflows int", R); return SEGS_ERR_INVALID_ARG; }
+
+    BinningState::carve(nullptr, R, &bin_bytes);
+    char* bin_ptr = binning_alloc(binning_user, bin_bytes);
+    if (!bin_ptr) { set_error("binning buffer allocation of %zu bytes failed", bin_bytes); return SEGS_ERR_ALLOC; }
+    BinningState b = BinningState::carve(bin_ptr, R, nullptr);
+
+    if ((rc = launch_binning(P, (int)R, vp, g, b, img, stream))) return rc;
+    if ((rc = launch_blend_forward(vp, g, b, img, background, out_color, stream))) return rc;
+    if (num_rendered) *num_rendered = (int)R;
+    return SEGS_OK;
+}
+
+int segs_raster_backward(
+    int P, int D, int M, int R,
+    const float* background, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp,
+    const float* scales, float scale_modifier, const float* rotations,
+    const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+    const float* campos, float tan_fovx, float tan_fovy, const int* radii,
+    char* geom_buffer, char* binning_buffer, char* image_buffer,
+    const float* dL_dpix, float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+    float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D, float* dL_dsh,
+    float* dL_dscale, float* dL_drot, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    (void)colors_precomp;
+    if (P == 0) return SEGS_OK;
+    if (P < 0 || R < 0 || width <= 0 || height <= 0) { set_error("invalid sizes"); return SEGS_ERR_INVALID_ARG; }
+    if (!geom_buffer || !image_buffer || (R > 0 && !binning_buffer)) { set_error("NULL state buffer"); return SEGS_ERR_INVALID_ARG; }
+    if (!dL_dpix || !dL_dmean2D || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot) {
+        set_error("NULL gradient output"); return SEGS_ERR_INVALID_ARG;
+    }
+    if (shs && M > 0 && !dL_dsh) { set_error("dL_dsh must not be NULL on the SH path"); return SEGS_ERR_INVALID_ARG; }
+    const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
+    const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
+    GeomState g = GeomState::carve(geom_buffer, P, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, nullptr);
+    ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
+    int rc;
+    if (R > 0)
+        if ((rc = launch_blend_backward(vp, g, b, img, background, dL_dpix, stream))) return rc;
+    if ((rc = launch_preprocess_backward(P, D, M, means3D, scales, rotations, shs, cov3D_precomp, viewmatrix,
+                                         projmatrix, campos, vp, radii, g, dL_dmean2D, dL_dconic, dL_dopacity,
+                                         dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream)))
+        return rc;
+    return SEGS_OK;
+}
+
+int segs_visible_filter(
+    int P, int M, int width, int height,
+    const float* means3D, const float* scales, float scale_modifier,
+    const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix,
+    float tan_fovx, float tan_fovy, int prefiltered, int* radii, void* stream_)
+{
+    (void)M; (void)prefiltered;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P == 0) return SEGS_OK;
+    if (P < 0 || width <= 0 || height <= 0 || !means3D || !radii || !viewmatrix || !projmatrix) {
+        set_error("invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    if (!cov3D_precomp && (!scales || !rotations)) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return SEGS_ERR_INVALID_ARG;
+    }
+    const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
+    return launch_filter(P, means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix, vp,
+                         false, radii, nullptr, stream);
+}
+
+int segs_mark_visible(int P, const float* means3D, const float* viewmatrix, const float* projmatrix,
+                      unsigned char* present, void* stream_)
+{
+    (void)projmatrix;   // only the view-space depth test is live (auxiliary.h:155-156)
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P == 0) return SEGS_OK;
+    if (P < 0 || !means3D || !viewmatrix || !present) { set_error("invalid argument"); return SEGS_ERR_INVALID_ARG; }
+    return launch_mark_visible(P, means3D, viewmatrix, present, stream);
+}
+
+int segs_project(
+    int P, int D, int M, int width, int height,
+    const float* means3D, const float* shs, const float* colors_precomp, const float* opacities,
+    const float* scales, float scale_modifier, const float* rotations, const float* cov3D_precomp,
+    const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+    float tan_fovx, float tan_fovy, int prefiltered,
+    float* out_rgb, float* points_image, int* radii, void* stream_)
+{
+    (void)prefiltered;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P == 0) return SEGS_OK;
+    if (P < 0 || width <= 0 || height <= 0 || !means3D || !radii || !out_rgb || !points_image || !viewmatrix || !projmatrix) {
+        set_error("invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    if (!colors_precomp && !shs) { set_error("Please provide exactly one of either SHs or precomputed colors!"); return SEGS_ERR_INVALID_ARG; }
+    if (!cov3D_precomp && (!scales || !rotations)) {
+        set_error("Please provide exactly one of either scale/rotation pair or precomputed 3D covariance!");
+        return SEGS_ERR_INVALID_ARG;
+    }
+    const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
+    return launch_project(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
+                          viewmatrix, projmatrix, cam_pos, vp, false, out_rgb, points_image, radii, stream);
+}
+
+int segs_buffer_section(const char* name, char* geom_buffer, char* binning_buffer, char* image_buffer,
+                        int P, int R, int width, int height, void** ptr, size_t* bytes)
+{
+    if (!name || !ptr || !bytes) { set_error("invalid argument"); return SEGS_ERR_INVALID_ARG; }
+    const ViewParams vp = make_view(width, height, 1.f, 1.f, 1.f);
+    const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
+    GeomState g = GeomState::carve(geom_buffer, P, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, nullptr);
+    ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
+    const int passes = num_tile_passes((uint32_t)T);
+    const std::string n(name);
+    auto out = [&](void* p, size_t sz) { *ptr = p; *bytes = sz; return SEGS_OK; };
+    if (n == "depths") return out(g.depths, sizeof(float) * P);
+    if (n == "tiles_touched") return out(g.tiles_touched, sizeof(uint32_t) * P);
+    if (n == "rect") return out(g.rect, sizeof(ushort4) * P);
+    if (n == "rec") return out(g.rec, sizeof(float4) * 3 * P);
+    if (n == "cov3D") return out(g.cov3D, sizeof(float) * 6 * P);
+    if (n == "depth_order") return out(g.val_a, sizeof(uint32_t) * P);
+    if (n == "point_offsets") return out(g.offsets, sizeof(uint32_t) * P);
+    if (n == "point_list") return out((passes & 1) ? b.idx_b : b.idx_a, sizeof(uint32_t) * R);
+    if (n == "tile_ids") return out((passes & 1) ? b.tile_b : b.tile_a, sizeof(uint32_t) * R);
+    if (n == "ranges") return out(img.ranges, sizeof(uint2) * T);
+    if (n == "final_T") return out(img.final_T, sizeof(float) * N);
+    if (n == "n_contrib") return out(img.n_contrib, sizeof(uint32_t) * N);
+    set_error("unknown section '%s'", name);
+    return SEGS_ERR_INVALID_ARG;
+}
+
+}  // extern "C"

@@ -1,0 +1,168 @@
+// Shared definitions for the sm_100a rasterizer kernels: opaque-buffer layout, error
+// plumbing, small device helpers.  Private to the library (nothing here is ABI).
+#pragma once
+#include <cstddef>
+#include <cstdint>
+#include <cstdio>
+#include <cuda_runtime.h>
+#include "../../include/segs_raster.h"
+
+namespace segs {
+
+constexpr int TILE_X = 16;              // reference config.h:16-17 (BLOCK_X/BLOCK_Y)
+constexpr int TILE_Y = 16;
+constexpr int TILE_PIX = TILE_X * TILE_Y;
+constexpr int NUM_CH = 3;               // reference config.h:15
+constexpr int SM_COUNT = 148;           // B200
+
+// ---- error plumbing -----------------------------------------------------------------
+void set_error(const char* fmt, ...);
+#define SEGS_CUDA_CHECK(expr)                                                            \
+    do {                                                                                 \
+        cudaError_t _e = (expr);                                                         \
+        if (_e != cudaSuccess) {                                                         \
+            ::segs::set_error("%s failed at %s:%d: %s", #expr, __FILE__, __LINE__,       \
+                              cudaGetErrorString(_e));                                   \
+            return SEGS_ERR_CUDA;                                                        \
+        }                                                                                \
+    } while (0)
+#define SEGS_LAUNCH_CHECK() SEGS_CUDA_CHECK(cudaGetLastError())
+
+// ---- opaque buffer layout -----------------------------------------------------------
+// A bump allocator over the caller-owned byte buffers, 128-byte aligned sections
+// (same idea as the reference's obtain()/required(), rasterizer_impl.h:22-72, but the
+// contents are this library's own SoA layout).
+struct Carver {
+    char* p;
+    explicit Carver(char* base) : p(base) {}
+    template <typename T>
+    T* take(size_t count) {
+        uintptr_t a = (reinterpret_cast<uintptr_t>(p) + 127) & ~uintptr_t(127);
+        T* r = reinterpret_cast<T*>(a);
+        p = reinterpret_cast<char*>(r + count);
+        return r;
+    }
+    size_t used(char* base) const { return size_t(p - base); }
+};
+
+constexpr int RADIX_BITS = 8;
+constexpr int RADIX_BINS = 1 << RADIX_BITS;
+constexpr int SORT_THREADS = 256;
+constexpr int SORT_ITEMS = 16;                       // items per thread per block
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 elements per block
+
+inline int sort_blocks(size_t n) { return int((n + SORT_TILE - 1) / SORT_TILE); }
+
+// Per-Gaussian render record, 48 bytes (three float4):
+//   rec[3i+0] = { x, y, hx, hy }            2D mean (pixels), conservative half extents
+//   rec[3i+1] = { conic.x, conic.y, conic.z, opacity }
+//   rec[3i+2] = { r, g, b, depth }
+// Per-Gaussian gradient accumulator written by the blend backward, 48 bytes:
+//   acc[3i+0] = { dL_dmean2D.x, dL_dmean2D.y, dL_dconic.x, dL_dconic.y }
+//   acc[3i+1] = { dL_dconic.w(=zz), dL_dopacity, dL_dcolor.r, dL_dcolor.g }
+//   acc[3i+2] = { dL_dcolor.b, 0, 0, 0 }
+struct GeomState {
+    float*    depths;         // [P]
+    uint32_t* tiles_touched;  // [P]
+    ushort4*  rect;           // [P] x0,y0,x1,y1 in tiles
+    float4*   rec;            // [3P]
+    float*    cov3D;          // [6][P] planes
+    float4*   acc;            // [3P]
+    uint8_t*  clamped;        // [3P] (SH path)
+    uint32_t* key_a;          // [P] depth-sort ping
+    uint32_t* key_b;          // [P] depth-sort pong
+    uint32_t* val_a;          // [P]
+    uint32_t* val_b;          // [P]  -> depth order after 4 passes lives in val_a
+    uint32_t* offsets;        // [P] exclusive scan of tiles_touched in depth order
+    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(P)]
+    uint32_t* global_hist;    // [RADIX_BINS]
+    uint32_t* scan_partials;  // [scan blocks + 1]
+    uint32_t* counters;       // [8]: 0 = num_rendered, 1 = error flag
+    static GeomState carve(char* base, size_t P, size_t* bytes);
+};
+
+struct BinningState {
+    uint32_t* tile_a;         // [R]
+    uint32_t* tile_b;         // [R]
+    uint32_t* idx_a;          // [R]
+    uint32_t* idx_b;          // [R]
+    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(R)]
+    uint32_t* global_hist;    // [RADIX_BINS]
+    static BinningState carve(char* base, size_t R, size_t* bytes);
+};
+
+struct ImageState {
+    float*    final_T;        // [N]
+    uint32_t* n_contrib;      // [N]
+    uint2*    ranges;         // [T]
+    static ImageState carve(char* base, size_t N, size_t T, size_t* bytes);
+};
+
+inline int num_tile_passes(uint32_t num_tiles) {
+    // number of 8-bit digits needed to cover tile ids 0..num_tiles-1
+    int passes = 1;
+    while (passes < 4 && (uint64_t(1) << (RADIX_BITS * passes)) < num_tiles) ++passes;
+    return passes;
+}
+
+// ---- kernel launchers (one per translation unit) ------------------------------------
+struct ViewParams {
+    int W, H;
+    int grid_x, grid_y;
+    float tan_fovx, tan_fovy;
+    float focal_x, focal_y;
+    float scale_modifier;
+};
+
+int launch_preprocess(int P, int D, int M, const float* means3D, const float* scales,
+                      const float* rotations, const float* opacities, const float* shs,
+                      const float* cov3D_precomp, const float* colors_precomp,
+                      const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                      const ViewParams& vp, bool prefiltered, int* radii, GeomState& g,
+                      cudaStream_t stream);
+
+int launch_filter(int P, const float* means3D, const float* scales, const float* rotations,
+                  const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,
+                  const ViewParams& vp, bool prefiltered, int* radii, uint32_t* err_flag,
+                  cudaStream_t stream);
+
+int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
+                        unsigned char* present, cudaStream_t stream);
+
+int launch_project(int P, int D, int M, const float* means3D, const float* scales,
+                   const float* rotations, const float* opacities, const float* shs,
+                   const float* cov3D_precomp, const float* colors_precomp,
+                   const float* viewmatrix, const float* projmatrix, const float* cam_pos,
+                   const ViewParams& vp, bool prefiltered, float* out_rgb, float* points_image,
+                   int* radii, cudaStream_t stream);
+
+// depth ordering of Gaussians + exclusive offsets + total (counters[0])
+int launch_depth_order(int P, GeomState& g, cudaStream_t stream);
+// instance emission, tile radix passes, ranges
+int launch_binning(int P, int R, const ViewParams& vp, GeomState& g, BinningState& b,
+                   ImageState& img, cudaStream_t stream);
+
+int launch_blend_forward(const ViewParams& vp, const GeomState& g, const BinningState& b,
+                         ImageState& img, const float* background, float* out_color,
+                         cudaStream_t stream);
+
+int launch_blend_backward(const ViewParams& vp, const GeomState& g, const BinningState& b,
+                          const ImageState& img, const float* background,
+                          const float* dL_dpix, cudaStream_t stream);
+
+int launch_preprocess_backward(int P, int D, int M, const float* means3D, const float* scales,
+                               const float* rotations, const float* shs,
+                               const float* cov3D_precomp, const float* viewmatrix,
+                               const float* projmatrix, const float* campos,
+                               const ViewParams& vp, const int* radii, GeomState& g,
+                               float* dL_dmean2D, float* dL_dconic, float* dL_dopacity,
+                               float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
+                               float* dL_dsh, float* dL_dscale, float* dL_drot,
+                               cudaStream_t stream);
+
+// generic device primitives (binning.cu)
+int radix_pass(const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in,
+               uint32_t* val_out, size_t n, int shift, uint32_t* block_hist,
+               uint32_t* global_hist, cudaStream_t stream);
+
+}  // namespace segs

@@ -1,0 +1,315 @@
+// Anchor-init kNN for sm_100a: mean squared distance to the three
+// nearest neighbours.  Replaces SimpleKNN::knn / distCUDA2 of the reference
+// (third_party/simple-knn/simple_knn.cu:45-221, spatial.cu:16-25).
+//
+// Same exact algorithm family as the reference (Morton order, boxes of 1024 points with
+// AABBs, conservative box pruning), re-laid out for B200:
+//  * no host round trips: the scene bounding box stays on the device (the reference does two
+//    blocking 12-byte D2H copies), no cudaMalloc/cudaFree per call (scratch comes from the
+//    caller's allocation callback), everything on the caller's stream;
+//  * points are gathered ONCE into Morton order as float4 (xyz + original index), so the
+//    search streams contiguous 16-byte records instead of chasing points[indices[i]];
+//  * one CTA per query box: candidate boxes are staged into shared memory with coalesced
+//    loads and scanned with broadcast reads by all of the CTA's queries; a CTA-level
+//    box-vs-box bound skips whole boxes before the per-query box-vs-point bound
+//    (simple_knn.cu:121-132) is even evaluated.
+// The result is the exact 3-NN, and each squared distance is evaluated with the same
+// operations as the reference (d = other - query; fma(dz,dz, fma(dx,dx, dy*dy))), so the
+// output is bit-identical whenever the reference's own pruning is exact.
+#include <cfloat>
+#include "common.cuh"
+
+namespace segs {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int BOX = 1024;          // simple_knn.cu:12
+constexpr int KNN_THREADS = 256;   // queries are processed 256 at a time, 4 rounds per box
+
+struct Box { float3 lo, hi; };
+
+__device__ __forceinline__ uint32_t prep_morton(uint32_t x) {   // simple_knn.cu:45-52
+    x = (x | (x << 16)) & 0x030000FF;
+    x = (x | (x << 8)) & 0x0300F00F;
+    x = (x | (x << 4)) & 0x030C30C3;
+    x = (x | (x << 2)) & 0x09249249;
+    return x;
+}
+
+// ---- K1: bounding box, init {0,0,0} for both min and max (simple_knn.cu:192-199) ---------
+__global__ void __launch_bounds__(256)
+bbox_partial_kernel(int P, const float* __restrict__ pts, float* __restrict__ partial /*[nb][6]*/)
+{
+    __shared__ float s[8][6];
+    float lo[3] = {0.f, 0.f, 0.f}, hi[3] = {0.f, 0.f, 0.f};
+    for (size_t i = size_t(blockIdx.x) * 256 + threadIdx.x; i < (size_t)P; i += size_t(gridDim.x) * 256) {
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const float v = __ldg(pts + 3 * i + k);
+            lo[k] = fminf(lo[k], v);
+            hi[k] = fmaxf(hi[k], v);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { s[warp][k] = lo[k]; s[warp][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x < 6) {
+        float v = s[0][threadIdx.x];
+        for (int w = 1; w < 8; ++w) v = (threadIdx.x < 3) ? fminf(v, s[w][threadIdx.x]) : fmaxf(v, s[w][threadIdx.x]);
+        partial[blockIdx.x * 6 + threadIdx.x] = v;
+    }
+}
+
+// ---- K2: Morton codes (simple_knn.cu:54-70); every CTA folds the few bbox partials itself ----
+__global__ void __launch_bounds__(256)
+morton_kernel(int P, const float* __restrict__ pts, const float* __restrict__ partial, int npartial,
+              uint32_t* __restrict__ codes, uint32_t* __restrict__ ids)
+{
+    __shared__ float s_box[6];
+    if (threadIdx.x < 6) {
+        float v = partial[threadIdx.x];
+        for (int b = 1; b < npartial; ++b)
+            v = (threadIdx.x < 3) ? fminf(v, partial[b * 6 + threadIdx.x]) : fmaxf(v, partial[b * 6 + threadIdx.x]);
+        s_box[threadIdx.x] = v;
+    }
+    __syncthreads();
+    const size_t i = size_t(blockIdx.x) * 256 + threadIdx.x;
+    if (i >= (size_t)P) return;
+    uint32_t m[3];
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const float c = __ldg(pts + 3 * i + k);
+        m[k] = prep_morton((uint32_t)(((c - s_box[k]) / (s_box[3 + k] - s_box[k])) * ((1 << 10) - 1)));
+    }
+    codes[i] = m[0] | (m[1] << 1) | (m[2] << 2);
+    ids[i] = (uint32_t)i;
+}
+
+// ---- K4: gather into Morton order + per-box AABB (simple_knn.cu:78-119) --------------------
+__global__ void __launch_bounds__(KNN_THREADS)
+gather_box_kernel(int P, const float* __restrict__ pts, const uint32_t* __restrict__ order,
+                  float4* __restrict__ sorted, Box* __restrict__ boxes)
+{
+    __shared__ float s[KNN_THREADS / 32][6];
+    float lo[3] = {FLT_MAX, FLT_MAX, FLT_MAX}, hi[3] = {-FLT_MAX, -FLT_MAX, -FLT_MAX};
+    for (int r = 0; r < BOX / KNN_THREADS; ++r) {
+        const size_t k = size_t(blockIdx.x) * BOX + r * KNN_THREADS + threadIdx.x;
+        if (k < (size_t)P) {
+            const uint32_t id = __ldg(order + k);
+            const float x = __ldg(pts + 3 * size_t(id)), y = __ldg(pts + 3 * size_t(id) + 1), z = __ldg(pts + 3 * size_t(id) + 2);
+            sorted[k] = make_float4(x, y, z, __uint_as_float(id));
+            lo[0] = fminf(lo[0], x); lo[1] = fminf(lo[1], y); lo[2] = fminf(lo[2], z);
+            hi[0] = fmaxf(hi[0], x); hi[1] = fmaxf(hi[1], y); hi[2] = fmaxf(hi[2], z);
+        }
+    }
+#pragma unroll
+    for (int k = 0; k < 3; ++k)
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) {
+            lo[k] = fminf(lo[k], __shfl_xor_sync(FULL, lo[k], o));
+            hi[k] = fmaxf(hi[k], __shfl_xor_sync(FULL, hi[k], o));
+        }
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (lane == 0)
+        for (int k = 0; k < 3; ++k) { s[warp][k] = lo[k]; s[warp][3 + k] = hi[k]; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        Box b;
+        float v[6];
+        for (int k = 0; k < 6; ++k) {
+            v[k] = s[0][k];
+            for (int w = 1; w < KNN_THREADS / 32; ++w) v[k] = (k < 3) ? fminf(v[k], s[w][k]) : fmaxf(v[k], s[w][k]);
+        }
+        b.lo = make_float3(v[0], v[1], v[2]);
+        b.hi = make_float3(v[3], v[4], v[5]);
+        boxes[blockIdx.x] = b;
+    }
+}
+
+// ---- K5: search --------------------------------------------------------------------------
+__device__ __forceinline__ float dist_box_point(const Box& b, float3 p) {   // simple_knn.cu:121-132
+    float dx = 0.f, dy = 0.f, dz = 0.f;
+    if (p.x < b.lo.x || p.x > b.hi.x) dx = fminf(fabsf(p.x - b.lo.x), fabsf(p.x - b.hi.x));
+    if (p.y < b.lo.y || p.y > b.hi.y) dy = fminf(fabsf(p.y - b.lo.y), fabsf(p.y - b.hi.y));
+    if (p.z < b.lo.z || p.z > b.hi.z) dz = fminf(fabsf(p.z - b.lo.z), fabsf(p.z - b.hi.z));
+    return dx * dx + dy * dy + dz * dz;
+}
+// lower bound of the distance between any point of box a and any point of box b
+__device__ __forceinline__ float dist_box_box(const Box& a, const Box& b) {
+    const float gx = fmaxf(0.f, fmaxf(a.lo.x - b.hi.x, b.lo.x - a.hi.x));
+    const float gy = fmaxf(0.f, fmaxf(a.lo.y - b.hi.y, b.lo.y - a.hi.y));
+    const float gz = fmaxf(0.f, fmaxf(a.lo.z - b.hi.z, b.lo.z - a.hi.z));
+    return (gx * gx + gy * gy + gz * gz) * 0.99999f;   // shaved: must stay a lower bound under rounding
+}
+__device__ __forceinline__ void update3(float3 q, float x, float y, float z, float (&best)[3]) {
+    // simple_knn.cu:134-149, d = other - query, nvcc contraction of dx*dx + dy*dy + dz*dz
+    const float dx = __fsub_rn(x, q.x), dy = __fsub_rn(y, q.y), dz = __fsub_rn(z, q.z);
+    float dist = __fmaf_rn(dz, dz, __fmaf_rn(dx, dx, __fmul_rn(dy, dy)));
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
+}
+
+constexpr int QPT = BOX / KNN_THREADS;   // queries per thread
+
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_search_kernel(int P, const float4* __restrict__ sorted, const Box* __restrict__ boxes, int nboxes,
+                  float* __restrict__ mean_dists)
+{
+    __shared__ float4 s_pts[BOX];
+    __shared__ float s_red[KNN_THREADS / 32];
+    __shared__ float s_bound;
+    const int qb = blockIdx.x;
+    const size_t q0 = size_t(qb) * BOX;
+    const int nq = (int)min(size_t(BOX), size_t(P) - q0);
+
+    float3 q[QPT];
+    float best[QPT][3];
+    float reject[QPT];
+    uint32_t qid[QPT];
+    bool valid[QPT];
+
+    // own box -> smem (also the first box to scan)
+    for (int i = threadIdx.x; i < BOX; i += KNN_THREADS)
+        if (i < nq) s_pts[i] = __ldg(sorted + q0 + i);
+    __syncthreads();
+
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        const int li = r * KNN_THREADS + threadIdx.x;
+        valid[r] = li < nq;
+        best[r][0] = best[r][1] = best[r][2] = FLT_MAX;
+        reject[r] = FLT_MAX;
+        qid[r] = 0;
+        q[r] = make_float3(0.f, 0.f, 0.f);
+        if (valid[r]) {
+            const float4 me = s_pts[li];
+            q[r] = make_float3(me.x, me.y, me.z);
+            qid[r] = __float_as_uint(me.w);
+            // seed from the +-3 Morton neighbours (simple_knn.cu:157-163); they may live in
+            // the adjacent boxes
+            const long long gi = (long long)q0 + li;
+            for (long long i = max(0LL, gi - 3); i <= min((long long)P - 1, gi + 3); ++i) {
+                if (i == gi) continue;
+                const float4 o = (i >= (long long)q0 && i < (long long)q0 + nq) ? s_pts[i - q0] : __ldg(sorted + i);
+                update3(q[r], o.x, o.y, o.z, best[r]);
+            }
+            reject[r] = best[r][2];
+            best[r][0] = best[r][1] = best[r][2] = FLT_MAX;
+        }
+    }
+
+    // scan own box
+#pragma unroll
+    for (int r = 0; r < QPT; ++r) {
+        if (!valid[r]) continue;
+        const int li = r * KNN_THREADS + threadIdx.x;
+        for (int i = 0; i < nq; ++i) {
+            if (i == li) continue;
+            const float4 o = s_pts[i];
+            update3(q[r], o.x, o.y, o.z, best[r]);
+        }
+    }
+
+    // CTA-wide bound: no query of this box needs anything farther than this
+    float bound = 0.f;
+#pragma unroll
+    for (int r = 0; r < QPT; ++r)
+        if (valid[r]) bound = fmaxf(bound, fminf(reject[r], best[r][2]));
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(FULL, bound, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        float b = s_red[0];
+        for (int w = 1; w < KNN_THREADS / 32; ++w) b = fmaxf(b, s_red[w]);
+        s_bound = b;
+    }
+    __syncthreads();
+    const float cta_bound = s_bound;
+    const Box mybox = boxes[qb];
+
+    for (int b = 0; b < nboxes; ++b) {
+        if (b == qb) continue;
+        const Box box = boxes[b];
+        if (dist_box_box(mybox, box) > cta_bound) continue;   // CTA-uniform
+        const size_t b0 = size_t(b) * BOX;
+        const int nb = (int)min(size_t(BOX), size_t(P) - b0);
+        __syncthreads();
+        for (int i = threadIdx.x; i < nb; i += KNN_THREADS) s_pts[i] = __ldg(sorted + b0 + i);
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < QPT; ++r) {
+            if (!valid[r]) continue;
+            const float d = dist_box_point(box, q[r]);
+            if (d > reject[r] || d > best[r][2]) continue;      // simple_knn.cu:172-174
+            for (int i = 0; i < nb; ++i) {
+                const float4 o = s_pts[i];
+                update3(q[r], o.x, o.y, o.z, best[r]);
+            }
+        }
+    }
+
+#pragma unroll
+    for (int r = 0; r < QPT; ++r)
+        if (valid[r])
+            mean_dists[qid[r]] = __fdiv_rn(__fadd_rn(__fadd_rn(best[r][0], best[r][1]), best[r][2]), 3.0f);
+}
+
+}  // namespace
+}  // namespace segs
+
+using namespace segs;
+
+extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists,
+                                   segs_alloc_fn scratch_alloc, void* scratch_user, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (P == 0) return SEGS_OK;
+    if (P < 0 || !points || !mean_dists || !scratch_alloc) { set_error("invalid argument"); return SEGS_ERR_INVALID_ARG; }
+    const int nboxes = (P + BOX - 1) / BOX;
+    const int npartial = min(SM_COUNT * 2, (P + 255) / 256);
+    // scratch layout
+    Carver probe(nullptr);
+    auto carve = [&](Carver& c, uint32_t*& ka, uint32_t*& kb, uint32_t*& va, uint32_t*& vb, uint32_t*& bh,
+                     uint32_t*& gh, float*& partial, float4*& sorted, Box*& boxes) {
+        ka = c.take<uint32_t>(P); kb = c.take<uint32_t>(P);
+        va = c.take<uint32_t>(P); vb = c.take<uint32_t>(P);
+        bh = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(P));
+        gh = c.take<uint32_t>(RADIX_BINS);
+        partial = c.take<float>(size_t(npartial) * 6);
+        sorted = c.take<float4>(P);
+        boxes = c.take<Box>(nboxes);
+    };
+    uint32_t *ka, *kb, *va, *vb, *bh, *gh; float* partial; float4* sorted; Box* boxes;
+    carve(probe, ka, kb, va, vb, bh, gh, partial, sorted, boxes);
+    const size_t bytes = probe.used(nullptr) + 128;
+    char* base = scratch_alloc(scratch_user, bytes);
+    if (!base) { set_error("kNN scratch allocation of %zu bytes failed", bytes); return SEGS_ERR_ALLOC; }
+    Carver real(base);
+    carve(real, ka, kb, va, vb, bh, gh, partial, sorted, boxes);
+
+    bbox_partial_kernel<<<npartial, 256, 0, stream>>>(P, points, partial);
+    SEGS_LAUNCH_CHECK();
+    morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, partial, npartial, ka, va);
+    SEGS_LAUNCH_CHECK();
+    int rc;
+    if ((rc = radix_pass(ka, kb, va, vb, P, 0, bh, gh, stream))) return rc;
+    if ((rc = radix_pass(kb, ka, vb, va, P, 8, bh, gh, stream))) return rc;
+    if ((rc = radix_pass(ka, kb, va, vb, P, 16, bh, gh, stream))) return rc;
+    if ((rc = radix_pass(kb, ka, vb, va, P, 24, bh, gh, stream))) return rc;
+    gather_box_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, points, va, sorted, boxes);
+    SEGS_LAUNCH_CHECK();
+    knn_search_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, sorted, boxes, nboxes, mean_dists);
+    SEGS_LAUNCH_CHECK();
+    return SEGS_OK;
+}
