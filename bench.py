@@ -1,0 +1,408 @@
+#!/usr/bin/env python
+"""bench.py — rasterizer forward+backward throughput on the BASELINE.json workload.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--config C2]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+Metric (BASELINE.json): rasterizer fwd+bwd iterations/s @ 1M Gaussians, 1200x680 (config C2 =
+`synth(1_000_000, 1200, 680, 600, 600, 1002)`).  One iteration = one view through
+segs_raster_forward + segs_raster_backward.  A *step* is VIEWS_PER_STEP (8) views of the replicated
+Gaussian set from 8 keyframe poses per GPU, gradients accumulated over the views, followed — when
+N > 1 — by one NCCL all-reduce of the accumulated gradients (the keyframe-batched mapping step of
+north_star: 8 GPUs x 8 views = the 64-keyframe batch).  `value` = views processed by all ranks /
+max-over-ranks device time, so it is directly the headline iterations/s at N = 1 and the mapping
+keyframes/s at N > 1 (weak scaling: per-GPU work is fixed).
+
+JSON keys follow the driver's contract; see DESIGN.md §"Measurement".  `--impl reference` times the
+UNMODIFIED reference CUDA rasterizer (oracle/_ref/libsegs_ref.so, sm_100a recompile) on the same
+GPU with the same harness — the denominator of north_star's ">= 3x" target; when that library is
+absent it times the CPU oracle port instead.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+VIEWS_PER_STEP = 8
+METRIC = "rasterizer fwd+bwd iters/sec @1M Gaussians 1200x680; mapping keyframes/sec 1/2/4/8 GPU"
+UNIT = "iterations/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
+    ap.add_argument("--config", default="C2")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    return ap.parse_args()
+
+
+# ---------------------------------------------------------------------------------------------
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                 "-lms", "100"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc:
+            self.proc.terminate()
+        sm, mx, reasons = [], [], set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx.append(float(r[1]))
+            except Exception:
+                continue
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def view_poses(n_views, first):
+    """Keyframe poses of the batched mapping step: the C2 camera shifted sideways by a few cm per
+    view (disjoint views of the same replicated scene, near-identical cost per view).  View 0 is
+    exactly the C2 camera of BASELINE.md §3."""
+    import numpy as np
+    out = []
+    for v in range(first, first + n_views):
+        k = v % 64
+        t = np.array([0.02 * (k % 8), 0.015 * (k // 8), 0.0], dtype=np.float32)
+        out.append((np.eye(3, dtype=np.float32), t))
+    return out
+
+
+# ---------------------------------------------------------------------------------------------
+def algorithmic_bytes(P, R, N):
+    """compulsory bytes per stage (each unique array touched once)."""
+    return {
+        "preprocess": 104 * P,
+        "depth_order": 8 * P + 20 * P,                 # F2 scan + the per-Gaussian part of F4
+        "binning": 12 * R + 24 * R + 8 * R,            # F4 emission + F5 sort + F6 ranges
+        "blend_forward": 40 * R + 20 * N,
+        "blend_backward": 40 * R + 20 * N + 44 * P,
+        "preprocess_backward": 160 * P,
+    }
+
+
+STAGES = ["preprocess", "depth_order", "binning", "blend_forward", "blend_backward", "preprocess_backward"]
+
+
+def main():
+    args = parse()
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    distributed = world > 1
+
+    if args.impl != "ours" and distributed and rank != 0:
+        return 0          # the reference is single-GPU: rank 0 alone runs and prints it
+
+    if args.impl == "reference-cpu" or (args.impl == "reference" and not _gpu_reference_available()):
+        return reference_cpu_arm(args, world)
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if distributed and args.impl == "ours":
+        dist.init_process_group("nccl", device_id=dev)
+
+    from segs_slam_b200 import synth
+    import common
+
+    scene0 = synth.config(args.config)
+    P, W, H = scene0.P, scene0.W, scene0.H
+    N = W * H
+    poses = view_poses(VIEWS_PER_STEP, first=rank * VIEWS_PER_STEP)
+    scenes = [synth.with_camera(scene0, Rm, t) if (t != 0).any() else scene0 for Rm, t in poses]
+    base = scene0.to_torch(dev)
+    cams = [{k: torch.from_numpy(np.ascontiguousarray(getattr(s, k))).to(dev)
+             for k in ("viewmatrix", "projmatrix", "campos")} for s in scenes]
+    dL = base["dL_dout"]
+
+    if args.impl == "ours":
+        from segs_slam_b200 import _lib, rasterize_points as rp
+        lib = _lib.load()
+
+        def fwd_bwd(cam, dL_dout):
+            a = (base["bg"], base["means3D"], base["colors"], base["opacities"], base["scales"], base["rotations"],
+                 1.0, common.empty(dev), cam["viewmatrix"], cam["projmatrix"], scene0.tanfovx, scene0.tanfovy, H, W,
+                 common.empty(dev), 0, cam["campos"], False)
+            R, color, radii, g, b, i = rp.RasterizeGaussiansCUDA(*a)
+            grads = rp.RasterizeGaussiansBackwardCUDA(
+                base["bg"], base["means3D"], radii, base["colors"], base["scales"], base["rotations"], 1.0,
+                common.empty(dev), cam["viewmatrix"], cam["projmatrix"], scene0.tanfovx, scene0.tanfovy, dL_dout,
+                common.empty(dev), 0, cam["campos"], g, R, b, i)
+            return R, color, grads
+    else:
+        import refimpl
+        lib = None
+
+        def fwd_bwd(cam, dL_dout):
+            e = common.empty(dev)
+            R, color, radii, g, b, i = refimpl.forward(
+                base["bg"], base["means3D"], base["colors"], base["opacities"], base["scales"], base["rotations"],
+                1.0, e, cam["viewmatrix"], cam["projmatrix"], scene0.tanfovx, scene0.tanfovy, H, W, e, 0,
+                cam["campos"])
+            d = refimpl.backward(base["bg"], base["means3D"], radii, base["colors"], base["scales"],
+                                 base["rotations"], 1.0, e, cam["viewmatrix"], cam["projmatrix"], scene0.tanfovx,
+                                 scene0.tanfovy, dL_dout, e, 0, cam["campos"], g, R, b, i)
+            grads = (d["dL_dmeans2D"], d["dL_dcolors"], d["dL_dopacity"], d["dL_dmeans3D"], d["dL_dcov3D"],
+                     d["dL_dsh"], d["dL_dscales"], d["dL_drotations"])
+            return R, color, grads
+
+    # flat gradient bucket = what the mapper all-reduces (means3D 3, means2D 3, colors 3, opacity 1,
+    # scales 3, rotations 4 floats per Gaussian)
+    GRAD_IDX = (3, 0, 1, 2, 6, 7)
+    widths = (3, 3, 3, 1, 3, 4)
+    bucket = torch.zeros((P, sum(widths)), dtype=torch.float32, device=dev)
+
+    def accumulate(grads, first):
+        col = 0
+        for gi, w in zip(GRAD_IDX, widths):
+            g = grads[gi].view(P, w)
+            if first:
+                bucket[:, col:col + w].copy_(g)
+            else:
+                bucket[:, col:col + w].add_(g)
+            col += w
+
+    R_seen = []
+
+    def step():
+        for v, cam in enumerate(cams):
+            R, color, grads = fwd_bwd(cam, dL)
+            accumulate(grads, v == 0)
+            R_seen.append(R)
+        if distributed and args.impl == "ours":
+            dist.all_reduce(bucket)
+        return color
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed and args.impl == "ours":
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident timing -------------------------------------------------
+    warm = max(3, args.warmup)
+    for _ in range(warm):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    stage_ms = np.zeros(len(STAGES))
+    launches0 = lib.segs_launch_count() if lib else 0
+    if lib:
+        lib.segs_profile_enable(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    R_seen.clear()
+    barrier()
+    ev0.record()
+    n_prof = 0
+    for s in range(args.steps):
+        step()
+        if lib and s % 4 == 0:        # last view of the step: per-stage events (already complete or nearly)
+            import ctypes as C
+            ms = (C.c_float * len(STAGES))()
+            lib.segs_profile_read(ms)
+            stage_ms += np.array(list(ms)); n_prof += 1
+    ev1.record()
+    barrier()
+    elapsed_ms = ev0.elapsed_time(ev1)
+    launches = (lib.segs_launch_count() - launches0) if lib else 0
+    if lib:
+        lib.segs_profile_enable(0)
+    t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
+    if distributed and args.impl == "ours":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    elapsed_ms = float(t.item())
+    n_ranks = world if args.impl == "ours" else 1
+    views = VIEWS_PER_STEP * args.steps * n_ranks
+    value = views / (elapsed_ms * 1e-3)
+    R_mean = float(np.mean(R_seen)) if R_seen else 0.0
+
+    # ---------------- end-to-end: host buffers in, host buffers out --------------------------
+    # Per step: the Gaussian parameters come from pinned host memory, every view's dL_dout comes
+    # from pinned host memory, every view's image and the step's accumulated gradients go back.
+    host_in = {k: base[k].cpu().pin_memory() for k in ("means3D", "colors", "opacities", "scales", "rotations")}
+    host_dL = dL.cpu().pin_memory()
+    host_img = torch.empty((3, H, W), dtype=torch.float32).pin_memory()
+    host_grads = torch.empty_like(bucket, device="cpu").pin_memory()
+    h2d = sum(v.numel() * 4 for v in host_in.values()) + VIEWS_PER_STEP * host_dL.numel() * 4
+    d2h = VIEWS_PER_STEP * host_img.numel() * 4 + host_grads.numel() * 4
+
+    def e2e_step():
+        for k, v in host_in.items():
+            base[k].copy_(v, non_blocking=True)
+        for v, cam in enumerate(cams):
+            dL.copy_(host_dL, non_blocking=True)
+            R, color, grads = fwd_bwd(cam, dL)
+            accumulate(grads, v == 0)
+            host_img.copy_(color, non_blocking=True)
+        if distributed and args.impl == "ours":
+            dist.all_reduce(bucket)
+        host_grads.copy_(bucket, non_blocking=True)
+        torch.cuda.current_stream().synchronize()     # the host owns the results when the step returns
+
+    e2e_steps = max(3, args.steps // 2)
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(e2e_steps):
+        e2e_step()
+    e1.record()
+    barrier()
+    e2e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)   # device events vs host wall clock
+    t = torch.tensor([e2e_ms], dtype=torch.float64, device=dev)
+    if distributed and args.impl == "ours":
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = VIEWS_PER_STEP * e2e_steps * n_ranks / (float(t.item()) * 1e-3)
+    clocks = sampler.stop() if rank == 0 else None
+
+    if rank != 0:
+        if distributed:
+            dist.destroy_process_group()
+        return 0
+
+    # ---------------- roofline of the dominant kernel ----------------------------------------
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak_gbs = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback (B200_PROFILING.md)"
+    roofline, stages_out = None, {}
+    if lib and n_prof:
+        ms = stage_ms / n_prof
+        ab = algorithmic_bytes(P, R_mean, N)
+        for name, m in zip(STAGES, ms):
+            stages_out[name] = {"ms": round(float(m), 4), "algorithmic_MB": round(ab[name] / 1e6, 2),
+                                "GBps": round(ab[name] / (m * 1e-3) / 1e9, 1) if m > 0 else None}
+        top = STAGES[int(np.argmax(ms))]
+        achieved = ab[top] / (float(ms[STAGES.index(top)]) * 1e-3) / 1e9
+        traffic = None
+        try:
+            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+        except Exception:
+            pass
+        roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs,
+                    "unit": "GB/s", "frac": round(achieved / peak_gbs, 4), "traffic": traffic,
+                    "peak_source": peak_src, "ms_per_launch": round(float(ms[STAGES.index(top)]), 4),
+                    "note": "blend kernels are FP32-ALU/MUFU bound, not HBM bound (SURVEY 8d); "
+                            "frac is algorithmic bytes / time / copy peak as the contract asks",
+                    "stages": stages_out, "step_share": round(float(ms[STAGES.index(top)] / ms.sum()), 3)}
+
+    line = {
+        "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+        "warmup": warm, "ms_per_step": round(elapsed_ms / args.steps, 4), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.config}: synth({P},{W},{H}) single-view rasterizer forward+backward "
+                               f"(BASELINE.md section 3), colours precomputed, scale+quaternion",
+                   "views_per_step_per_gpu": VIEWS_PER_STEP, "P": P, "W": W, "H": H,
+                   "num_rendered_mean": round(R_mean), "parallelism": f"dp{n_ranks} (keyframe views)",
+                   "l2": "working set per view (~0.45 GB state + gradients) exceeds the 126 MB L2; no flush"},
+        "clocks": clocks,
+        "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+                "d2h_bytes_per_step": int(d2h), "steps": e2e_steps},
+        "gpu_launches": int(launches),
+    }
+    if args.impl != "ours":
+        line["impl"] = "reference"
+        line["gpu_launches"] = 0
+        line["config"]["reference"] = ("unmodified SEGS-SLAM cuda_rasterizer compiled for sm_100a "
+                                       "(oracle/_ref), same GPU, same harness; single GPU")
+        line["cpu_baseline"] = {"value": line["value"], "unit": UNIT, "cores": 0, "kind": "reference",
+                                "sample": "the reference's own CUDA kernels on the GPU (it has no CPU path)"}
+    else:
+        line["roofline"] = roofline
+        if not args.no_cpu_baseline and args.gpus == 1:
+            line["cpu_baseline"] = cpu_baseline(args.config)
+    print(json.dumps(line), flush=True)
+    if distributed and args.impl == "ours":
+        dist.destroy_process_group()
+    return 0
+
+
+def _gpu_reference_available():
+    try:
+        import torch
+        import refimpl
+        return torch.cuda.is_available() and refimpl.available()
+    except Exception:
+        return False
+
+
+def cpu_baseline(config):
+    """CPU oracle (scalar C++ port, oracle/raster_oracle.cpp) on all host cores: one full
+    forward+backward of the same workload."""
+    import oracle_lib
+    from segs_slam_b200 import synth
+    cores = os.cpu_count() or 1
+    scene = synth.config(config)
+    t0 = time.perf_counter()
+    f = oracle_lib.from_scene(scene, nthreads=cores)
+    f.backward(scene.dL_dout)
+    dt = time.perf_counter() - t0
+    f.close()
+    return {"value": round(1.0 / dt, 4), "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"1 full forward+backward iteration of {config} ({scene.P} Gaussians, {scene.W}x{scene.H}) "
+                      f"on {cores} threads, {dt:.2f} s"}
+
+
+def reference_cpu_arm(args, world):
+    """Fallback reference arm when oracle/_ref cannot run: the CPU oracle port."""
+    cb = cpu_baseline(args.config)
+    line = {"metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": 1, "warmup": 0,
+            "ms_per_step": round(1e3 / cb["value"], 2), "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": f"{args.config} single-view rasterizer forward+backward, CPU oracle port"},
+            "cpu_baseline": cb,
+            "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

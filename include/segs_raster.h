@@ -191,6 +191,19 @@ int segs_knn_mean_dist2(
     segs_alloc_fn scratch_alloc, void* scratch_user,
     void* stream);
 
+/* ---- per-stage device timing (bench.py roofline) -------------------------------------- */
+/* When enabled (per host thread), segs_raster_forward / segs_raster_backward bracket their
+ * stages with CUDA events on the caller's stream.  segs_profile_read synchronises those
+ * events and returns the milliseconds of the most recent forward and backward call:
+ *   ms[0] preprocess   ms[1] depth order + offsets   ms[2] instance emission + tile sort + ranges
+ *   ms[3] blend forward   ms[4] blend backward   ms[5] preprocess backward
+ * (a stage that did not run since the last read reports 0). */
+#define SEGS_PROFILE_STAGES 6
+/* Number of kernels this library has launched from the calling host thread so far. */
+unsigned long long segs_launch_count(void);
+int segs_profile_enable(int on);
+int segs_profile_read(float* ms /* [SEGS_PROFILE_STAGES] */);
+
 /* ---- inspection of the opaque buffers (parity tests, debugging) --------------------- */
 /* Returns in *ptr / *bytes the device address and size of a named section of the
  * buffers produced by segs_raster_forward for the given (P, R, width, height).

@@ -52,6 +52,9 @@ _PROTOTYPES = {
          C.c_float, C.c_float, C.c_int, _f32p, _f32p, _i32p, C.c_void_p],
     ),
     "segs_knn_mean_dist2": (C.c_int, [C.c_int, _f32p, _f32p, ALLOC_FN, C.c_void_p, C.c_void_p]),
+    "segs_launch_count": (C.c_ulonglong, []),
+    "segs_profile_enable": (C.c_int, [C.c_int]),
+    "segs_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
     "segs_buffer_section": (
         C.c_int,
         [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

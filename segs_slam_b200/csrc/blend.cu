@@ -47,8 +47,9 @@ __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_gr
 // power of forward.cu:413 / backward.cu:494 with nvcc's contraction:
 //   -0.5f * (con.x*d.x*d.x + con.z*d.y*d.y) - con.y*d.x*d.y
 __device__ __forceinline__ float gauss_power(float dx, float dy, float cx, float cy, float cz) {
+    // SASS of the reference: FFMA(a, -0.5, -(dy*(dx*cy)))
     const float a = __fmaf_rn(dx, __fmul_rn(dx, cx), __fmul_rn(dy, __fmul_rn(dy, cz)));
-    return __fsub_rn(__fmul_rn(a, -0.5f), __fmul_rn(dy, __fmul_rn(dx, cy)));
+    return __fmaf_rn(a, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cy)));
 }
 
 // conservative sub-tile test; written so that NaNs never cull

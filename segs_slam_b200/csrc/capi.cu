@@ -22,6 +22,9 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
+static thread_local unsigned long long g_launches = 0;
+void count_launch() { ++g_launches; }
+
 // ---- layouts --------------------------------------------------------------------------
 GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
     Carver c(base);
@@ -95,6 +98,29 @@ static uint32_t* pinned_words() {
     return p;
 }
 
+// ---- optional per-stage timing ----------------------------------------------------------
+struct Profile {
+    bool on = false;
+    bool created = false;
+    cudaEvent_t ev[2 * SEGS_PROFILE_STAGES];
+    bool armed[SEGS_PROFILE_STAGES] = {false, false, false, false, false, false};
+};
+static thread_local Profile g_prof;
+
+static void prof_begin(int stage, cudaStream_t s) {
+    if (!g_prof.on) return;
+    if (!g_prof.created) {
+        for (auto& e : g_prof.ev) cudaEventCreate(&e);
+        g_prof.created = true;
+    }
+    cudaEventRecord(g_prof.ev[2 * stage], s);
+}
+static void prof_end(int stage, cudaStream_t s) {
+    if (!g_prof.on) return;
+    cudaEventRecord(g_prof.ev[2 * stage + 1], s);
+    g_prof.armed[stage] = true;
+}
+
 }  // namespace segs
 
 using namespace segs;
@@ -102,6 +128,22 @@ using namespace segs;
 extern "C" {
 
 int segs_version(void) { return SEGS_ABI_VERSION; }
+
+unsigned long long segs_launch_count(void) { return g_launches; }
+
+int segs_profile_enable(int on) { g_prof.on = on != 0; return SEGS_OK; }
+
+int segs_profile_read(float* ms) {
+    if (!ms) { set_error("invalid argument"); return SEGS_ERR_INVALID_ARG; }
+    for (int s = 0; s < SEGS_PROFILE_STAGES; ++s) {
+        ms[s] = 0.f;
+        if (!g_prof.created || !g_prof.armed[s]) continue;
+        SEGS_CUDA_CHECK(cudaEventSynchronize(g_prof.ev[2 * s + 1]));
+        SEGS_CUDA_CHECK(cudaEventElapsedTime(&ms[s], g_prof.ev[2 * s], g_prof.ev[2 * s + 1]));
+        g_prof.armed[s] = false;
+    }
+    return SEGS_OK;
+}
 const char* segs_last_error(void) { return g_last_error; }
 
 int segs_raster_forward(
@@ -163,10 +205,14 @@ int segs_raster_forward(
 
     SEGS_CUDA_CHECK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), stream));
     int rc;
+    prof_begin(0, stream);
     if ((rc = launch_preprocess(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
                                 colors_precomp, viewmatrix, projmatrix, cam_pos, vp, prefiltered != 0,
                                 radii, g, stream))) return rc;
+    prof_end(0, stream);
+    prof_begin(1, stream);
     if ((rc = launch_depth_order(P, g, stream))) return rc;
+    prof_end(1, stream);
 
     // num_rendered sizes the binning buffer, so it has to reach the host here
     // (rasterizer_impl.cu:279-285).
@@ -184,8 +230,12 @@ int segs_raster_forward(
     if (!bin_ptr) { set_error("binning buffer allocation of %zu bytes failed", bin_bytes); return SEGS_ERR_ALLOC; }
     BinningState b = BinningState::carve(bin_ptr, R, nullptr);
 
+    prof_begin(2, stream);
     if ((rc = launch_binning(P, (int)R, vp, g, b, img, stream))) return rc;
+    prof_end(2, stream);
+    prof_begin(3, stream);
     if ((rc = launch_blend_forward(vp, g, b, img, background, out_color, stream))) return rc;
+    prof_end(3, stream);
     if (num_rendered) *num_rendered = (int)R;
     return SEGS_OK;
 }
@@ -217,12 +267,17 @@ int segs_raster_backward(
     BinningState b = BinningState::carve(binning_buffer, R, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
     int rc;
-    if (R > 0)
+    if (R > 0) {
+        prof_begin(4, stream);
         if ((rc = launch_blend_backward(vp, g, b, img, background, dL_dpix, stream))) return rc;
+        prof_end(4, stream);
+    }
+    prof_begin(5, stream);
     if ((rc = launch_preprocess_backward(P, D, M, means3D, scales, rotations, shs, cov3D_precomp, viewmatrix,
                                          projmatrix, campos, vp, radii, g, dL_dmean2D, dL_dconic, dL_dopacity,
                                          dL_dcolor, dL_dmean3D, dL_dcov3D, dL_dsh, dL_dscale, dL_drot, stream)))
         return rc;
+    prof_end(5, stream);
     return SEGS_OK;
 }
 

@@ -26,7 +26,12 @@ void set_error(const char* fmt, ...);
             return SEGS_ERR_CUDA;                                                        \
         }                                                                                \
     } while (0)
-#define SEGS_LAUNCH_CHECK() SEGS_CUDA_CHECK(cudaGetLastError())
+void count_launch();
+#define SEGS_LAUNCH_CHECK()                  \
+    do {                                     \
+        ::segs::count_launch();              \
+        SEGS_CUDA_CHECK(cudaGetLastError()); \
+    } while (0)
 
 // ---- opaque buffer layout -----------------------------------------------------------
 // A bump allocator over the caller-owned byte buffers, 128-byte aligned sections

@@ -18,7 +18,9 @@
 // so it does not depend on how this file happens to be optimised:  for a sum of three
 // products  a0*b0 + a1*b1 + a2*b2  nvcc emits  fma(a2,b2, fma(a0,b0, mul(a1,b1)))  — see
 // dot3c() — and products with a structural zero are kept (0*x is not folded without
-// fast-math).  DESIGN.md §"bit-exact preprocess" lists the PTX this was checked against.
+// fast-math).  The pattern was read from the SASS of the reference build (NVVM contracts
+// some pairs in PTX, ptxas fuses more of the remaining mul/add pairs), see DESIGN.md
+// §"bit-exact preprocess".
 #include "common.cuh"
 
 namespace segs {
@@ -52,22 +54,25 @@ __device__ __forceinline__ void cov3d_from_scale_rot(float mod, float s0, float 
 {
     const float r = q.x, x = q.y, y = q.z, z = q.w;   // (r,x,y,z), NOT normalised (forward.cu:127)
     const float sx = __fmul_rn(mod, s0), sy = __fmul_rn(mod, s1), sz = __fmul_rn(mod, s2);
+    // Final contraction as it appears in the reference's SASS (ptxas fuses one product of each
+    // a*b +- c*d pair that NVVM left as mul/add): xy, yz and ry are never rounded on their own.
     const float yy = __fmul_rn(y, y), zz = __fmul_rn(z, z);
-    const float xy = __fmul_rn(x, y), rz = __fmul_rn(r, z);
-    const float xz = __fmul_rn(x, z), ry = __fmul_rn(r, y);
-    const float yz = __fmul_rn(y, z), rx = __fmul_rn(r, x);
+    const float rz = __fmul_rn(r, z), xz = __fmul_rn(x, z), rx = __fmul_rn(r, x);
     const float yy_zz = __fadd_rn(yy, zz);
     const float xx_zz = __fmaf_rn(x, x, zz);
     const float xx_yy = __fmaf_rn(x, x, yy);
+    const float xy_m_rz = __fmaf_rn(x, y, -rz), xy_p_rz = __fmaf_rn(x, y, rz);
+    const float xz_p_ry = __fmaf_rn(r, y, xz), xz_m_ry = __fmaf_rn(-r, y, xz);
+    const float yz_m_rx = __fmaf_rn(y, z, -rx), yz_p_rx = __fmaf_rn(y, z, rx);
     // glm::mat3 R(...) column-major: R[c][r]
     const float R00 = __fsub_rn(1.f, __fadd_rn(yy_zz, yy_zz));
-    const float R01 = __fadd_rn(__fsub_rn(xy, rz), __fsub_rn(xy, rz));
-    const float R02 = __fadd_rn(__fadd_rn(ry, xz), __fadd_rn(ry, xz));
-    const float R10 = __fadd_rn(__fadd_rn(xy, rz), __fadd_rn(xy, rz));
+    const float R01 = __fadd_rn(xy_m_rz, xy_m_rz);
+    const float R02 = __fadd_rn(xz_p_ry, xz_p_ry);
+    const float R10 = __fadd_rn(xy_p_rz, xy_p_rz);
     const float R11 = __fsub_rn(1.f, __fadd_rn(xx_zz, xx_zz));
-    const float R12 = __fadd_rn(__fsub_rn(yz, rx), __fsub_rn(yz, rx));
-    const float R20 = __fadd_rn(__fsub_rn(xz, ry), __fsub_rn(xz, ry));
-    const float R21 = __fadd_rn(__fadd_rn(rx, yz), __fadd_rn(rx, yz));
+    const float R12 = __fadd_rn(yz_m_rx, yz_m_rx);
+    const float R20 = __fadd_rn(xz_m_ry, xz_m_ry);
+    const float R21 = __fadd_rn(yz_p_rx, yz_p_rx);
     const float R22 = __fsub_rn(1.f, __fadd_rn(xx_yy, xx_yy));
     // M = S * R with S = diag(sx,sy,sz): M[c][r] = S[0][r]*R[c][0] + S[1][r]*R[c][1] + S[2][r]*R[c][2]
     const float M00 = dot3c(sx, R00, 0.f, R01, 0.f, R02);
@@ -147,11 +152,11 @@ __device__ __forceinline__ bool project_gaussian(float px, float py, float pz, c
     o.cov_y = cov01;
     o.cov_z = __fadd_rn(cov11, 0.3f);
 
-    // forward.cu:219-232 (none of these a*b - c*d forms is contracted by nvcc)
-    o.det = __fsub_rn(__fmul_rn(o.cov_x, o.cov_z), __fmul_rn(o.cov_y, o.cov_y));
+    // forward.cu:219-232; in SASS: det = fma(a, c, -(b*b)), discriminant = fma(mid, mid, -det)
+    o.det = __fmaf_rn(o.cov_x, o.cov_z, -__fmul_rn(o.cov_y, o.cov_y));
     if (o.det == 0.0f) return false;
     const float mid = __fmul_rn(0.5f, __fadd_rn(o.cov_x, o.cov_z));
-    const float disc = __fsqrt_rn(fmaxf(0.1f, __fsub_rn(__fmul_rn(mid, mid), o.det)));
+    const float disc = __fsqrt_rn(fmaxf(0.1f, __fmaf_rn(mid, mid, -o.det)));
     const float lambda1 = __fadd_rn(mid, disc);
     const float lambda2 = __fsub_rn(mid, disc);
     const float my_radius = ceilf(__fmul_rn(3.f, __fsqrt_rn(fmaxf(lambda1, lambda2))));

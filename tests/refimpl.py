@@ -73,7 +73,8 @@ def _empty(dev):
 def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
             projmatrix, tan_fovx, tan_fovy, H, W, sh, degree, campos, prefiltered=False):
     """RasterizeGaussiansCUDA of the reference, minus torch glue (zeros for outputs as
-    src/rasterize_points.cu:69-70).  The reference launches on the legacy default stream."""
+    src/rasterize_points.cu:69-70).  The reference launches on the legacy default stream, which
+    is also torch's default stream, so no extra synchronisation is needed (or added)."""
     lib = load()
     dev = means3D.device
     P = means3D.size(0)
@@ -83,7 +84,6 @@ def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov
     M = sh.size(1) if sh.numel() else 0
     rendered = 0
     if P:
-        torch.cuda.current_stream().synchronize()
         rendered = lib.ref_raster_forward(g.cb, None, b.cb, None, i.cb, None, P, int(degree), int(M),
                                           _ptr(bg), W, H, _ptr(means3D), _ptr(sh), _ptr(colors), _ptr(opacity),
                                           _ptr(scales), float(scale_modifier), _ptr(rotations),
@@ -106,7 +106,6 @@ def backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3
              dL_dsh=torch.zeros((P, M, 3), **o), dL_dscales=torch.zeros((P, 3), **o),
              dL_drotations=torch.zeros((P, 4), **o))
     if P:
-        torch.cuda.current_stream().synchronize()
         lib.ref_raster_backward(P, int(degree), int(M), int(R), _ptr(bg), W, H, _ptr(means3D), _ptr(sh),
                                 _ptr(colors), _ptr(scales), float(scale_modifier), _ptr(rotations),
                                 _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
@@ -126,7 +125,6 @@ def visible_filter(means3D, scales, rotations, scale_modifier, cov3D_precomp, vi
     radii = torch.zeros((P,), dtype=torch.int32, device=dev)
     g, b, i = _Grower(dev), _Grower(dev), _Grower(dev)
     if P:
-        torch.cuda.current_stream().synchronize()
         lib.ref_visible_filter(g.cb, None, b.cb, None, i.cb, None, P, 0, W, H, _ptr(means3D), _ptr(scales),
                                float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                                _ptr(projmatrix), float(tan_fovx), float(tan_fovy), 0, _ptr(radii))
@@ -139,7 +137,6 @@ def mark_visible(means3D, viewmatrix, projmatrix):
     P = means3D.size(0)
     present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
     if P:
-        torch.cuda.current_stream().synchronize()
         lib.ref_mark_visible(P, _ptr(means3D), _ptr(viewmatrix), _ptr(projmatrix), present.data_ptr())
         lib.ref_sync()
     return present
@@ -150,7 +147,6 @@ def knn(points):
     P = points.size(0)
     out = torch.zeros((P,), dtype=torch.float32, device=points.device)
     if P:
-        torch.cuda.current_stream().synchronize()
         lib.ref_knn_mean_dist2(P, _ptr(points), _ptr(out))
         lib.ref_sync()
     return out

@@ -102,7 +102,8 @@ def _compare_backward(m, r, r2, name):
     # gradients of non-rendered Gaussians are exactly zero
     inv = ~(r["radii"] > 0)
     for k in ("dL_dmeans3D", "dL_dscales", "dL_drotations", "dL_dcolors", "dL_dopacity", "dL_dmeans2D"):
-        assert m["grads"][k][inv].abs().max().item() == 0.0 if inv.any() else True
+        if inv.any():
+            assert m["grads"][k][inv].abs().max().item() == 0.0
 
 
 @needs_ref
@@ -181,7 +182,8 @@ def test_empty_and_culled(device):
     expect = t["bg"].view(3, 1, 1).expand(3, scene.H, scene.W)
     assert torch.equal(m["color"], expect)
     for g_ in m["grads"].values():
-        assert g_.abs().max().item() == 0.0
+        if g_.numel():
+            assert g_.abs().max().item() == 0.0
     if refimpl.available():
         r = common.run_ref(a)
         assert torch.equal(m["color"], r["color"])
