@@ -220,35 +220,42 @@ def main():
         torch.cuda.synchronize()
 
     # ---------------- device-resident timing -------------------------------------------------
-    warm = max(3, args.warmup)
-    for _ in range(warm):
+    # warm-up: at least W (>= 3) steps, continued until the GPU has been busy for ~1.5 s so that
+    # clocks and the caching allocator are in steady state (the count actually run is reported)
+    warm = 0
+    t_warm = time.perf_counter()
+    while warm < max(3, args.warmup) or (time.perf_counter() - t_warm < 1.5 and warm < 200):
         step()
+        torch.cuda.synchronize()
+        warm += 1
     barrier()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
     stage_ms = np.zeros(len(STAGES))
     launches0 = lib.segs_launch_count() if lib else 0
-    if lib:
-        lib.segs_profile_enable(1)
+    import ctypes as C
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     R_seen.clear()
     barrier()
     ev0.record()
     n_prof = 0
     for s in range(args.steps):
+        # per-stage CUDA events (12 event records per view) are only armed on every 5th step so
+        # that they do not perturb the step time they are part of
+        prof = lib is not None and s % 5 == 0
+        if prof:
+            lib.segs_profile_enable(1)
         step()
-        if lib and s % 4 == 0:        # last view of the step: per-stage events (already complete or nearly)
-            import ctypes as C
+        if prof:
+            lib.segs_profile_enable(0)
             ms = (C.c_float * len(STAGES))()
-            lib.segs_profile_read(ms)
+            lib.segs_profile_read(ms)          # stages of the step's last view
             stage_ms += np.array(list(ms)); n_prof += 1
     ev1.record()
     barrier()
     elapsed_ms = ev0.elapsed_time(ev1)
     launches = (lib.segs_launch_count() - launches0) if lib else 0
-    if lib:
-        lib.segs_profile_enable(0)
     t = torch.tensor([elapsed_ms], dtype=torch.float64, device=dev)
     if distributed and args.impl == "ours":
         dist.all_reduce(t, op=dist.ReduceOp.MAX)

@@ -20,9 +20,11 @@
 //  * Early termination is per warp (all 32 pixels saturated) on top of the reference's
 //    per-CTA vote.
 //  * Backward: gradients of one Gaussian are reduced across the warp with a 9-shuffle
-//    transpose-reduce, accumulated across the tile's 8 warps in shared memory, and flushed
-//    once per (Gaussian, tile) with 128-bit vector reductions into a packed 48-byte
-//    accumulator — instead of the reference's 9 global atomics per (Gaussian, pixel).
+//    transpose-reduce and sent as ONE reduction per value per (Gaussian, 8x4 sub-tile) into a
+//    packed 48-byte accumulator (8 lanes hit 8 consecutive floats) — instead of the
+//    reference's 9 global atomics per (Gaussian, pixel).  (Shared-memory float atomics
+//    compile to CAS loops on sm_100a, so a per-tile shared accumulator costs more
+//    instructions than it saves; measured in profiles/r1.)
 //
 // The per-pair arithmetic (power, alpha, T update, colour accumulation) follows the
 // reference's operations and FMA contraction one by one so that n_contrib / final_T decisions
@@ -150,28 +152,27 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int slot = c * 32 + j;
-                    if (!done) {
-                        const float4 g0 = s_rec[buf][0][slot];
-                        const float4 g1 = s_rec[buf][1][slot];
-                        const float dx = __fsub_rn(g0.x, pixfx);
-                        const float dy = __fsub_rn(g0.y, pixfy);
-                        const float power = gauss_power(dx, dy, g1.x, g1.y, g1.z);
-                        if (!(power > 0.0f)) {
-                            const float alpha = fminf(0.99f, __fmul_rn(g1.w, expf(power)));
-                            if (!(alpha < 1.0f / 255.0f)) {
-                                const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
-                                if (test_T < 0.0001f) {
-                                    done = true;
-                                } else {
-                                    const float4 g2 = s_rec[buf][2][slot];
-                                    C0 = __fmaf_rn(T, __fmul_rn(alpha, g2.x), C0);
-                                    C1 = __fmaf_rn(T, __fmul_rn(alpha, g2.y), C1);
-                                    C2 = __fmaf_rn(T, __fmul_rn(alpha, g2.z), C2);
-                                    T = test_T;
-                                    last_contributor = (uint32_t)(base + slot + 1);
-                                }
-                            }
-                        }
+                    // Straight-line body (no divergent branches): every lane evaluates the pair,
+                    // lanes that are done / miss the reference's tests simply do not commit.
+                    const float4 g0 = s_rec[buf][0][slot];
+                    const float4 g1 = s_rec[buf][1][slot];
+                    const float4 g2 = s_rec[buf][2][slot];
+                    const float dx = __fsub_rn(g0.x, pixfx);
+                    const float dy = __fsub_rn(g0.y, pixfy);
+                    const float power = gauss_power(dx, dy, g1.x, g1.y, g1.z);
+                    const float alpha = fminf(0.99f, __fmul_rn(g1.w, expf(power)));
+                    const float test_T = __fmul_rn(T, __fsub_rn(1.f, alpha));
+                    // forward.cu:414-429: power > 0 / alpha < 1/255 skip; T < 1e-4 stops the pixel
+                    const bool contrib = !done && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    const bool stop = contrib && (test_T < 0.0001f);
+                    const bool blend = contrib && !stop;
+                    done = done || stop;
+                    if (blend) {
+                        C0 = __fmaf_rn(T, __fmul_rn(alpha, g2.x), C0);
+                        C1 = __fmaf_rn(T, __fmul_rn(alpha, g2.y), C1);
+                        C2 = __fmaf_rn(T, __fmul_rn(alpha, g2.z), C2);
+                        T = test_T;
+                        last_contributor = (uint32_t)(base + slot + 1);
                     }
                 }
                 if (__all_sync(FULL, done)) break;
@@ -195,8 +196,6 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
 // =======================================================================================
 // backward
 // =======================================================================================
-constexpr int ACC_STRIDE = 12;   // floats per slot in the shared accumulator (9 used)
-
 // Sum v[0..7] over the warp with 9 shuffles.  Afterwards lane l holds the total of value
 // ((l>>4)&1)*4 + ((l>>3)&1)*2 + ((l>>2)&1) (all four lanes of a quad hold the same total).
 __device__ __forceinline__ float transpose_reduce8(float (&v)[8], int lane) {
@@ -231,7 +230,6 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                       float4* __restrict__ acc)
 {
     __shared__ float4 s_rec[2][3][BATCH];
-    __shared__ float s_acc[BATCH * ACC_STRIDE];
     __shared__ uint32_t s_id[2][BATCH];
     __shared__ int s_bmax;
 
@@ -261,7 +259,6 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
     // last list position any pixel of the warp / CTA needs
     const int wmax = __reduce_max_sync(FULL, my_last);
     if (tid == 0) s_bmax = 0;
-    for (int i = tid; i < BATCH * ACC_STRIDE; i += TILE_PIX) s_acc[i] = 0.f;
     __syncthreads();
     if (lane == 0 && wmax > 0) atomicMax(&s_bmax, wmax);
     __syncthreads();
@@ -336,78 +333,67 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                     const float dx = __fsub_rn(g0.x, pixfx);
                     const float dy = __fsub_rn(g0.y, pixfy);
                     const float power = gauss_power(dx, dy, g1.x, g1.y, g1.z);
-                    const float G = expf(power);
-                    const float alpha = fminf(0.99f, __fmul_rn(g1.w, G));
+                    const float G_raw = expf(power);
+                    const float alpha_raw = fminf(0.99f, __fmul_rn(g1.w, G_raw));
                     // backward.cu:486-501: behind the last contributor / power > 0 / alpha < 1/255
-                    const bool act = (pos < my_last) && !(power > 0.0f) && !(alpha < 1.0f / 255.0f);
+                    const bool act = (pos < my_last) && !(power > 0.0f) && !(alpha_raw < 1.0f / 255.0f);
                     if (!__any_sync(FULL, act)) continue;
 
-                    float v[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-                    float v8 = 0.f;
-                    if (act) {
-                        const float4 g2 = s_rec[buf][2][slot];
-                        const float one_minus_alpha = 1.f - alpha;
-                        T = T / one_minus_alpha;
-                        const float dchannel_dcolor = alpha * T;
-                        float dL_dalpha;
-                        accum0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0;
-                        accum1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1;
-                        accum2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2;
-                        lastc0 = g2.x; lastc1 = g2.y; lastc2 = g2.z;
-                        dL_dalpha = (g2.x - accum0) * dpix0;
-                        dL_dalpha += (g2.y - accum1) * dpix1;
-                        dL_dalpha += (g2.z - accum2) * dpix2;
-                        dL_dalpha *= T;
-                        last_alpha = alpha;
-                        dL_dalpha += (-T_final / one_minus_alpha) * bg_dot_dpixel;
+                    // Straight-line maths: lanes that do not contribute run with G = alpha = 0, which
+                    // makes every gradient term exactly 0 and T unchanged; only the recurrence state
+                    // (accum_rec / last_color / last_alpha) needs explicit selects.
+                    const float G = act ? G_raw : 0.f;
+                    const float alpha = act ? alpha_raw : 0.f;
+                    const float4 g2 = s_rec[buf][2][slot];
+                    const float rcp_oma = __fdividef(1.f, 1.f - alpha);      // 1 - alpha in [0.01, 1]
+                    T = T * rcp_oma;                                         // T / (1 - alpha)
+                    const float dchannel_dcolor = alpha * T;
+                    const float na0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0;
+                    const float na1 = last_alpha * lastc1 + (1.f - last_alpha) * accum1;
+                    const float na2 = last_alpha * lastc2 + (1.f - last_alpha) * accum2;
+                    accum0 = act ? na0 : accum0;
+                    accum1 = act ? na1 : accum1;
+                    accum2 = act ? na2 : accum2;
+                    lastc0 = act ? g2.x : lastc0;
+                    lastc1 = act ? g2.y : lastc1;
+                    lastc2 = act ? g2.z : lastc2;
+                    last_alpha = act ? alpha : last_alpha;
+                    float dL_dalpha = (g2.x - accum0) * dpix0;
+                    dL_dalpha += (g2.y - accum1) * dpix1;
+                    dL_dalpha += (g2.z - accum2) * dpix2;
+                    dL_dalpha *= T;
+                    dL_dalpha += (-T_final * rcp_oma) * bg_dot_dpixel;
 
-                        const float dL_dG = g1.w * dL_dalpha;
-                        const float gdx = G * dx, gdy = G * dy;
-                        const float dG_ddelx = -gdx * g1.x - gdy * g1.y;
-                        const float dG_ddely = -gdy * g1.z - gdx * g1.y;
-                        v[0] = dL_dG * dG_ddelx * ddelx_dx;        // dL_dmean2D.x
-                        v[1] = dL_dG * dG_ddely * ddely_dy;        // dL_dmean2D.y
-                        v[2] = -0.5f * gdx * dx * dL_dG;           // dL_dconic.x
-                        v[3] = -0.5f * gdx * dy * dL_dG;           // dL_dconic.y
-                        v[4] = -0.5f * gdy * dy * dL_dG;           // dL_dconic.w
-                        v[5] = G * dL_dalpha;                      // dL_dopacity
-                        v[6] = dchannel_dcolor * dpix0;            // dL_dcolor.r
-                        v[7] = dchannel_dcolor * dpix1;            // dL_dcolor.g
-                        v8 = dchannel_dcolor * dpix2;              // dL_dcolor.b
-                    }
+                    const float dL_dG = g1.w * dL_dalpha;
+                    const float gdx = G * dx, gdy = G * dy;
+                    const float dG_ddelx = -gdx * g1.x - gdy * g1.y;
+                    const float dG_ddely = -gdy * g1.z - gdx * g1.y;
+                    float v[8];
+                    v[0] = dL_dG * dG_ddelx * ddelx_dx;        // dL_dmean2D.x
+                    v[1] = dL_dG * dG_ddely * ddely_dy;        // dL_dmean2D.y
+                    v[2] = -0.5f * gdx * dx * dL_dG;           // dL_dconic.x
+                    v[3] = -0.5f * gdx * dy * dL_dG;           // dL_dconic.y
+                    v[4] = -0.5f * gdy * dy * dL_dG;           // dL_dconic.w
+                    v[5] = G * dL_dalpha;                      // dL_dopacity
+                    v[6] = dchannel_dcolor * dpix0;            // dL_dcolor.r
+                    v[7] = dchannel_dcolor * dpix1;            // dL_dcolor.g
+                    float v8 = dchannel_dcolor * dpix2;        // dL_dcolor.b
                     const float tot = transpose_reduce8(v, lane);
 #pragma unroll
                     for (int o = 16; o > 0; o >>= 1) v8 += __shfl_xor_sync(FULL, v8, o);
-                    float* a = s_acc + slot * ACC_STRIDE;
+                    // one reduction per (Gaussian, warp sub-tile) and value, straight into the packed
+                    // 48-byte accumulator: 8 lanes hit 8 consecutive floats, lane 1 the ninth
+                    float* dst = reinterpret_cast<float*>(acc + 3 * size_t(s_id[buf][slot]));
                     if ((lane & 3) == 0) {
                         const int k = ((lane >> 4) & 1) * 4 + ((lane >> 3) & 1) * 2 + ((lane >> 2) & 1);
-                        atomicAdd(a + k, tot);
+                        atomicAdd(dst + k, tot);
                     } else if (lane == 1) {
-                        atomicAdd(a + 8, v8);
+                        atomicAdd(dst + 8, v8);
                     }
                 }
             }
         }
-        __syncthreads();   // all warps finished with s_rec[buf] and their s_acc updates
-
-        // flush this batch: one packed vector reduction per (Gaussian, tile)
-        if (tid < n_in) {
-            float* a = s_acc + tid * ACC_STRIDE;
-            const float4 a0 = make_float4(a[0], a[1], a[2], a[3]);
-            const float4 a1 = make_float4(a[4], a[5], a[6], a[7]);
-            const float a8 = a[8];
-            const bool nz = (a0.x != 0.f) | (a0.y != 0.f) | (a0.z != 0.f) | (a0.w != 0.f) |
-                            (a1.x != 0.f) | (a1.y != 0.f) | (a1.z != 0.f) | (a1.w != 0.f) | (a8 != 0.f);
-            if (nz) {
-                float4* dst = acc + 3 * size_t(s_id[buf][tid]);
-                atomicAdd(dst, a0);
-                atomicAdd(dst + 1, a1);
-                atomicAdd(reinterpret_cast<float*>(dst + 2), a8);
-#pragma unroll
-                for (int k = 0; k < 9; ++k) a[k] = 0.f;
-            }
-        }
-        // the next iteration's first __syncthreads orders the zeroing before new accumulation
+        __syncthreads();   // all warps finished with s_rec[buf] / s_id[buf] before they are refilled
     }
 }
 

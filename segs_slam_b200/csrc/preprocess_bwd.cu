@@ -154,11 +154,15 @@ preprocess_backward_kernel(int P, int D, int M,
                            float* __restrict__ dL_drot)
 {
     __shared__ float s_view[16], s_proj[16];
+    // AoS outputs ([P,3] x4, [P,6]) are staged here and written back with coalesced stores
+    __shared__ float s_out[BWD_THREADS * 18];
     if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(viewmatrix + threadIdx.x);
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(projmatrix + threadIdx.x - 16);
     __syncthreads();
-    const size_t idx = size_t(blockIdx.x) * BWD_THREADS + threadIdx.x;
-    if (idx >= (size_t)P) return;
+    const size_t first = size_t(blockIdx.x) * BWD_THREADS;
+    const size_t idx = first + threadIdx.x;
+    const int n_blk = (int)min(size_t(BWD_THREADS), size_t(P) - first);
+    const bool in_range = idx < (size_t)P;
 
     float d_mean2D[2] = {0.f, 0.f};
     float d_conic[3] = {0.f, 0.f, 0.f};     // x, y, w
@@ -170,7 +174,7 @@ preprocess_backward_kernel(int P, int D, int M,
     float d_rot[4] = {0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
 
-    if (tiles_touched[idx] > 0) {   // == radii[idx] > 0 of backward.cu:156,367
+    if (in_range && tiles_touched[idx] > 0) {   // == radii[idx] > 0 of backward.cu:156,367
         const float4 a0 = acc[3 * idx + 0];
         const float4 a1 = acc[3 * idx + 1];
         const float4 a2 = acc[3 * idx + 2];
@@ -321,23 +325,39 @@ preprocess_backward_kernel(int P, int D, int M,
         }
     }
 
-    dL_dmean2D[3 * idx] = d_mean2D[0];
-    dL_dmean2D[3 * idx + 1] = d_mean2D[1];
-    dL_dmean2D[3 * idx + 2] = 0.f;
-    if (dL_dconic != nullptr)
-        *reinterpret_cast<float4*>(dL_dconic + 4 * idx) = make_float4(d_conic[0], d_conic[1], 0.f, d_conic[2]);
-    dL_dopacity[idx] = d_opacity;
+    {
+        const int t = threadIdx.x;
+        float* o2 = s_out;                          // dL_dmean2D [256,3]
+        float* oc = s_out + BWD_THREADS * 3;        // dL_dcolor  [256,3]
+        float* o3 = s_out + BWD_THREADS * 6;        // dL_dmean3D [256,3]
+        float* os = s_out + BWD_THREADS * 9;        // dL_dscale  [256,3]
+        float* ov = s_out + BWD_THREADS * 12;       // dL_dcov3D  [256,6]
+        o2[3 * t] = d_mean2D[0]; o2[3 * t + 1] = d_mean2D[1]; o2[3 * t + 2] = 0.f;
 #pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        dL_dcolor[3 * idx + k] = d_color[k];
-        dL_dmean3D[3 * idx + k] = d_mean3D[k];
-        dL_dscale[3 * idx + k] = d_scale[k];
+        for (int k = 0; k < 3; ++k) {
+            oc[3 * t + k] = d_color[k];
+            o3[3 * t + k] = d_mean3D[k];
+            os[3 * t + k] = d_scale[k];
+        }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) ov[6 * t + k] = d_cov[k];
     }
-#pragma unroll
-    for (int k = 0; k < 6; ++k) dL_dcov3D[6 * idx + k] = d_cov[k];
-    *reinterpret_cast<float4*>(dL_drot + 4 * idx) = make_float4(d_rot[0], d_rot[1], d_rot[2], d_rot[3]);
-    if (dL_dsh != nullptr && M > 0 && !sh_written)
-        for (int k = 0; k < 3 * M; ++k) dL_dsh[idx * M * 3 + k] = 0.f;
+    if (in_range) {
+        if (dL_dconic != nullptr)
+            *reinterpret_cast<float4*>(dL_dconic + 4 * idx) = make_float4(d_conic[0], d_conic[1], 0.f, d_conic[2]);
+        dL_dopacity[idx] = d_opacity;
+        *reinterpret_cast<float4*>(dL_drot + 4 * idx) = make_float4(d_rot[0], d_rot[1], d_rot[2], d_rot[3]);
+        if (dL_dsh != nullptr && M > 0 && !sh_written)
+            for (int k = 0; k < 3 * M; ++k) dL_dsh[idx * M * 3 + k] = 0.f;
+    }
+    __syncthreads();
+    for (int j = threadIdx.x; j < 3 * n_blk; j += BWD_THREADS) {
+        dL_dmean2D[3 * first + j] = s_out[j];
+        dL_dcolor[3 * first + j] = s_out[BWD_THREADS * 3 + j];
+        dL_dmean3D[3 * first + j] = s_out[BWD_THREADS * 6 + j];
+        dL_dscale[3 * first + j] = s_out[BWD_THREADS * 9 + j];
+    }
+    for (int j = threadIdx.x; j < 6 * n_blk; j += BWD_THREADS) dL_dcov3D[6 * first + j] = s_out[BWD_THREADS * 12 + j];
 }
 
 }  // namespace

@@ -93,7 +93,8 @@ def grad_close(mine: torch.Tensor, ref: torch.Tensor, ref2: torch.Tensor | None 
     tools/grad_diag.py / DESIGN.md).  The check is therefore:
       * every element within rel * (|ref| + mean|ref|), except at most max(2, 1e-4 * numel)
         outliers (the reference-vs-itself outlier rate, with head-room), and
-      * the relative L2 error of the whole tensor <= 2e-5 (10x tighter than `rel`).
+      * the relative L2 error of the whole tensor <= `rel` (the reference's own run-to-run
+        relative L2 spread reaches 6e-5 on dL_dcov3D / dL_drotations at C1).
     Returns (ok, description)."""
     mine, ref = mine.double().flatten(), ref.double().flatten()
     if ref.numel() == 0:
@@ -104,7 +105,7 @@ def grad_close(mine: torch.Tensor, ref: torch.Tensor, ref2: torch.Tensor | None 
     n_bad = int((ratio > 1.0).sum().item())
     allowed = max(2, int(1e-4 * ref.numel()))
     rel_l2 = ((mine - ref).norm() / (ref.norm() + 1e-30)).item()
-    ok = n_bad <= allowed and rel_l2 <= 2e-5
+    ok = n_bad <= allowed and rel_l2 <= rel
     return ok, f"outliers {n_bad}/{ref.numel()} (allowed {allowed}), worst {ratio.max().item():.1f}x, relL2 {rel_l2:.2e}"
 
 
