@@ -209,8 +209,7 @@ int segs_profile_read(float* ms /* [SEGS_PROFILE_STAGES] */);
  * buffers produced by segs_raster_forward for the given (P, R, width, height).
  * Sections: "depths" f32[P], "tiles_touched" u32[P], "rect" u16[P,4] (x0,y0,x1,y1),
  * "rec" f32[P,12] (x,y,hx,hy | conic.x,conic.y,conic.z,opacity | r,g,b,depth),
- * "cov3D" f32[6,P] (planes), "depth_order" u32[P], "point_offsets" u32[P] (exclusive, in
- * depth order), "point_list" u32[R], "tile_ids" u32[R] (sorted), "ranges" u32[T,2],
+ * "cov3D" f32[6,P] (planes), "depth_order" u32[P], "point_list" u32[R], "ranges" u32[T,2],
  * "final_T" f32[N], "n_contrib" u32[N]. */
 int segs_buffer_section(
     const char* name,

@@ -1,25 +1,29 @@
-// Depth ordering, instance emission, tile binning and tile ranges for sm_100a
-// (SURVEY §8 rows F2-F6).
+// Depth ordering and tile binning for sm_100a.
 //
 // Replaces cub::DeviceScan::InclusiveSum, duplicateWithKeys, the 64-bit-key
 // cub::DeviceRadixSort::SortPairs and identifyTileRanges of the reference
 // (cuda_rasterizer/rasterizer_impl.cu:70-138, 276-318).
 //
-// The reference sorts R (Gaussian x tile) instances by a 64-bit key  tile<<32 | depth_bits
-// with a stable LSD radix sort over 32+msb(T) bits (6 CUB passes of 24 B/instance at C2).
-// Here the same total order (tile, depth_bits, Gaussian index) is produced as
-//   1. a stable radix sort of the P Gaussians by depth_bits (4 passes over 8 B/Gaussian,
-//      P is ~8x smaller than R),
-//   2. emission of the instances in that depth order (instances of one Gaussian are
-//      row-major over its tile rectangle, as in duplicateWithKeys),
-//   3. a stable radix sort of the instances by tile id only: ceil(log256(T)) passes of
-//      8 B/instance (2 passes for every image up to 4096x4096).
-// Stability of each step makes ties resolve by ascending Gaussian index, exactly like the
-// reference's single stable sort, so point_list and ranges are bit-identical.
+// The reference materialises R (Gaussian x tile) 12-byte instances and sorts them by the
+// 64-bit key  tile<<32 | depth_bits  with a stable LSD radix sort (6 CUB passes, ~150 B of
+// traffic per instance).  The same total order (tile, depth_bits, Gaussian index) is produced
+// here WITHOUT sorting the R instances, by hierarchical binning:
 //
-// Radix pass = histogram kernel (per-CTA digit counts, bin-major) + one CTA per bin that
-// turns them into global scatter bases + a scatter kernel that ranks with warp
-// __match_any_sync (stable, no atomics on the ranking path).
+//   0. a stable 4-pass radix sort of the P Gaussians by depth_bits (P is ~8x smaller than R);
+//   1. coarse level: the image is cut into super-tiles of SxS tiles (S a power of two chosen
+//      so that there are <= 256 super-tiles).  The depth-ordered Gaussians are expanded into
+//      (super-tile, Gaussian) candidates (R' ~ 0.25 R) and ONE stable radix pass on the
+//      super-tile id groups them: every super-tile now has its depth-ordered candidate list;
+//   2. fine level: one CTA per super-tile, one warp per tile.  The CTA streams its candidate
+//      list through shared memory; each warp tests 32 candidates per step against its tile
+//      and stream-compacts the hits with a ballot — compaction preserves the list order, so
+//      every tile's list is in (depth_bits, Gaussian index) order, exactly the reference's
+//      sorted order, bit for bit.  A count pass + a scan over the T tile counts gives
+//      `ranges`; the write pass emits point_list (the only R-sized traffic: 4 B/instance).
+//
+// Radix pass (depth sort, coarse pass, kNN Morton sort) = histogram kernel (per-CTA digit
+// counts, bin-major) + one CTA per bin turning them into scatter bases + a scatter kernel that
+// ranks with warp __match_any_sync (stable, no atomics on the ranking path).
 #include "common.cuh"
 
 namespace segs {
@@ -40,10 +44,16 @@ radix_hist_kernel(const uint32_t* __restrict__ key_in, size_t n, int shift, int 
     hist[threadIdx.x] = 0;
     __syncthreads();
     const size_t base = size_t(blockIdx.x) * SORT_TILE;
+    uint32_t k[SORT_ITEMS];
 #pragma unroll
     for (int i = 0; i < SORT_ITEMS; ++i) {
         const size_t e = base + size_t(i) * SORT_THREADS + threadIdx.x;
-        if (e < n) atomicAdd(&hist[(__ldg(key_in + e) >> shift) & (RADIX_BINS - 1)], 1u);
+        k[i] = (e < n) ? __ldg(key_in + e) : 0u;
+    }
+#pragma unroll
+    for (int i = 0; i < SORT_ITEMS; ++i) {
+        const size_t e = base + size_t(i) * SORT_THREADS + threadIdx.x;
+        if (e < n) atomicAdd(&hist[(k[i] >> shift) & (RADIX_BINS - 1)], 1u);
     }
     __syncthreads();
     const uint32_t c = hist[threadIdx.x];
@@ -61,7 +71,6 @@ radix_scan_kernel(uint32_t* __restrict__ block_hist, const uint32_t* __restrict_
     const int bin = blockIdx.x;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
 
-    // base = sum of global_hist[0..bin)
     uint32_t v = (threadIdx.x < bin) ? global_hist[threadIdx.x] : 0u;
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
@@ -78,7 +87,6 @@ radix_scan_kernel(uint32_t* __restrict__ block_hist, const uint32_t* __restrict_
     for (int start = 0; start < nblocks; start += 256) {
         const int i = start + threadIdx.x;
         const uint32_t x = (i < nblocks) ? row[i] : 0u;
-        // inclusive warp scan
         uint32_t inc = x;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
@@ -162,11 +170,19 @@ radix_scatter_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__
 }
 
 // ---------------------------------------------------------------------------------------
-// exclusive scan of tiles_touched in depth order
+// exclusive scan of the coarse candidate counts in depth order
 // ---------------------------------------------------------------------------------------
 constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_ITEMS = 8;
 constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+
+// number of super-tiles a tile rectangle overlaps (0 for an empty rectangle)
+__device__ __forceinline__ uint32_t coarse_count(ushort4 rc, int sshift) {
+    if (rc.x >= rc.z || rc.y >= rc.w) return 0u;
+    const uint32_t sx0 = rc.x >> sshift, sx1 = (rc.z - 1) >> sshift;
+    const uint32_t sy0 = rc.y >> sshift, sy1 = (rc.w - 1) >> sshift;
+    return (sx1 - sx0 + 1) * (sy1 - sy0 + 1);
+}
 
 __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s_warp, uint32_t* total) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -191,23 +207,22 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_reduce_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
-                   int P, uint32_t* __restrict__ partials)
+coarse_reduce_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, int sshift,
+                     uint32_t* __restrict__ partials)
 {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < P) sum += __ldg(tiles_touched + __ldg(order + base + i));
+        if (base + i < P) sum += coarse_count(__ldg(rect + __ldg(order + base + i)), sshift);
     uint32_t total;
     block_exclusive_scan(sum, s_warp, &total);
     if (threadIdx.x == 0) partials[blockIdx.x] = total;
 }
 
-// single CTA: exclusive scan of the per-CTA sums; total -> counters[0]
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_partials_kernel(uint32_t* __restrict__ partials, int nb, uint32_t* __restrict__ counters)
+coarse_partials_kernel(uint32_t* __restrict__ partials, int nb)
 {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     uint32_t carry = 0;
@@ -219,101 +234,204 @@ scan_partials_kernel(uint32_t* __restrict__ partials, int nb, uint32_t* __restri
         if (i < nb) partials[i] = carry + ex;
         carry += total;
     }
-    if (threadIdx.x == 0) counters[0] = carry;
 }
 
+// scan + emission fused: candidate j of depth-ordered Gaussian k goes to offsets[k] + j
+// (row-major over its super-tile rectangle), key = super-tile id, value = Gaussian id
 __global__ void __launch_bounds__(SCAN_THREADS)
-scan_apply_kernel(const uint32_t* __restrict__ order, const uint32_t* __restrict__ tiles_touched,
-                  int P, const uint32_t* __restrict__ partials, uint32_t* __restrict__ offsets)
+coarse_emit_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, int sshift,
+                   int sgrid_x, const uint32_t* __restrict__ partials, uint32_t* __restrict__ key_out,
+                   uint32_t* __restrict__ val_out)
 {
     __shared__ uint32_t s_warp[SCAN_THREADS / 32];
     const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t c[SCAN_ITEMS];
+    uint32_t id[SCAN_ITEMS], c[SCAN_ITEMS];
+    ushort4 rc[SCAN_ITEMS];
     uint32_t sum = 0;
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        c[i] = (base + i < P) ? __ldg(tiles_touched + __ldg(order + base + i)) : 0u;
+        c[i] = 0;
+        if (base + i < P) {
+            id[i] = __ldg(order + base + i);
+            rc[i] = __ldg(rect + id[i]);
+            c[i] = coarse_count(rc[i], sshift);
+        }
         sum += c[i];
     }
     uint32_t total;
     uint32_t run = partials[blockIdx.x] + block_exclusive_scan(sum, s_warp, &total);
 #pragma unroll
     for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (base + i < P) offsets[base + i] = run;
-        run += c[i];
+        if (c[i]) {
+            const uint32_t sx0 = rc[i].x >> sshift, sx1 = (rc[i].z - 1) >> sshift;
+            const uint32_t sy0 = rc[i].y >> sshift, sy1 = (rc[i].w - 1) >> sshift;
+            for (uint32_t sy = sy0; sy <= sy1; ++sy)
+                for (uint32_t sx = sx0; sx <= sx1; ++sx) {
+                    key_out[run] = sy * (uint32_t)sgrid_x + sx;
+                    val_out[run] = id[i];
+                    ++run;
+                }
+        }
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// instance emission in depth order (duplicateWithKeys, rasterizer_impl.cu:70-111)
+// fine level: CTA = super-tile, warp = tile(s); ordered ballot compaction
 // ---------------------------------------------------------------------------------------
-// One warp per 32 consecutive depth-ordered Gaussians; the warp walks the flat range of
-// their instances so every store is a full coalesced 128-byte line regardless of how the
-// instance counts are distributed (one Gaussian covers 1..900+ tiles).
-constexpr int EMIT_THREADS = 256;
+constexpr int FINE_MAX_THREADS = 1024;
 
-__global__ void __launch_bounds__(EMIT_THREADS)
-emit_instances_kernel(int P, const uint32_t* __restrict__ order, const uint32_t* __restrict__ offsets,
-                      const uint32_t* __restrict__ tiles_touched, const ushort4* __restrict__ rect,
-                      int grid_x, uint32_t* __restrict__ tile_out, uint32_t* __restrict__ idx_out)
+__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
+    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// The candidate list is streamed in batches of blockDim.x candidates, double-buffered: the ids of
+// batch b+2 are prefetched into registers and the 8-byte rectangles of batch b+1 are gathered
+// with cp.async while the warps test batch b.
+template <bool WRITE>
+__global__ void __launch_bounds__(FINE_MAX_THREADS)
+fine_bin_kernel(int sshift, int sgrid_x, int grid_x, int grid_y, const uint32_t* __restrict__ coarse_hist,
+                const uint32_t* __restrict__ cand_id, const ushort4* __restrict__ rect,
+                uint32_t* __restrict__ tile_counts, const uint2* __restrict__ ranges,
+                uint32_t* __restrict__ point_list)
 {
-    const int lane = threadIdx.x & 31;
-    const int gwarp = (blockIdx.x * EMIT_THREADS + threadIdx.x) >> 5;
-    const int k = gwarp * 32 + lane;
-    uint32_t id = 0, off = 0, cnt = 0;
-    ushort4 rc = make_ushort4(0, 0, 0, 0);
-    if (k < P) {
-        id = __ldg(order + k);
-        off = __ldg(offsets + k);
-        cnt = __ldg(tiles_touched + id);
-        rc = __ldg(rect + id);
-    }
-    const uint32_t begin = __shfl_sync(FULL, off, 0);
-    const uint32_t end = __reduce_max_sync(FULL, (k < P) ? off + cnt : 0u);
-    // lanes past P must never win the search below
-    if (k >= P) off = 0xFFFFFFFFu;
-    for (uint32_t sb = begin; sb < end; sb += 32) {          // warp-uniform trip count
-        const uint32_t s = sb + lane;
-        // largest j with off_j <= s (offsets are non-decreasing over lanes).  Gaussians with
-        // cnt == 0 share their offset with the next one, so the LAST such lane owns s.
-        int j = 0;
+    extern __shared__ __align__(16) unsigned char s_fine[];
+    const int NT = blockDim.x;
+    ushort4* s_rect = reinterpret_cast<ushort4*>(s_fine);                  // [2][NT]
+    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_fine + size_t(2) * NT * sizeof(ushort4));   // [2][NT]
+    __shared__ uint32_t s_red[32];
+    __shared__ uint32_t s_start, s_len;
+    const int st = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
+
+    // candidate range of this super-tile = prefix of the coarse histogram (<= 256 bins)
+    {
+        uint32_t v = 0;
+        for (int i = tid; i < st; i += blockDim.x) v += coarse_hist[i];
 #pragma unroll
-        for (int step = 16; step > 0; step >>= 1) {
-            const uint32_t o = __shfl_sync(FULL, off, (j + step) & 31);
-            if (o <= s) j += step;                           // j + step <= 31 by construction
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
+        if (lane == 0) s_red[warp] = v;
+        __syncthreads();
+        if (tid == 0) {
+            uint32_t t = 0;
+            for (int w = 0; w < nwarps; ++w) t += s_red[w];
+            s_start = t;
+            s_len = coarse_hist[st];
         }
-        const uint32_t oj = __shfl_sync(FULL, off, j);
-        const uint32_t idj = __shfl_sync(FULL, id, j);
-        const uint32_t x0 = __shfl_sync(FULL, (uint32_t)rc.x, j);
-        const uint32_t y0 = __shfl_sync(FULL, (uint32_t)rc.y, j);
-        const uint32_t x1 = __shfl_sync(FULL, (uint32_t)rc.z, j);
-        if (s < end) {
-            const uint32_t w = x1 - x0;
-            const uint32_t local = s - oj;
-            const uint32_t ty = local / w, tx = local - ty * w;
-            tile_out[s] = (y0 + ty) * (uint32_t)grid_x + (x0 + tx);
-            idx_out[s] = idj;
+        __syncthreads();
+    }
+    const uint32_t clen = s_len;
+    const uint32_t* list = cand_id + s_start;
+    const int nbatches = (int)((clen + NT - 1) / NT);
+
+    // tiles of this super-tile handled by this warp: local index li = warp, warp + nwarps, ...
+    // (at most MAX_TPW per warp; kept in registers, all loops over them are fully unrolled)
+    const int S = 1 << sshift;
+    const int stx = (st % sgrid_x) << sshift, sty = (st / sgrid_x) << sshift;
+    constexpr int MAX_TPW = 8;
+    uint32_t run[MAX_TPW];
+    unsigned ttx[MAX_TPW], tty[MAX_TPW];
+    bool live[MAX_TPW];
+#pragma unroll
+    for (int q = 0; q < MAX_TPW; ++q) {
+        const int li = warp + q * nwarps;
+        const int tx = stx + (li & (S - 1)), ty = sty + (li >> sshift);
+        live[q] = li < S * S && tx < grid_x && ty < grid_y;
+        ttx[q] = (unsigned)tx; tty[q] = (unsigned)ty;
+        run[q] = (WRITE && live[q]) ? ranges[ty * grid_x + tx].x : 0u;
+    }
+    const uint32_t lt = (1u << lane) - 1u;
+
+    // pipeline prologue: batch 0 rectangles in flight, batch 1 ids in registers
+    uint32_t id_next = ((uint32_t)tid < clen) ? __ldg(list + tid) : 0u;
+    if ((uint32_t)tid < clen) {
+        s_id[tid] = id_next;
+        cp_async8(&s_rect[tid], rect + id_next);
+    }
+    cp_async_commit_group();
+    id_next = ((uint32_t)(NT + tid) < clen) ? __ldg(list + NT + tid) : 0u;
+
+    for (int b = 0; b < nbatches; ++b) {
+        const int buf = b & 1;
+        const uint32_t n_in = min((uint32_t)NT, clen - (uint32_t)b * NT);
+        if (b + 1 < nbatches) {
+            const uint32_t p = (uint32_t)(b + 1) * NT + tid;
+            if (p < clen) {
+                s_id[(buf ^ 1) * NT + tid] = id_next;
+                cp_async8(&s_rect[(buf ^ 1) * NT + tid], rect + id_next);
+            }
+            cp_async_commit_group();
+            const uint32_t p2 = (uint32_t)(b + 2) * NT + tid;
+            id_next = (p2 < clen) ? __ldg(list + p2) : 0u;
+            cp_async_wait_group<1>();
+        } else {
+            cp_async_wait_group<0>();
         }
+        __syncthreads();
+        const ushort4* b_rect = s_rect + buf * NT;
+        const uint32_t* b_id = s_id + buf * NT;
+        for (uint32_t c = 0; c < n_in; c += 32) {
+            const uint32_t slot = c + lane;
+            ushort4 rc = make_ushort4(1, 1, 0, 0);      // empty rectangle: never hits
+            uint32_t id = 0;
+            if (slot < n_in) {
+                rc = b_rect[slot];
+                if (WRITE) id = b_id[slot];
+            }
+#pragma unroll
+            for (int q = 0; q < MAX_TPW; ++q) {
+                if (live[q]) {                              // warp-uniform
+                    const bool hit = (ttx[q] >= rc.x) && (ttx[q] < rc.z) && (tty[q] >= rc.y) && (tty[q] < rc.w);
+                    const unsigned mask = __ballot_sync(FULL, hit);
+                    if (WRITE && hit) point_list[run[q] + __popc(mask & lt)] = id;
+                    run[q] += __popc(mask);
+                }
+            }
+        }
+        __syncthreads();   // everyone is done with this buffer before it is refilled
+    }
+    if (!WRITE && lane == 0) {
+#pragma unroll
+        for (int q = 0; q < MAX_TPW; ++q)
+            if (live[q]) tile_counts[tty[q] * grid_x + ttx[q]] = run[q];
     }
 }
 
-// identifyTileRanges (rasterizer_impl.cu:116-138) on the sorted 32-bit tile ids
-__global__ void __launch_bounds__(256)
-tile_ranges_kernel(int L, const uint32_t* __restrict__ tile_sorted, uint2* __restrict__ ranges)
+// single CTA: exclusive scan of the T tile counts -> ranges (rasterizer_impl.cu:116-138:
+// [first, last+1), {0,0} for an empty tile); total -> *total_out
+__global__ void __launch_bounds__(1024)
+tile_scan_kernel(int T, const uint32_t* __restrict__ tile_counts, uint2* __restrict__ ranges,
+                 uint32_t* __restrict__ total_out)
 {
-    const int idx = blockIdx.x * 256 + threadIdx.x;
-    if (idx >= L) return;
-    const uint32_t cur = __ldg(tile_sorted + idx);
-    if (idx == 0) {
-        ranges[cur].x = 0;
-    } else {
-        const uint32_t prev = __ldg(tile_sorted + idx - 1);
-        if (cur != prev) {
-            ranges[prev].y = idx;
-            ranges[cur].x = idx;
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x == 0) s_carry = 0;
+    __syncthreads();
+    for (int start = 0; start < T; start += 1024) {
+        const int t = start + threadIdx.x;
+        const uint32_t total = (t < T) ? tile_counts[t] : 0u;
+        uint32_t inc = total;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(FULL, inc, o);
+            if (lane >= o) inc += y;
         }
+        if (lane == 31) s_warp[warp] = inc;
+        __syncthreads();
+        uint32_t woff = 0;
+        for (int w = 0; w < warp; ++w) woff += s_warp[w];
+        const uint32_t carry = s_carry;
+        const uint32_t first = carry + woff + inc - total;
+        if (t < T) ranges[t] = total ? make_uint2(first, first + total) : make_uint2(0u, 0u);
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = carry + woff + inc;
+        __syncthreads();
     }
-    if (idx == L - 1) ranges[cur].y = L;
+    if (threadIdx.x == 0 && total_out) *total_out = s_carry;
 }
 
 }  // namespace
@@ -343,38 +461,60 @@ int launch_depth_order(int P, GeomState& g, cudaStream_t stream)
     if ((rc = radix_pass(g.key_b, g.key_a, g.val_b, g.val_a, P, 8, g.block_hist, g.global_hist, stream))) return rc;
     if ((rc = radix_pass(g.key_a, g.key_b, g.val_a, g.val_b, P, 16, g.block_hist, g.global_hist, stream))) return rc;
     if ((rc = radix_pass(g.key_b, g.key_a, g.val_b, g.val_a, P, 24, g.block_hist, g.global_hist, stream))) return rc;
-    // exclusive offsets of tiles_touched in depth order; total -> counters[0]
-    const int nb = (P + SCAN_TILE - 1) / SCAN_TILE;
-    scan_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.tiles_touched, P, g.scan_partials);
-    SEGS_LAUNCH_CHECK();
-    scan_partials_kernel<<<1, SCAN_THREADS, 0, stream>>>(g.scan_partials, nb, g.counters);
-    SEGS_LAUNCH_CHECK();
-    scan_apply_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.tiles_touched, P, g.scan_partials, g.offsets);
-    SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
 
-int launch_binning(int P, int R, const ViewParams& vp, GeomState& g, BinningState& b,
+// Super-tile side (in tiles, power of two) such that there are at most 256 super-tiles, i.e.
+// one 8-bit radix pass groups the candidates.  Deterministic in the tile grid.
+BinningPlan plan_binning(int grid_x, int grid_y)
+{
+    BinningPlan p;
+    p.sshift = 1;
+    while (((grid_x + (1 << p.sshift) - 1) >> p.sshift) * ((grid_y + (1 << p.sshift) - 1) >> p.sshift) > RADIX_BINS)
+        ++p.sshift;
+    p.sgrid_x = (grid_x + (1 << p.sshift) - 1) >> p.sshift;
+    p.sgrid_y = (grid_y + (1 << p.sshift) - 1) >> p.sshift;
+    return p;
+}
+
+int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, BinningState& b,
                    ImageState& img, cudaStream_t stream)
 {
     const int T = vp.grid_x * vp.grid_y;
-    SEGS_CUDA_CHECK(cudaMemsetAsync(img.ranges, 0, size_t(T) * sizeof(uint2), stream));
-    if (R == 0) return SEGS_OK;
-    const int warps = (P + 31) / 32;
-    const int blocks = (warps * 32 + EMIT_THREADS - 1) / EMIT_THREADS;
-    emit_instances_kernel<<<blocks, EMIT_THREADS, 0, stream>>>(P, g.val_a, g.offsets, g.tiles_touched, g.rect,
-                                                             vp.grid_x, b.tile_a, b.idx_a);
-    SEGS_LAUNCH_CHECK();
-    const int passes = num_tile_passes((uint32_t)T);
-    uint32_t *ka = b.tile_a, *kb = b.tile_b, *va = b.idx_a, *vb = b.idx_b;
-    for (int p = 0; p < passes; ++p) {
-        int rc = radix_pass(ka, kb, va, vb, (size_t)R, 8 * p, b.block_hist, b.global_hist, stream);
-        if (rc) return rc;
-        uint32_t* t = ka; ka = kb; kb = t;
-        t = va; va = vb; vb = t;
+    if (R == 0) {
+        SEGS_CUDA_CHECK(cudaMemsetAsync(img.ranges, 0, size_t(T) * sizeof(uint2), stream));
+        return SEGS_OK;
     }
-    // sorted tile ids now in ka, point_list in va
-    tile_ranges_kernel<<<(R + 255) / 256, 256, 0, stream>>>(R, ka, img.ranges);
+    const BinningPlan pl = plan_binning(vp.grid_x, vp.grid_y);
+    if (pl.sshift > 4) { set_error("image too large for the two-level tile binning (%d x %d tiles)", vp.grid_x, vp.grid_y); return SEGS_ERR_INVALID_ARG; }
+
+    // coarse: expand depth-ordered Gaussians into (super-tile, id) candidates ...
+    const int nb = (P + SCAN_TILE - 1) / SCAN_TILE;
+    coarse_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.rect, P, pl.sshift, b.partials);
+    SEGS_LAUNCH_CHECK();
+    coarse_partials_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.partials, nb);
+    SEGS_LAUNCH_CHECK();
+    coarse_emit_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.rect, P, pl.sshift, pl.sgrid_x, b.partials,
+                                                        b.cand_key_a, b.cand_val_a);
+    SEGS_LAUNCH_CHECK();
+    // ... and group them by super-tile with one stable 8-bit pass (global_hist = candidates per super-tile)
+    int rc = radix_pass(b.cand_key_a, b.cand_key_b, b.cand_val_a, b.cand_val_b, (size_t)Rc, 0, b.block_hist,
+                        b.global_hist, stream);
+    if (rc) return rc;
+
+    // fine: per tile count -> ranges -> ordered write
+    const int nst = pl.sgrid_x * pl.sgrid_y;
+    const int tiles_per_st = 1 << (2 * pl.sshift);
+    // warps per CTA: each warp owns up to 8 tiles of the super-tile
+    const int warps = tiles_per_st <= 4 ? 4 : (tiles_per_st <= 128 ? 16 : 32);
+    const size_t fine_smem = size_t(2) * warps * 32 * (sizeof(ushort4) + sizeof(uint32_t));
+    fine_bin_kernel<false><<<nst, warps * 32, fine_smem, stream>>>(pl.sshift, pl.sgrid_x, vp.grid_x, vp.grid_y, b.global_hist,
+                                                          b.cand_val_b, g.rect, b.tile_counts, nullptr, nullptr);
+    SEGS_LAUNCH_CHECK();
+    tile_scan_kernel<<<1, 1024, 0, stream>>>(T, b.tile_counts, img.ranges, g.counters + 3);
+    SEGS_LAUNCH_CHECK();
+    fine_bin_kernel<true><<<nst, warps * 32, fine_smem, stream>>>(pl.sshift, pl.sgrid_x, vp.grid_x, vp.grid_y, b.global_hist,
+                                                         b.cand_val_b, g.rect, nullptr, img.ranges, b.point_list);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }

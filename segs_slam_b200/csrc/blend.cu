@@ -404,8 +404,7 @@ int launch_blend_forward(const ViewParams& vp, const GeomState& g, const Binning
                          cudaStream_t stream)
 {
     const int T = vp.grid_x * vp.grid_y;
-    const int passes = num_tile_passes((uint32_t)T);
-    const uint32_t* point_list = (passes & 1) ? b.idx_b : b.idx_a;
+    const uint32_t* point_list = b.point_list;
     blend_forward_kernel<<<T, TILE_PIX, 0, stream>>>(img.ranges, point_list, vp.W, vp.H, vp.grid_x, g.rec,
                                                     background, img.final_T, img.n_contrib, out_color);
     SEGS_LAUNCH_CHECK();
@@ -417,8 +416,7 @@ int launch_blend_backward(const ViewParams& vp, const GeomState& g, const Binnin
                           const float* dL_dpix, cudaStream_t stream)
 {
     const int T = vp.grid_x * vp.grid_y;
-    const int passes = num_tile_passes((uint32_t)T);
-    const uint32_t* point_list = (passes & 1) ? b.idx_b : b.idx_a;
+    const uint32_t* point_list = b.point_list;
     blend_backward_kernel<<<T, TILE_PIX, 0, stream>>>(img.ranges, point_list, vp.W, vp.H, vp.grid_x, g.rec,
                                                      background, img.final_T, img.n_contrib, dL_dpix, g.acc);
     SEGS_LAUNCH_CHECK();

@@ -40,24 +40,25 @@ GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
     g.key_b = c.take<uint32_t>(P);
     g.val_a = c.take<uint32_t>(P);
     g.val_b = c.take<uint32_t>(P);
-    g.offsets = c.take<uint32_t>(P);
     g.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(P));
     g.global_hist = c.take<uint32_t>(RADIX_BINS);
-    g.scan_partials = c.take<uint32_t>(P / 2048 + 2);
     g.counters = c.take<uint32_t>(8);
     if (bytes) *bytes = c.used(base) + 128;
     return g;
 }
 
-BinningState BinningState::carve(char* base, size_t R, size_t* bytes) {
+BinningState BinningState::carve(char* base, size_t R, size_t Rc, size_t P, size_t T, size_t* bytes) {
     Carver c(base);
     BinningState b;
-    b.tile_a = c.take<uint32_t>(R);
-    b.tile_b = c.take<uint32_t>(R);
-    b.idx_a = c.take<uint32_t>(R);
-    b.idx_b = c.take<uint32_t>(R);
-    b.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(R));
+    b.point_list = c.take<uint32_t>(R);      // first: the only section the backward reads
+    b.cand_key_a = c.take<uint32_t>(Rc);
+    b.cand_key_b = c.take<uint32_t>(Rc);
+    b.cand_val_a = c.take<uint32_t>(Rc);
+    b.cand_val_b = c.take<uint32_t>(Rc);
+    b.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(Rc));
     b.global_hist = c.take<uint32_t>(RADIX_BINS);
+    b.partials = c.take<uint32_t>(P / 2048 + 2);
+    b.tile_counts = c.take<uint32_t>(T);
     if (bytes) *bytes = c.used(base) + 128;
     return b;
 }
@@ -84,6 +85,7 @@ static ViewParams make_view(int width, int height, float tan_fovx, float tan_fov
     vp.focal_y = height / (2.0f * tan_fovy);
     vp.focal_x = width / (2.0f * tan_fovx);
     vp.scale_modifier = scale_modifier;
+    vp.sshift = plan_binning(vp.grid_x, vp.grid_y).sshift;
     return vp;
 }
 
@@ -96,6 +98,13 @@ static uint32_t* pinned_words() {
         }
     }
     return p;
+}
+
+// One event per host thread marking "num_rendered has landed in pinned memory".
+static cudaEvent_t readback_event() {
+    static thread_local cudaEvent_t ev = nullptr;
+    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    return ev;
 }
 
 // ---- optional per-stage timing ----------------------------------------------------------
@@ -210,28 +219,31 @@ int segs_raster_forward(
                                 colors_precomp, viewmatrix, projmatrix, cam_pos, vp, prefiltered != 0,
                                 radii, g, stream))) return rc;
     prof_end(0, stream);
+    // num_rendered (accumulated by the preprocess) sizes the binning buffer, so it has to reach
+    // the host (rasterizer_impl.cu:279-285) — but only the preprocess is waited for: the depth
+    // sort is already queued behind the copy and runs while the host allocates.
+    SEGS_CUDA_CHECK(cudaMemcpyAsync(host_words, g.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    cudaEvent_t ready = readback_event();
+    if (!ready) { set_error("cudaEventCreate failed"); return SEGS_ERR_CUDA; }
+    SEGS_CUDA_CHECK(cudaEventRecord(ready, stream));
     prof_begin(1, stream);
     if ((rc = launch_depth_order(P, g, stream))) return rc;
     prof_end(1, stream);
-
-    // num_rendered sizes the binning buffer, so it has to reach the host here
-    // (rasterizer_impl.cu:279-285).
-    SEGS_CUDA_CHECK(cudaMemcpyAsync(host_words, g.counters, 2 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
-    SEGS_CUDA_CHECK(cudaStreamSynchronize(stream));
-    const uint32_t R = host_words[0];
+    SEGS_CUDA_CHECK(cudaEventSynchronize(ready));
+    const uint32_t R = host_words[0], Rc = host_words[2];
     if (host_words[1] != 0) {
         set_error("Point is filtered although prefiltered is set. This shouldn't happen!");
         return SEGS_ERR_PREFILTERED;
     }
     if (R > 0x7FFFFFFFu) { set_error("num_rendered %u overflows int", R); return SEGS_ERR_INVALID_ARG; }
 
-    BinningState::carve(nullptr, R, &bin_bytes);
+    BinningState::carve(nullptr, R, Rc, P, T, &bin_bytes);
     char* bin_ptr = binning_alloc(binning_user, bin_bytes);
     if (!bin_ptr) { set_error("binning buffer allocation of %zu bytes failed", bin_bytes); return SEGS_ERR_ALLOC; }
-    BinningState b = BinningState::carve(bin_ptr, R, nullptr);
+    BinningState b = BinningState::carve(bin_ptr, R, Rc, P, T, nullptr);
 
     prof_begin(2, stream);
-    if ((rc = launch_binning(P, (int)R, vp, g, b, img, stream))) return rc;
+    if ((rc = launch_binning(P, (int)R, (int)Rc, vp, g, b, img, stream))) return rc;
     prof_end(2, stream);
     prof_begin(3, stream);
     if ((rc = launch_blend_forward(vp, g, b, img, background, out_color, stream))) return rc;
@@ -264,7 +276,7 @@ int segs_raster_backward(
     const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
     const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
     GeomState g = GeomState::carve(geom_buffer, P, nullptr);
-    BinningState b = BinningState::carve(binning_buffer, R, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, 0, P, T, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
     int rc;
     if (R > 0) {
@@ -344,9 +356,8 @@ int segs_buffer_section(const char* name, char* geom_buffer, char* binning_buffe
     const ViewParams vp = make_view(width, height, 1.f, 1.f, 1.f);
     const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
     GeomState g = GeomState::carve(geom_buffer, P, nullptr);
-    BinningState b = BinningState::carve(binning_buffer, R, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, 0, P, T, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
-    const int passes = num_tile_passes((uint32_t)T);
     const std::string n(name);
     auto out = [&](void* p, size_t sz) { *ptr = p; *bytes = sz; return SEGS_OK; };
     if (n == "depths") return out(g.depths, sizeof(float) * P);
@@ -355,9 +366,7 @@ int segs_buffer_section(const char* name, char* geom_buffer, char* binning_buffe
     if (n == "rec") return out(g.rec, sizeof(float4) * 3 * P);
     if (n == "cov3D") return out(g.cov3D, sizeof(float) * 6 * P);
     if (n == "depth_order") return out(g.val_a, sizeof(uint32_t) * P);
-    if (n == "point_offsets") return out(g.offsets, sizeof(uint32_t) * P);
-    if (n == "point_list") return out((passes & 1) ? b.idx_b : b.idx_a, sizeof(uint32_t) * R);
-    if (n == "tile_ids") return out((passes & 1) ? b.tile_b : b.tile_a, sizeof(uint32_t) * R);
+    if (n == "point_list") return out(b.point_list, sizeof(uint32_t) * R);
     if (n == "ranges") return out(img.ranges, sizeof(uint2) * T);
     if (n == "final_T") return out(img.final_T, sizeof(float) * N);
     if (n == "n_contrib") return out(img.n_contrib, sizeof(uint32_t) * N);

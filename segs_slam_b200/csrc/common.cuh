@@ -53,8 +53,9 @@ struct Carver {
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX_BINS = 1 << RADIX_BITS;
 constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 16;                       // items per thread per block
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 4096 elements per block
+constexpr int SORT_ITEMS = 4;                        // items per thread per block
+constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 1024 elements per block (P-sized sorts:
+                                                     // many small CTAs hide latency better)
 
 inline int sort_blocks(size_t n) { return int((n + SORT_TILE - 1) / SORT_TILE); }
 
@@ -78,22 +79,29 @@ struct GeomState {
     uint32_t* key_b;          // [P] depth-sort pong
     uint32_t* val_a;          // [P]
     uint32_t* val_b;          // [P]  -> depth order after 4 passes lives in val_a
-    uint32_t* offsets;        // [P] exclusive scan of tiles_touched in depth order
     uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(P)]
     uint32_t* global_hist;    // [RADIX_BINS]
-    uint32_t* scan_partials;  // [scan blocks + 1]
-    uint32_t* counters;       // [8]: 0 = num_rendered, 1 = error flag
+    uint32_t* counters;       // [8]: 0 = num_rendered (sum of tiles_touched), 1 = error flag,
+                              //      2 = number of coarse (super-tile, Gaussian) candidates,
+                              //      3 = num_rendered as seen by the tile scan (cross-check)
     static GeomState carve(char* base, size_t P, size_t* bytes);
 };
 
+// two-level tile binning (binning.cu): super-tiles of (1 << sshift)^2 tiles
+struct BinningPlan { int sshift, sgrid_x, sgrid_y; };
+BinningPlan plan_binning(int grid_x, int grid_y);
+
 struct BinningState {
-    uint32_t* tile_a;         // [R]
-    uint32_t* tile_b;         // [R]
-    uint32_t* idx_a;          // [R]
-    uint32_t* idx_b;          // [R]
-    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(R)]
-    uint32_t* global_hist;    // [RADIX_BINS]
-    static BinningState carve(char* base, size_t R, size_t* bytes);
+    uint32_t* point_list;     // [R]   Gaussian ids, tile-major, depth-minor
+    uint32_t* cand_key_a;     // [Rc]  super-tile id of each candidate (depth order)
+    uint32_t* cand_key_b;     // [Rc]
+    uint32_t* cand_val_a;     // [Rc]  Gaussian id of each candidate
+    uint32_t* cand_val_b;     // [Rc]  -> grouped by super-tile, depth order inside
+    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(Rc)]
+    uint32_t* global_hist;    // [RADIX_BINS] candidates per super-tile
+    uint32_t* partials;       // [scan blocks]
+    uint32_t* tile_counts;    // [T]
+    static BinningState carve(char* base, size_t R, size_t Rc, size_t P, size_t T, size_t* bytes);
 };
 
 struct ImageState {
@@ -103,13 +111,6 @@ struct ImageState {
     static ImageState carve(char* base, size_t N, size_t T, size_t* bytes);
 };
 
-inline int num_tile_passes(uint32_t num_tiles) {
-    // number of 8-bit digits needed to cover tile ids 0..num_tiles-1
-    int passes = 1;
-    while (passes < 4 && (uint64_t(1) << (RADIX_BITS * passes)) < num_tiles) ++passes;
-    return passes;
-}
-
 // ---- kernel launchers (one per translation unit) ------------------------------------
 struct ViewParams {
     int W, H;
@@ -117,6 +118,7 @@ struct ViewParams {
     float tan_fovx, tan_fovy;
     float focal_x, focal_y;
     float scale_modifier;
+    int sshift;               // log2 of the super-tile side in tiles (two-level binning)
 };
 
 int launch_preprocess(int P, int D, int M, const float* means3D, const float* scales,
@@ -141,10 +143,10 @@ int launch_project(int P, int D, int M, const float* means3D, const float* scale
                    const ViewParams& vp, bool prefiltered, float* out_rgb, float* points_image,
                    int* radii, cudaStream_t stream);
 
-// depth ordering of Gaussians + exclusive offsets + total (counters[0])
+// depth ordering of Gaussians (stable radix sort of (depth_bits, index))
 int launch_depth_order(int P, GeomState& g, cudaStream_t stream);
-// instance emission, tile radix passes, ranges
-int launch_binning(int P, int R, const ViewParams& vp, GeomState& g, BinningState& b,
+// chunked tile multisplit: point_list + ranges
+int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, BinningState& b,
                    ImageState& img, cudaStream_t stream);
 
 int launch_blend_forward(const ViewParams& vp, const GeomState& g, const BinningState& b,

@@ -265,7 +265,7 @@ preprocess_kernel(int P, int D, int M,
                   ushort4* __restrict__ rect, float4* __restrict__ rec, float* __restrict__ cov3D,
                   float4* __restrict__ acc, uint8_t* __restrict__ clamped,
                   uint32_t* __restrict__ sort_key, uint32_t* __restrict__ sort_val,
-                  uint32_t* __restrict__ err_flag,
+                  uint32_t* __restrict__ err_flag, uint32_t* __restrict__ num_rendered,
                   // Project outputs
                   float* __restrict__ out_rgb, float* __restrict__ points_image)
 {
@@ -284,10 +284,11 @@ preprocess_kernel(int P, int D, int M,
     __syncthreads();
 
     const int t = threadIdx.x;
-    if (t >= n) return;
-    const size_t idx = first + t;
+    const bool in_range = t < n;
+    const size_t idx = first + (in_range ? t : 0);
 
-    const float px = s_mean[3 * t], py = s_mean[3 * t + 1], pz = s_mean[3 * t + 2];
+    const float px = s_mean[3 * (in_range ? t : 0)], py = s_mean[3 * (in_range ? t : 0) + 1],
+                pz = s_mean[3 * (in_range ? t : 0) + 2];
 
     bool visible = false;
     Projected pr;
@@ -295,7 +296,9 @@ preprocess_kernel(int P, int D, int M,
 
     // in_frustum (auxiliary.h:140-166): only the near-plane test is live.
     const float depth = affine_row(s_view, 2, px, py, pz);
-    if (depth <= 0.2f) {
+    if (!in_range) {
+        // tail lanes of the last CTA: nothing to do, but stay for the warp-wide sum below
+    } else if (depth <= 0.2f) {
         if (prefiltered && err_flag != nullptr) atomicExch(err_flag, 1u);
     } else {
         if (cov3D_precomp != nullptr) {
@@ -307,6 +310,24 @@ preprocess_kernel(int P, int D, int M,
         }
         visible = project_gaussian(px, py, pz, c3, s_view, s_proj, vp, pr);
     }
+
+    if (MODE == Mode::Render) {
+        // num_rendered = sum of tiles_touched (what the reference gets from its inclusive scan,
+        // rasterizer_impl.cu:276-281): one atomic per warp
+        const uint32_t warp_tiles = __reduce_add_sync(0xFFFFFFFFu, visible ? pr.tiles : 0u);
+        // ... and the number of (super-tile, Gaussian) candidates of the two-level binning
+        uint32_t cand = 0;
+        if (visible) {
+            const int sh = vp.sshift;
+            cand = (((pr.x1 - 1) >> sh) - (pr.x0 >> sh) + 1) * (((pr.y1 - 1) >> sh) - (pr.y0 >> sh) + 1);
+        }
+        const uint32_t warp_cand = __reduce_add_sync(0xFFFFFFFFu, cand);
+        if ((threadIdx.x & 31) == 0 && warp_tiles) {
+            atomicAdd(num_rendered, warp_tiles);
+            atomicAdd(num_rendered + 2, warp_cand);
+        }
+    }
+    if (!in_range) return;
 
     if (MODE == Mode::Filter) {
         radii[idx] = visible ? pr.radius : 0;
@@ -406,7 +427,7 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sc
         P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
         viewmatrix, projmatrix, cam_pos, vp, prefiltered ? 1 : 0, radii, g.depths,
         g.tiles_touched, g.rect, g.rec, g.cov3D, g.acc, g.clamped, g.key_a, g.val_a,
-        g.counters + 1, nullptr, nullptr);
+        g.counters + 1, g.counters, nullptr, nullptr);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
@@ -419,7 +440,7 @@ int launch_filter(int P, const float* means3D, const float* scales, const float*
     preprocess_kernel<Mode::Filter><<<grid_for(P), PRE_THREADS, 0, stream>>>(
         P, 0, 0, means3D, scales, rotations, nullptr, nullptr, cov3D_precomp, nullptr,
         viewmatrix, projmatrix, nullptr, vp, prefiltered ? 1 : 0, radii, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, nullptr, nullptr);
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, nullptr, nullptr, nullptr);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
@@ -434,7 +455,7 @@ int launch_project(int P, int D, int M, const float* means3D, const float* scale
     preprocess_kernel<Mode::Project><<<grid_for(P), PRE_THREADS, 0, stream>>>(
         P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
         viewmatrix, projmatrix, cam_pos, vp, prefiltered ? 1 : 0, radii, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_rgb,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_rgb,
         points_image);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;

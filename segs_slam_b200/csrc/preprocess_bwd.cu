@@ -137,7 +137,7 @@ __device__ float3 sh_backward(int deg, int M, const float* __restrict__ sh, floa
     return dnormvdv3(dir_orig, make_float3(ddx, ddy, ddz));
 }
 
-__global__ void __launch_bounds__(BWD_THREADS)
+__global__ void __launch_bounds__(BWD_THREADS, 4)
 preprocess_backward_kernel(int P, int D, int M,
                            const float* __restrict__ means3D, const float* __restrict__ scales,
                            const float* __restrict__ rotations, const float* __restrict__ shs,
@@ -174,24 +174,44 @@ preprocess_backward_kernel(int P, int D, int M,
     float d_rot[4] = {0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
 
-    if (in_range && tiles_touched[idx] > 0) {   // == radii[idx] > 0 of backward.cu:156,367
-        const float4 a0 = acc[3 * idx + 0];
-        const float4 a1 = acc[3 * idx + 1];
-        const float4 a2 = acc[3 * idx + 2];
-        const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-        acc[3 * idx + 0] = z4; acc[3 * idx + 1] = z4; acc[3 * idx + 2] = z4;
+    // Every global load of this thread is issued up front, before the first dependent use, so
+    // the kernel pays ONE memory round trip instead of three serialised ones (visibility flag ->
+    // accumulator/mean/covariance -> scale/rotation).  Out-of-range lanes read element 0.
+    const size_t li = in_range ? idx : 0;
+    float4 a0 = acc[3 * li + 0];
+    float4 a1 = acc[3 * li + 1];
+    float4 a2 = acc[3 * li + 2];
+    float3 mean = make_float3(__ldg(means3D + 3 * li), __ldg(means3D + 3 * li + 1), __ldg(means3D + 3 * li + 2));
+    float c3[6];
+#pragma unroll
+    for (int k = 0; k < 6; ++k)
+        c3[k] = cov3D_precomp ? __ldg(cov3D_precomp + 6 * li + k) : __ldg(cov3D_planes + size_t(k) * P + li);
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float sc3[3] = {1.f, 1.f, 1.f};
+    if (scales != nullptr) {
+        q = __ldg(reinterpret_cast<const float4*>(rotations) + li);
+        sc3[0] = __ldg(scales + 3 * li); sc3[1] = __ldg(scales + 3 * li + 1); sc3[2] = __ldg(scales + 3 * li + 2);
+    }
+    // (loaded last: the SM issues in order, so the first instruction that waits on a load
+    // must come after every other load has been issued)
+    const uint32_t touched = __ldg(tiles_touched + li);
+
+    // The chain below runs for EVERY lane (no branch for the loads to sink into; ~11% of the
+    // Gaussians are not rendered and compute on don't-care values) and the results are masked
+    // by `vis` at the end.
+    const bool vis = in_range && touched > 0;   // == radii[idx] > 0 of backward.cu:156,367
+    {
+        if (vis) {
+            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            acc[3 * idx + 0] = z4; acc[3 * idx + 1] = z4; acc[3 * idx + 2] = z4;
+        }
         d_mean2D[0] = a0.x; d_mean2D[1] = a0.y;
         d_conic[0] = a0.z; d_conic[1] = a0.w; d_conic[2] = a1.x;
         d_opacity = a1.y;
         d_color[0] = a1.z; d_color[1] = a1.w; d_color[2] = a2.x;
 
-        const float3 mean = make_float3(means3D[3 * idx], means3D[3 * idx + 1], means3D[3 * idx + 2]);
         const float* V = s_view;
         const float* Pm = s_proj;
-        float c3[6];
-#pragma unroll
-        for (int k = 0; k < 6; ++k)
-            c3[k] = cov3D_precomp ? cov3D_precomp[6 * idx + k] : cov3D_planes[size_t(k) * P + idx];
 
         // ---- computeCov2DCUDA (backward.cu:144-274) --------------------------------------
         float3 t;
@@ -275,7 +295,7 @@ preprocess_backward_kernel(int P, int D, int M,
         d_mean3D[1] += (Pm[4] * m_w - Pm[7] * mul1) * d_mean2D[0] + (Pm[5] * m_w - Pm[7] * mul2) * d_mean2D[1];
         d_mean3D[2] += (Pm[8] * m_w - Pm[11] * mul1) * d_mean2D[0] + (Pm[9] * m_w - Pm[11] * mul2) * d_mean2D[1];
 
-        if (shs != nullptr) {
+        if (shs != nullptr && vis) {
             const float3 cp = make_float3(__ldg(campos), __ldg(campos + 1), __ldg(campos + 2));
             const float3 dm = sh_backward(D, M, shs + idx * M * 3, mean, cp, clamped + 3 * idx,
                                           make_float3(d_color[0], d_color[1], d_color[2]),
@@ -286,14 +306,12 @@ preprocess_backward_kernel(int P, int D, int M,
 
         if (scales != nullptr) {
             // ---- computeCov3D backward (backward.cu:278-341) -----------------------------
-            const float4 q = *reinterpret_cast<const float4*>(rotations + 4 * idx);
             const float r = q.x, x = q.y, y = q.z, z = q.w;
             M3 R;
             R.m[0][0] = 1.f - 2.f * (y * y + z * z); R.m[0][1] = 2.f * (x * y - r * z); R.m[0][2] = 2.f * (x * z + r * y);
             R.m[1][0] = 2.f * (x * y + r * z); R.m[1][1] = 1.f - 2.f * (x * x + z * z); R.m[1][2] = 2.f * (y * z - r * x);
             R.m[2][0] = 2.f * (x * z - r * y); R.m[2][1] = 2.f * (y * z + r * x); R.m[2][2] = 1.f - 2.f * (x * x + y * y);
-            const float s[3] = {vp.scale_modifier * scales[3 * idx], vp.scale_modifier * scales[3 * idx + 1],
-                                vp.scale_modifier * scales[3 * idx + 2]};
+            const float s[3] = {vp.scale_modifier * sc3[0], vp.scale_modifier * sc3[1], vp.scale_modifier * sc3[2]};
             M3 S;
 #pragma unroll
             for (int c2 = 0; c2 < 3; ++c2)
@@ -323,6 +341,17 @@ preprocess_backward_kernel(int P, int D, int M,
             d_rot[2] = 2 * x * (d[1][0] + d[0][1]) + 2 * r * (d[2][0] - d[0][2]) + 2 * z * (d[1][2] + d[2][1]) - 4 * y * (d[2][2] + d[0][0]);
             d_rot[3] = 2 * r * (d[0][1] - d[1][0]) + 2 * x * (d[2][0] + d[0][2]) + 2 * y * (d[1][2] + d[2][1]) - 4 * z * (d[1][1] + d[0][0]);
         }
+    }
+    if (!vis) {
+        d_mean2D[0] = d_mean2D[1] = 0.f;
+        d_conic[0] = d_conic[1] = d_conic[2] = 0.f;
+        d_opacity = 0.f;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) { d_color[k] = 0.f; d_mean3D[k] = 0.f; d_scale[k] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d_cov[k] = 0.f;
+#pragma unroll
+        for (int k = 0; k < 4; ++k) d_rot[k] = 0.f;
     }
 
     {

@@ -73,9 +73,12 @@ def mine_sections(m, P, W, H):
              conic_opacity=rec[:, 4:8], rgb=rec[:, 8:11],
              cov3D=sec("cov3D", torch.float32, (6, P)).t(),
              point_list=sec("point_list", torch.int32) if R else torch.empty(0, dtype=torch.int32, device=rec.device),
-             tile_ids=sec("tile_ids", torch.int32) if R else torch.empty(0, dtype=torch.int32, device=rec.device),
              ranges=sec("ranges", torch.int32, (T, 2)), final_T=sec("final_T", torch.float32),
              n_contrib=sec("n_contrib", torch.int32))
+    # tile id of every list position (the product never materialises tile|depth keys; they are
+    # reconstructed for the parity check from ranges + depth bits)
+    counts = (s["ranges"][:, 1] - s["ranges"][:, 0]).long()
+    s["tile_ids"] = torch.repeat_interleave(torch.arange(T, device=rec.device, dtype=torch.int32), counts)
     return s
 
 
