@@ -63,3 +63,27 @@ def test_synth_scene_is_deterministic():
     for k in ("means3D", "scales", "rotations", "opacities", "colors", "dL_dout", "projmatrix"):
         np.testing.assert_array_equal(getattr(a, k), getattr(b, k))
     assert abs(a.tanfovx - 64 / (2 * 60.0)) < 1e-6
+
+
+def test_libtorch_shim_exports_reference_entry_points():
+    """The C++/LibTorch host layer (csrc/torch_shim) builds, loads against libsegs_raster.so and
+    exposes the six entry points of include/rasterize_points.h:18-102 + spatial.h:14 under the
+    reference's names; shape errors are raised before any device work."""
+    import torch
+    from segs_slam_b200 import _segs_torch as shim
+    for n in ("RasterizeGaussiansCUDA", "RasterizeGaussiansBackwardCUDA", "markVisible",
+              "RasterizeGaussiansfilterCUDA", "RasterizeGaussiansprojectCUDA", "distCUDA2"):
+        assert hasattr(shim, n), n
+    e = torch.empty(0)
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        shim.RasterizeGaussiansCUDA(torch.zeros(3), torch.zeros((4, 4)), e, e, e, e, 1.0, e, torch.eye(4),
+                                    torch.eye(4), 1.0, 1.0, 16, 16, e, 0, torch.zeros(3), False)
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        shim.distCUDA2(torch.zeros((4, 3)))
+    x = torch.zeros((4, 3))
+    with pytest.raises(RuntimeError, match="excatly one of either SHs or precomputed colors"):
+        shim.rasterizer_forward(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3),
+                                False, x, x, x[:, :1], e, e, x, torch.zeros((4, 4)), e)
+    with pytest.raises(RuntimeError, match="exactly one of either scale/rotation pair"):
+        shim.rasterizer_forward(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3),
+                                False, x, x, x[:, :1], e, x, x, e, e)

@@ -1,0 +1,122 @@
+"""GPU parity through the C++/LibTorch host layer (segs_slam_b200/csrc/torch_shim): the SAME entry
+points a SEGS-SLAM build links instead of src/rasterize_points.cu — RasterizeGaussiansCUDA,
+RasterizeGaussiansBackwardCUDA, RasterizeGaussiansfilterCUDA, RasterizeGaussiansprojectCUDA,
+markVisible, distCUDA2 (/root/reference/include/rasterize_points.h:18-102, spatial.h:14) — and the
+C++ autograd function (src/gaussian_rasterizer.cpp:28-154), compared with the unmodified
+reference CUDA rasterizer (oracle/_ref) on identical inputs."""
+import pytest
+import torch
+
+import common
+import refimpl
+from segs_slam_b200 import synth
+
+pytestmark = pytest.mark.gpu
+needs_ref = pytest.mark.skipif(not refimpl.available(), reason="oracle/_ref/libsegs_ref.so not built")
+
+
+@pytest.fixture(scope="module")
+def shim():
+    from segs_slam_b200 import _segs_torch   # raises if the extension has not been built: no fallback
+    return _segs_torch
+
+
+def _fwd_args(a):
+    return (a["bg"], a["means3D"], a["colors"], a["opacity"], a["scales"], a["rotations"], a["scale_modifier"],
+            a["cov3D_precomp"], a["viewmatrix"], a["projmatrix"], a["tan_fovx"], a["tan_fovy"], a["H"], a["W"],
+            a["sh"], a["degree"], a["campos"], False)
+
+
+@needs_ref
+@pytest.mark.parametrize("name", ["tiny", "small", "C1"])
+def test_cpp_entry_points_match_reference(device, shim, name):
+    scene = synth.config(name)
+    t = scene.to_torch(device)
+    a = common.scene_args(t, scene, device)
+    R, color, radii, geom, binning, img = shim.RasterizeGaussiansCUDA(*_fwd_args(a))
+    grads = shim.RasterizeGaussiansBackwardCUDA(
+        a["bg"], a["means3D"], radii, a["colors"], a["scales"], a["rotations"], a["scale_modifier"],
+        a["cov3D_precomp"], a["viewmatrix"], a["projmatrix"], a["tan_fovx"], a["tan_fovy"], t["dL_dout"],
+        a["sh"], a["degree"], a["campos"], geom, R, binning, img)
+    r = common.run_ref(a, t["dL_dout"])
+    r2 = common.run_ref(a, t["dL_dout"])
+    torch.cuda.synchronize()
+    assert R == r["R"]
+    assert torch.equal(radii, r["radii"])
+    assert torch.equal(common.bits(color), common.bits(r["color"]))
+    assert geom.dtype == torch.uint8 and binning.dtype == torch.uint8 and img.dtype == torch.uint8
+    names = ("dL_dmeans2D", "dL_dcolors", "dL_dopacity", "dL_dmeans3D", "dL_dcov3D", "dL_dsh", "dL_dscales",
+             "dL_drotations")   # tuple order of src/rasterize_points.cu:192
+    P = scene.P
+    shapes = dict(dL_dmeans2D=(P, 3), dL_dcolors=(P, 3), dL_dopacity=(P, 1), dL_dmeans3D=(P, 3), dL_dcov3D=(P, 6),
+                  dL_dsh=(P, 0, 3), dL_dscales=(P, 3), dL_drotations=(P, 4))
+    for k, g in zip(names, grads):
+        assert tuple(g.shape) == shapes[k], k
+        ok, why = common.grad_close(g, r["grads"][k], r2["grads"][k], 1e-4)
+        assert ok, (k, why)
+
+
+@needs_ref
+def test_cpp_autograd_function(device, shim):
+    """GaussianRasterizer::forward -> GaussianRasterizerFunction (C++ autograd): gradients land on
+    the right leaves in the order of src/gaussian_rasterizer.cpp:143-153."""
+    scene = synth.config("small", bg=(0.3, 0.1, 0.6))
+    t = scene.to_torch(device)
+    leaf = {k: t[k].clone().requires_grad_(True) for k in ("means3D", "colors", "opacities", "scales", "rotations")}
+    means2D = torch.zeros_like(leaf["means3D"], requires_grad=True)
+    e = common.empty(device)
+    color, radii = shim.rasterizer_forward(scene.H, scene.W, scene.tanfovx, scene.tanfovy, t["bg"], 1.0,
+                                           t["viewmatrix"], t["projmatrix"], 0, t["campos"], False,
+                                           leaf["means3D"], means2D, leaf["opacities"], e, leaf["colors"],
+                                           leaf["scales"], leaf["rotations"], e)
+    (color * t["dL_dout"]).sum().backward()
+    a = common.scene_args(t, scene, device)
+    r = common.run_ref(a, t["dL_dout"])
+    r2 = common.run_ref(a, t["dL_dout"])
+    torch.cuda.synchronize()
+    assert torch.equal(radii, r["radii"])
+    assert torch.equal(common.bits(color.detach()), common.bits(r["color"]))
+    for leaf_name, gname in [("means3D", "dL_dmeans3D"), ("colors", "dL_dcolors"), ("opacities", "dL_dopacity"),
+                             ("scales", "dL_dscales"), ("rotations", "dL_drotations")]:
+        ok, why = common.grad_close(leaf[leaf_name].grad, r["grads"][gname], r2["grads"][gname], 1e-4)
+        assert ok, (leaf_name, why)
+    ok, why = common.grad_close(means2D.grad, r["grads"]["dL_dmeans2D"], r2["grads"]["dL_dmeans2D"], 1e-4)
+    assert ok, why
+    with pytest.raises(RuntimeError, match="excatly one of either SHs or precomputed colors"):
+        shim.rasterizer_forward(scene.H, scene.W, scene.tanfovx, scene.tanfovy, t["bg"], 1.0, t["viewmatrix"],
+                                t["projmatrix"], 0, t["campos"], False, leaf["means3D"], means2D, leaf["opacities"],
+                                e, e, leaf["scales"], leaf["rotations"], e)
+
+
+@needs_ref
+def test_cpp_aux_entry_points(device, shim):
+    scene = synth.config("small")
+    t = scene.to_torch(device)
+    a = common.scene_args(t, scene, device)
+    e = common.empty(device)
+    radii = shim.RasterizeGaussiansfilterCUDA(a["means3D"], a["scales"], a["rotations"], 1.0, e, a["viewmatrix"],
+                                              a["projmatrix"], a["tan_fovx"], a["tan_fovy"], a["H"], a["W"], False,
+                                              False)
+    ref = refimpl.visible_filter(a["means3D"], a["scales"], a["rotations"], 1.0, e, a["viewmatrix"], a["projmatrix"],
+                                 a["tan_fovx"], a["tan_fovy"], a["H"], a["W"])
+    assert torch.equal(radii, ref)
+    present = shim.markVisible(a["means3D"], a["viewmatrix"], a["projmatrix"])
+    assert present.dtype == torch.bool
+    assert torch.equal(present, refimpl.mark_visible(a["means3D"], a["viewmatrix"], a["projmatrix"]))
+    pts, rad, col = shim.RasterizeGaussiansprojectCUDA(*_fwd_args(a))
+    assert pts.shape == (scene.P, 2) and col.shape == (scene.P, 3)
+    assert torch.equal(rad, ref)
+    d = shim.distCUDA2(a["means3D"][:5000].contiguous())
+    assert torch.equal(common.bits(d), common.bits(refimpl.knn(a["means3D"][:5000].contiguous())))
+
+
+def test_cpp_empty_and_errors(device, shim):
+    e = common.empty(device)
+    bg = torch.zeros(3, device=device)
+    eye = torch.eye(4, device=device)
+    R, color, radii, g, b, i = shim.RasterizeGaussiansCUDA(bg, torch.zeros((0, 3), device=device), e, e, e, e, 1.0, e,
+                                                          eye, eye, 1.0, 1.0, 32, 48, e, 0, bg, False)
+    assert R == 0 and color.abs().max().item() == 0.0 and g.numel() == 0
+    with pytest.raises(RuntimeError, match="means3D must have dimensions"):
+        shim.RasterizeGaussiansCUDA(bg, torch.zeros((5, 4), device=device), e, e, e, e, 1.0, e, eye, eye, 1.0, 1.0,
+                                    16, 16, e, 0, bg, False)
