@@ -9,184 +9,95 @@
 // traffic per instance).  The same total order (tile, depth_bits, Gaussian index) is produced
 // here WITHOUT sorting the R instances, by hierarchical binning:
 //
-//   0. a stable 4-pass radix sort of the P Gaussians by depth_bits (P is ~8x smaller than R);
-//   1. coarse level: the image is cut into super-tiles of SxS tiles (S a power of two chosen
-//      so that there are <= 256 super-tiles).  The depth-ordered Gaussians are expanded into
-//      (super-tile, Gaussian) candidates (R' ~ 0.25 R) and ONE stable radix pass on the
-//      super-tile id groups them: every super-tile now has its depth-ordered candidate list;
-//   2. fine level: one CTA per super-tile, one warp per tile.  The CTA streams its candidate
-//      list through shared memory; each warp tests 32 candidates per step against its tile
-//      and stream-compacts the hits with a ballot — compaction preserves the list order, so
-//      every tile's list is in (depth_bits, Gaussian index) order, exactly the reference's
-//      sorted order, bit for bit.  A count pass + a scan over the T tile counts gives
-//      `ranges`; the write pass emits point_list (the only R-sized traffic: 4 B/instance).
-//
-// Radix pass (depth sort, coarse pass, kNN Morton sort) = histogram kernel (per-CTA digit
-// counts, bin-major) + one CTA per bin turning them into scatter bases + a scatter kernel that
-// ranks with warp __match_any_sync (stable, no atomics on the ranking path).
+//   0. a stable 4-digit radix sort of the P Gaussians by depth_bits (radix_sort.cu; P is ~8x
+//      smaller than R);
+//   1. coarse level: the image is cut into super-tiles of 4x4 tiles.  The depth-ordered Gaussians
+//      are expanded into (super-tile, Gaussian) candidates (R' ~ 0.25 R); each candidate carries
+//      the 16-bit mask of the tiles of its super-tile that the Gaussian's rectangle covers
+//      (key = super-tile | mask << 16, value = Gaussian id).  A stable radix sort on the
+//      super-tile bits (one digit up to 256 super-tiles, two up to 65536) groups them: every
+//      super-tile now owns a contiguous, depth-ordered candidate list;
+//   2. one streaming pass over the grouped keys finds the super-tile boundaries and counts the
+//      set mask bits per tile (packed counters + redux, ~16 atomics per 256 candidates); a scan
+//      over the T tile counts gives `ranges`;
+//   3. fine level: one warp per tile streams its super-tile's candidate list and
+//      stream-compacts the candidates whose mask has the tile's bit with a ballot — compaction
+//      preserves list order, so every tile's list is in (depth_bits, Gaussian index) order,
+//      exactly the reference's sorted order, bit for bit.  point_list is the only R-sized
+//      array ever written (4 B/instance).
 #include "common.cuh"
+#include <vector>
+#include <cstdlib>
 
 namespace segs {
 
 namespace {
 
 constexpr unsigned FULL = 0xFFFFFFFFu;
-static_assert(SORT_THREADS == RADIX_BINS, "one thread per radix bin is assumed");
+constexpr int SSHIFT = 2;                 // super-tile = 4x4 tiles -> 16-bit tile mask
+constexpr int SSIDE = 1 << SSHIFT;
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t FLAG_MASK = 3u << 30;
 
 // ---------------------------------------------------------------------------------------
-// radix pass
+// coarse level: load-balanced expansion of depth-ordered Gaussians into candidates
 // ---------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_hist_kernel(const uint32_t* __restrict__ key_in, size_t n, int shift, int nblocks,
-                  uint32_t* __restrict__ block_hist, uint32_t* __restrict__ global_hist)
-{
-    __shared__ uint32_t hist[RADIX_BINS];
-    hist[threadIdx.x] = 0;
-    __syncthreads();
-    const size_t base = size_t(blockIdx.x) * SORT_TILE;
-    uint32_t k[SORT_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const size_t e = base + size_t(i) * SORT_THREADS + threadIdx.x;
-        k[i] = (e < n) ? __ldg(key_in + e) : 0u;
-    }
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const size_t e = base + size_t(i) * SORT_THREADS + threadIdx.x;
-        if (e < n) atomicAdd(&hist[(k[i] >> shift) & (RADIX_BINS - 1)], 1u);
-    }
-    __syncthreads();
-    const uint32_t c = hist[threadIdx.x];
-    block_hist[size_t(threadIdx.x) * nblocks + blockIdx.x] = c;
-    if (c) atomicAdd(&global_hist[threadIdx.x], c);
-}
-
-// One CTA per bin: exclusive scan of that bin's per-CTA counts, offset by the total of all
-// lower bins.  In place.
-__global__ void __launch_bounds__(256)
-radix_scan_kernel(uint32_t* __restrict__ block_hist, const uint32_t* __restrict__ global_hist, int nblocks)
-{
-    __shared__ uint32_t s_warp[8];
-    __shared__ uint32_t s_carry;
-    const int bin = blockIdx.x;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-
-    uint32_t v = (threadIdx.x < bin) ? global_hist[threadIdx.x] : 0u;
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-    if (lane == 0) s_warp[warp] = v;
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        uint32_t t = 0;
-        for (int w = 0; w < 8; ++w) t += s_warp[w];
-        s_carry = t;
-    }
-    __syncthreads();
-
-    uint32_t* row = block_hist + size_t(bin) * nblocks;
-    for (int start = 0; start < nblocks; start += 256) {
-        const int i = start + threadIdx.x;
-        const uint32_t x = (i < nblocks) ? row[i] : 0u;
-        uint32_t inc = x;
-#pragma unroll
-        for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t y = __shfl_up_sync(FULL, inc, o);
-            if (lane >= o) inc += y;
-        }
-        __syncthreads();                   // s_warp / s_carry from the previous round consumed
-        if (lane == 31) s_warp[warp] = inc;
-        __syncthreads();
-        uint32_t woff = 0;
-        for (int w = 0; w < warp; ++w) woff += s_warp[w];
-        const uint32_t carry = s_carry;
-        if (i < nblocks) row[i] = carry + woff + inc - x;
-        __syncthreads();
-        if (threadIdx.x == 255) s_carry = carry + woff + inc;
-    }
-}
-
-__global__ void __launch_bounds__(SORT_THREADS)
-radix_scatter_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out,
-                     const uint32_t* __restrict__ val_in, uint32_t* __restrict__ val_out,
-                     size_t n, int shift, int nblocks, const uint32_t* __restrict__ block_hist)
-{
-    constexpr int WARPS = SORT_THREADS / 32;
-    __shared__ uint32_t warp_hist[WARPS][RADIX_BINS];
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    for (int i = threadIdx.x; i < WARPS * RADIX_BINS; i += SORT_THREADS) (&warp_hist[0][0])[i] = 0;
-    __syncthreads();
-
-    // warp-striped: warp w owns [wbase, wbase + 32*ITEMS); item i of lane l is wbase + 32*i + l
-    const size_t wbase = size_t(blockIdx.x) * SORT_TILE + size_t(warp) * (32 * SORT_ITEMS);
-    uint32_t key[SORT_ITEMS], val[SORT_ITEMS];
-    uint32_t rank[SORT_ITEMS];
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const size_t e = wbase + size_t(i) * 32 + lane;
-        const bool valid = e < n;
-        key[i] = valid ? __ldg(key_in + e) : 0u;
-        val[i] = valid ? __ldg(val_in + e) : 0u;
-    }
-    const uint32_t lt_mask = (1u << lane) - 1u;
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const size_t e = wbase + size_t(i) * 32 + lane;
-        const bool valid = e < n;
-        const uint32_t digit = valid ? ((key[i] >> shift) & (RADIX_BINS - 1)) : RADIX_BINS;
-        const uint32_t peers = __match_any_sync(FULL, digit);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = warp_hist[warp][digit];
-            warp_hist[warp][digit] = old + __popc(peers);
-        }
-        old = __shfl_sync(FULL, old, leader);
-        rank[i] = old + __popc(peers & lt_mask);
-        __syncwarp();
-    }
-    __syncthreads();
-    {
-        // thread t owns bin t: turn per-warp counts into scatter bases
-        const int bin = threadIdx.x;
-        uint32_t running = block_hist[size_t(bin) * nblocks + blockIdx.x];
-#pragma unroll
-        for (int w = 0; w < WARPS; ++w) {
-            const uint32_t c = warp_hist[w][bin];
-            warp_hist[w][bin] = running;
-            running += c;
-        }
-    }
-    __syncthreads();
-#pragma unroll
-    for (int i = 0; i < SORT_ITEMS; ++i) {
-        const size_t e = wbase + size_t(i) * 32 + lane;
-        if (e < n) {
-            const uint32_t digit = (key[i] >> shift) & (RADIX_BINS - 1);
-            const uint32_t pos = warp_hist[warp][digit] + rank[i];
-            key_out[pos] = key[i];
-            val_out[pos] = val[i];
-        }
-    }
-}
-
-// ---------------------------------------------------------------------------------------
-// exclusive scan of the coarse candidate counts in depth order
-// ---------------------------------------------------------------------------------------
-constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;
-constexpr int SCAN_TILE = SCAN_THREADS * SCAN_ITEMS;
+constexpr int EMIT_THREADS = 256;
+constexpr int EMIT_ITEMS = 8;
+constexpr int EMIT_TILE = EMIT_THREADS * EMIT_ITEMS;   // Gaussians per CTA
 
 // number of super-tiles a tile rectangle overlaps (0 for an empty rectangle)
-__device__ __forceinline__ uint32_t coarse_count(ushort4 rc, int sshift) {
+__device__ __forceinline__ uint32_t coarse_count(ushort4 rc) {
     if (rc.x >= rc.z || rc.y >= rc.w) return 0u;
-    const uint32_t sx0 = rc.x >> sshift, sx1 = (rc.z - 1) >> sshift;
-    const uint32_t sy0 = rc.y >> sshift, sy1 = (rc.w - 1) >> sshift;
+    const uint32_t sx0 = rc.x >> SSHIFT, sx1 = (rc.z - 1) >> SSHIFT;
+    const uint32_t sy0 = rc.y >> SSHIFT, sy1 = (rc.w - 1) >> SSHIFT;
     return (sx1 - sx0 + 1) * (sy1 - sy0 + 1);
 }
 
-__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s_warp, uint32_t* total) {
+// bits [lo, hi) of a 4-bit field
+__device__ __forceinline__ uint32_t span4(uint32_t lo, uint32_t hi) { return ((1u << hi) - 1u) & ~((1u << lo) - 1u); }
+
+// 16-bit mask (bit = ly*4 + lx) of the tiles of super-tile (sx, sy) inside the rectangle
+__device__ __forceinline__ uint32_t tile_mask(ushort4 rc, uint32_t sx, uint32_t sy) {
+    const uint32_t bx = sx << SSHIFT, by = sy << SSHIFT;
+    const uint32_t lx0 = max((uint32_t)rc.x, bx) - bx, lx1 = min((uint32_t)rc.z, bx + SSIDE) - bx;
+    const uint32_t ly0 = max((uint32_t)rc.y, by) - by, ly1 = min((uint32_t)rc.w, by + SSIDE) - by;
+    const uint32_t rows = span4(ly0, ly1);
+    const uint32_t rows4 = (rows & 1u) | ((rows & 2u) << 3) | ((rows & 4u) << 6) | ((rows & 8u) << 9);   // bit ly -> bit 4*ly
+    return rows4 * span4(lx0, lx1);                              // times the row pattern (no overlap, no carries)
+}
+
+__global__ void __launch_bounds__(EMIT_THREADS)
+coarse_emit_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, int sgrid_x,
+                   uint32_t* __restrict__ ticket, volatile uint32_t* __restrict__ look,
+                   uint32_t* __restrict__ key_out, uint32_t* __restrict__ val_out)
+{
+    __shared__ uint32_t s_off[EMIT_TILE + 1];      // exclusive candidate offset of every item of the CTA
+    __shared__ uint32_t s_id[EMIT_TILE];
+    __shared__ ushort4 s_rect[EMIT_TILE];
+    __shared__ uint32_t s_warp[EMIT_THREADS / 32];
+    __shared__ uint32_t s_tile, s_base;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    uint32_t inc = x;
+    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
+    __syncthreads();
+    const uint32_t tile = s_tile;
+
+    // blocked arrangement: thread t owns items [8t, 8t+8) of the CTA's depth-ordered run
+    const int first = (int)tile * EMIT_TILE + threadIdx.x * EMIT_ITEMS;
+    uint32_t id[EMIT_ITEMS], c[EMIT_ITEMS];
+    ushort4 rc[EMIT_ITEMS];
+    uint32_t sum = 0;
+#pragma unroll
+    for (int i = 0; i < EMIT_ITEMS; ++i) id[i] = (first + i < P) ? __ldg(order + first + i) : 0u;
+#pragma unroll
+    for (int i = 0; i < EMIT_ITEMS; ++i) {
+        rc[i] = (first + i < P) ? __ldg(rect + id[i]) : make_ushort4(0, 0, 0, 0);
+        c[i] = coarse_count(rc[i]);
+        sum += c[i];
+    }
+    // block exclusive scan of the per-thread sums
+    uint32_t inc = sum;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(FULL, inc, o);
@@ -194,209 +105,161 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t x, uint32_t* s
     }
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
-    uint32_t woff = 0, tot = 0;
+    uint32_t woff = 0, total = 0;
 #pragma unroll
-    for (int w = 0; w < SCAN_THREADS / 32; ++w) {
-        const uint32_t c = s_warp[w];
-        if (w < warp) woff += c;
-        tot += c;
+    for (int w = 0; w < EMIT_THREADS / 32; ++w) {
+        const uint32_t x = s_warp[w];
+        if (w < warp) woff += x;
+        total += x;
     }
-    *total = tot;
+    uint32_t run = woff + inc - sum;
+#pragma unroll
+    for (int i = 0; i < EMIT_ITEMS; ++i) {
+        const int slot = threadIdx.x * EMIT_ITEMS + i;
+        s_off[slot] = run;
+        s_id[slot] = id[i];
+        s_rect[slot] = rc[i];
+        run += c[i];
+    }
+    if (warp == 0) {
+        // decoupled look-back over the preceding CTAs' totals (one word per CTA), 32 tiles per
+        // round: lane l polls tile (t - l); the nearest lane holding an inclusive prefix ends the walk
+        if (lane == 0) {
+            s_off[EMIT_TILE] = total;
+            look[tile] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | total;
+        }
+        uint32_t excl = 0;
+        if (tile != 0) {
+            for (int t = (int)tile - 1;; t -= 32) {
+                uint32_t w = FLAG_PREFIX;                       // tiles before 0: an empty prefix
+                if (t - lane >= 0) {
+                    do { w = look[t - lane]; } while ((w & FLAG_MASK) == 0u);
+                }
+                const unsigned pref = __ballot_sync(FULL, (w & FLAG_MASK) == FLAG_PREFIX);
+                const int stop = __ffs(pref) - 1;               // nearest published prefix (-1: none)
+                const uint32_t v = (stop < 0 || lane <= stop) ? (w & ~FLAG_MASK) : 0u;
+                excl += __reduce_add_sync(FULL, v);
+                if (stop >= 0) break;
+            }
+            if (lane == 0) look[tile] = FLAG_PREFIX | (excl + total);
+        }
+        if (lane == 0) s_base = excl;
+    }
     __syncthreads();
-    return woff + inc - x;
-}
+    const uint32_t base = s_base;
 
-__global__ void __launch_bounds__(SCAN_THREADS)
-coarse_reduce_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, int sshift,
-                     uint32_t* __restrict__ partials)
-{
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t sum = 0;
+    // load-balanced expansion: output slot j belongs to the last item whose offset is <= j
+    for (uint32_t j = threadIdx.x; j < total; j += EMIT_THREADS) {
+        int lo = 0, hi = EMIT_TILE;            // invariant: s_off[lo] <= j < s_off[hi]
 #pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i)
-        if (base + i < P) sum += coarse_count(__ldg(rect + __ldg(order + base + i)), sshift);
-    uint32_t total;
-    block_exclusive_scan(sum, s_warp, &total);
-    if (threadIdx.x == 0) partials[blockIdx.x] = total;
-}
-
-__global__ void __launch_bounds__(SCAN_THREADS)
-coarse_partials_kernel(uint32_t* __restrict__ partials, int nb)
-{
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    uint32_t carry = 0;
-    for (int start = 0; start < nb; start += SCAN_THREADS) {
-        const int i = start + threadIdx.x;
-        const uint32_t x = (i < nb) ? partials[i] : 0u;
-        uint32_t total;
-        const uint32_t ex = block_exclusive_scan(x, s_warp, &total);
-        if (i < nb) partials[i] = carry + ex;
-        carry += total;
-    }
-}
-
-// scan + emission fused: candidate j of depth-ordered Gaussian k goes to offsets[k] + j
-// (row-major over its super-tile rectangle), key = super-tile id, value = Gaussian id
-__global__ void __launch_bounds__(SCAN_THREADS)
-coarse_emit_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict__ rect, int P, int sshift,
-                   int sgrid_x, const uint32_t* __restrict__ partials, uint32_t* __restrict__ key_out,
-                   uint32_t* __restrict__ val_out)
-{
-    __shared__ uint32_t s_warp[SCAN_THREADS / 32];
-    const int base = blockIdx.x * SCAN_TILE + threadIdx.x * SCAN_ITEMS;
-    uint32_t id[SCAN_ITEMS], c[SCAN_ITEMS];
-    ushort4 rc[SCAN_ITEMS];
-    uint32_t sum = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        c[i] = 0;
-        if (base + i < P) {
-            id[i] = __ldg(order + base + i);
-            rc[i] = __ldg(rect + id[i]);
-            c[i] = coarse_count(rc[i], sshift);
+        for (int step = 0; step < 11; ++step) {       // log2(EMIT_TILE) = 11
+            const int mid = (lo + hi) >> 1;
+            if (s_off[mid] <= j) lo = mid; else hi = mid;
         }
-        sum += c[i];
-    }
-    uint32_t total;
-    uint32_t run = partials[blockIdx.x] + block_exclusive_scan(sum, s_warp, &total);
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; ++i) {
-        if (c[i]) {
-            const uint32_t sx0 = rc[i].x >> sshift, sx1 = (rc[i].z - 1) >> sshift;
-            const uint32_t sy0 = rc[i].y >> sshift, sy1 = (rc[i].w - 1) >> sshift;
-            for (uint32_t sy = sy0; sy <= sy1; ++sy)
-                for (uint32_t sx = sx0; sx <= sx1; ++sx) {
-                    key_out[run] = sy * (uint32_t)sgrid_x + sx;
-                    val_out[run] = id[i];
-                    ++run;
-                }
-        }
+        const ushort4 r = s_rect[lo];
+        const uint32_t k = j - s_off[lo];
+        const uint32_t sx0 = r.x >> SSHIFT, sx1 = (r.z - 1) >> SSHIFT, sy0 = r.y >> SSHIFT;
+        const uint32_t w = sx1 - sx0 + 1;
+        const uint32_t sy = sy0 + k / w, sx = sx0 + k % w;      // row-major over the super-tile rectangle
+        key_out[base + j] = (sy * (uint32_t)sgrid_x + sx) | (tile_mask(r, sx, sy) << 16);
+        val_out[base + j] = s_id[lo];
     }
 }
 
 // ---------------------------------------------------------------------------------------
-// fine level: CTA = super-tile, warp = tile(s); ordered ballot compaction
+// super-tile boundaries + per-tile counts from the grouped candidate keys
 // ---------------------------------------------------------------------------------------
-constexpr int FINE_MAX_THREADS = 1024;
+constexpr int CNT_THREADS = 256;
+constexpr int CNT_ITEMS = 8;                              // candidates per lane -> 4-bit counters suffice
+constexpr int CNT_WARP_RUN = 32 * CNT_ITEMS;
 
-__device__ __forceinline__ void cp_async8(void* smem_dst, const void* gmem_src) {
-    const unsigned d = (unsigned)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;\n" ::"r"(d), "l"(gmem_src));
+// bit k of the low byte -> bit 4k
+__device__ __forceinline__ uint32_t spread8x4(uint32_t x) {
+    x &= 0xFFu;
+    x = (x | (x << 12)) & 0x000F000Fu;
+    x = (x | (x << 6)) & 0x03030303u;
+    x = (x | (x << 3)) & 0x11111111u;
+    return x;
 }
-__device__ __forceinline__ void cp_async_commit_group() { asm volatile("cp.async.commit_group;\n" ::); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait_group() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
 
-// The candidate list is streamed in batches of blockDim.x candidates, double-buffered: the ids of
-// batch b+2 are prefetched into registers and the 8-byte rectangles of batch b+1 are gathered
-// with cp.async while the warps test batch b.
-template <bool WRITE>
-__global__ void __launch_bounds__(FINE_MAX_THREADS)
-fine_bin_kernel(int sshift, int sgrid_x, int grid_x, int grid_y, const uint32_t* __restrict__ coarse_hist,
-                const uint32_t* __restrict__ cand_id, const ushort4* __restrict__ rect,
-                uint32_t* __restrict__ tile_counts, const uint2* __restrict__ ranges,
-                uint32_t* __restrict__ point_list)
+__global__ void __launch_bounds__(CNT_THREADS)
+count_bounds_kernel(const uint32_t* __restrict__ keys, uint32_t n, int sgrid_x, int grid_x, int grid_y,
+                    uint32_t* __restrict__ st_begin, uint32_t* __restrict__ st_end,
+                    uint32_t* __restrict__ tile_counts)
 {
-    extern __shared__ __align__(16) unsigned char s_fine[];
-    const int NT = blockDim.x;
-    ushort4* s_rect = reinterpret_cast<ushort4*>(s_fine);                  // [2][NT]
-    uint32_t* s_id = reinterpret_cast<uint32_t*>(s_fine + size_t(2) * NT * sizeof(ushort4));   // [2][NT]
-    __shared__ uint32_t s_red[32];
-    __shared__ uint32_t s_start, s_len;
-    const int st = blockIdx.x;
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nwarps = blockDim.x >> 5;
-
-    // candidate range of this super-tile = prefix of the coarse histogram (<= 256 bins)
-    {
-        uint32_t v = 0;
-        for (int i = tid; i < st; i += blockDim.x) v += coarse_hist[i];
+    const int lane = threadIdx.x & 31;
+    const uint32_t wid = (blockIdx.x * CNT_THREADS + threadIdx.x) >> 5;
+    const uint32_t base = wid * CNT_WARP_RUN;
+    if (base >= n) return;
+    uint32_t key[CNT_ITEMS];
 #pragma unroll
-        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
-        if (lane == 0) s_red[warp] = v;
-        __syncthreads();
-        if (tid == 0) {
-            uint32_t t = 0;
-            for (int w = 0; w < nwarps; ++w) t += s_red[w];
-            s_start = t;
-            s_len = coarse_hist[st];
-        }
-        __syncthreads();
+    for (int i = 0; i < CNT_ITEMS; ++i) {
+        const uint32_t e = base + i * 32 + lane;
+        key[i] = (e < n) ? __ldg(keys + e) : 0xFFFFFFFFu;
     }
-    const uint32_t clen = s_len;
-    const uint32_t* list = cand_id + s_start;
-    const int nbatches = (int)((clen + NT - 1) / NT);
-
-    // tiles of this super-tile handled by this warp: local index li = warp, warp + nwarps, ...
-    // (at most MAX_TPW per warp; kept in registers, all loops over them are fully unrolled)
-    const int S = 1 << sshift;
-    const int stx = (st % sgrid_x) << sshift, sty = (st / sgrid_x) << sshift;
-    constexpr int MAX_TPW = 8;
-    uint32_t run[MAX_TPW];
-    unsigned ttx[MAX_TPW], tty[MAX_TPW];
-    bool live[MAX_TPW];
+    const uint32_t prev_run = (base > 0 && lane == 0) ? (__ldg(keys + base - 1) & 0xFFFFu) : 0xFFFFFFFFu;
+    // boundaries: candidate e starts a super-tile if its id differs from candidate e-1's
+    uint32_t carry = prev_run;   // id of the element before item i's lane 0
+    uint32_t lo4 = 0, hi4 = 0;   // 16 x 4-bit per-tile counters (tiles 0-7, 8-15)
+    uint32_t st_min = 0xFFFFFFFFu, st_max = 0u;
 #pragma unroll
-    for (int q = 0; q < MAX_TPW; ++q) {
-        const int li = warp + q * nwarps;
-        const int tx = stx + (li & (S - 1)), ty = sty + (li >> sshift);
-        live[q] = li < S * S && tx < grid_x && ty < grid_y;
-        ttx[q] = (unsigned)tx; tty[q] = (unsigned)ty;
-        run[q] = (WRITE && live[q]) ? ranges[ty * grid_x + tx].x : 0u;
-    }
-    const uint32_t lt = (1u << lane) - 1u;
-
-    // pipeline prologue: batch 0 rectangles in flight, batch 1 ids in registers
-    uint32_t id_next = ((uint32_t)tid < clen) ? __ldg(list + tid) : 0u;
-    if ((uint32_t)tid < clen) {
-        s_id[tid] = id_next;
-        cp_async8(&s_rect[tid], rect + id_next);
-    }
-    cp_async_commit_group();
-    id_next = ((uint32_t)(NT + tid) < clen) ? __ldg(list + NT + tid) : 0u;
-
-    for (int b = 0; b < nbatches; ++b) {
-        const int buf = b & 1;
-        const uint32_t n_in = min((uint32_t)NT, clen - (uint32_t)b * NT);
-        if (b + 1 < nbatches) {
-            const uint32_t p = (uint32_t)(b + 1) * NT + tid;
-            if (p < clen) {
-                s_id[(buf ^ 1) * NT + tid] = id_next;
-                cp_async8(&s_rect[(buf ^ 1) * NT + tid], rect + id_next);
+    for (int i = 0; i < CNT_ITEMS; ++i) {
+        const uint32_t e = base + i * 32 + lane;
+        const uint32_t st = key[i] & 0xFFFFu;
+        uint32_t prev = __shfl_up_sync(FULL, st, 1);
+        const uint32_t last = __shfl_sync(FULL, st, 31);
+        if (lane == 0) prev = carry;
+        carry = last;
+        if (e < n) {
+            if (e == 0 || st != prev) {
+                st_begin[st] = e;
+                if (e != 0) st_end[prev] = e;
             }
-            cp_async_commit_group();
-            const uint32_t p2 = (uint32_t)(b + 2) * NT + tid;
-            id_next = (p2 < clen) ? __ldg(list + p2) : 0u;
-            cp_async_wait_group<1>();
-        } else {
-            cp_async_wait_group<0>();
+            if (e == n - 1) st_end[st] = n;
+            st_min = min(st_min, st);
+            st_max = max(st_max, st);
+            lo4 += spread8x4(key[i] >> 16);
+            hi4 += spread8x4(key[i] >> 24);
         }
-        __syncthreads();
-        const ushort4* b_rect = s_rect + buf * NT;
-        const uint32_t* b_id = s_id + buf * NT;
-        for (uint32_t c = 0; c < n_in; c += 32) {
-            const uint32_t slot = c + lane;
-            ushort4 rc = make_ushort4(1, 1, 0, 0);      // empty rectangle: never hits
-            uint32_t id = 0;
-            if (slot < n_in) {
-                rc = b_rect[slot];
-                if (WRITE) id = b_id[slot];
-            }
+    }
+    // whole run inside one super-tile (the common case: runs are 256 long, lists thousands)?
+    // the keys are sorted by super-tile, so it is enough to compare the smallest and largest id
+    const uint32_t first_st = __reduce_min_sync(FULL, st_min);
+    const uint32_t last_st = __reduce_max_sync(FULL, st_max);
+    if (first_st == last_st) {
+        // widen the nibble counters to 16 bits (warp totals reach 256) and reduce with redux.sync
+        uint32_t tot[8];
 #pragma unroll
-            for (int q = 0; q < MAX_TPW; ++q) {
-                if (live[q]) {                              // warp-uniform
-                    const bool hit = (ttx[q] >= rc.x) && (ttx[q] < rc.z) && (tty[q] >= rc.y) && (tty[q] < rc.w);
-                    const unsigned mask = __ballot_sync(FULL, hit);
-                    if (WRITE && hit) point_list[run[q] + __popc(mask & lt)] = id;
-                    run[q] += __popc(mask);
-                }
+        for (int q = 0; q < 4; ++q) {
+            const uint32_t a = (lo4 >> (8 * q)) & 0xFFu, b = (hi4 >> (8 * q)) & 0xFFu;
+            tot[q] = __reduce_add_sync(FULL, (a & 0xFu) | ((a >> 4) << 16));          // tiles 2q, 2q+1
+            tot[4 + q] = __reduce_add_sync(FULL, (b & 0xFu) | ((b >> 4) << 16));      // tiles 8+2q, 9+2q
+        }
+        if (lane < 16) {
+            uint32_t word = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                if ((lane >> 1) == q) word = tot[q];
+            const uint32_t cnt = (lane & 1) ? (word >> 16) : (word & 0xFFFFu);
+            const int tx = (int)((first_st % (uint32_t)sgrid_x) << SSHIFT) + (lane & (SSIDE - 1));
+            const int ty = (int)((first_st / (uint32_t)sgrid_x) << SSHIFT) + (lane >> SSHIFT);
+            if (cnt && tx < grid_x && ty < grid_y) atomicAdd(&tile_counts[ty * grid_x + tx], cnt);
+        }
+    } else {
+        // the run straddles a super-tile boundary: per-candidate updates
+#pragma unroll
+        for (int i = 0; i < CNT_ITEMS; ++i) {
+            const uint32_t e = base + i * 32 + lane;
+            if (e >= n) continue;
+            const uint32_t st = key[i] & 0xFFFFu;
+            const int bx = (int)((st % (uint32_t)sgrid_x) << SSHIFT), by = (int)((st / (uint32_t)sgrid_x) << SSHIFT);
+            uint32_t m = key[i] >> 16;
+            while (m) {
+                const int li = __ffs(m) - 1;
+                m &= m - 1;
+                atomicAdd(&tile_counts[(by + (li >> SSHIFT)) * grid_x + bx + (li & (SSIDE - 1))], 1u);
             }
         }
-        __syncthreads();   // everyone is done with this buffer before it is refilled
-    }
-    if (!WRITE && lane == 0) {
-#pragma unroll
-        for (int q = 0; q < MAX_TPW; ++q)
-            if (live[q]) tile_counts[tty[q] * grid_x + ttx[q]] = run[q];
     }
 }
 
@@ -434,48 +297,67 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_counts, uint2* __restr
     if (threadIdx.x == 0 && total_out) *total_out = s_carry;
 }
 
-}  // namespace
+// ---------------------------------------------------------------------------------------
+// fine level: warp = tile, ordered ballot compaction of the super-tile's candidate list
+// ---------------------------------------------------------------------------------------
+constexpr int FINE_WARPS = 4;       // CTA = one tile row of a super-tile
 
-int radix_pass(const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in,
-               uint32_t* val_out, size_t n, int shift, uint32_t* block_hist,
-               uint32_t* global_hist, cudaStream_t stream)
+__global__ void __launch_bounds__(FINE_WARPS * 32)
+fine_write_kernel(int sgrid_x, int grid_x, int grid_y, const uint32_t* __restrict__ st_begin,
+                  const uint32_t* __restrict__ st_end, const uint32_t* __restrict__ keys,
+                  const uint32_t* __restrict__ vals, const uint2* __restrict__ ranges,
+                  uint32_t* __restrict__ point_list)
 {
-    if (n == 0) return SEGS_OK;
-    const int nblocks = sort_blocks(n);
-    SEGS_CUDA_CHECK(cudaMemsetAsync(global_hist, 0, RADIX_BINS * sizeof(uint32_t), stream));
-    radix_hist_kernel<<<nblocks, SORT_THREADS, 0, stream>>>(key_in, n, shift, nblocks, block_hist, global_hist);
-    SEGS_LAUNCH_CHECK();
-    radix_scan_kernel<<<RADIX_BINS, 256, 0, stream>>>(block_hist, global_hist, nblocks);
-    SEGS_LAUNCH_CHECK();
-    radix_scatter_kernel<<<nblocks, SORT_THREADS, 0, stream>>>(key_in, key_out, val_in, val_out, n, shift,
-                                                              nblocks, block_hist);
-    SEGS_LAUNCH_CHECK();
-    return SEGS_OK;
+    const int lane = threadIdx.x & 31, lx = threadIdx.x >> 5;
+    const int st = blockIdx.x >> SSHIFT, ly = blockIdx.x & (SSIDE - 1);
+    const int tx = ((st % sgrid_x) << SSHIFT) + lx, ty = ((st / sgrid_x) << SSHIFT) + ly;
+    if (tx >= grid_x || ty >= grid_y) return;
+    const uint2 range = ranges[ty * grid_x + tx];
+    if (range.x == range.y) return;
+    const uint32_t begin = st_begin[st], end = st_end[st];
+    const int bit = 16 + ly * SSIDE + lx;
+    const uint32_t lt = (1u << lane) - 1u;
+    uint32_t* out = point_list + range.x;
+    uint32_t run = 0;
+    constexpr int UNROLL = 4;
+    for (uint32_t c = begin; c < end; c += 32 * UNROLL) {
+        uint32_t k[UNROLL];
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const uint32_t e = c + u * 32 + lane;
+            k[u] = (e < end) ? __ldg(keys + e) : 0u;
+        }
+#pragma unroll
+        for (int u = 0; u < UNROLL; ++u) {
+            const bool hit = (k[u] >> bit) & 1u;
+            const unsigned m = __ballot_sync(FULL, hit);
+            if (hit) out[run + __popc(m & lt)] = __ldg(vals + c + u * 32 + lane);
+            run += __popc(m);
+        }
+    }
 }
+
+}  // namespace
 
 int launch_depth_order(int P, GeomState& g, cudaStream_t stream)
 {
-    // 4 stable 8-bit passes over (depth_bits, index): a -> b -> a -> b -> a
-    int rc;
-    if ((rc = radix_pass(g.key_a, g.key_b, g.val_a, g.val_b, P, 0, g.block_hist, g.global_hist, stream))) return rc;
-    if ((rc = radix_pass(g.key_b, g.key_a, g.val_b, g.val_a, P, 8, g.block_hist, g.global_hist, stream))) return rc;
-    if ((rc = radix_pass(g.key_a, g.key_b, g.val_a, g.val_b, P, 16, g.block_hist, g.global_hist, stream))) return rc;
-    if ((rc = radix_pass(g.key_b, g.key_a, g.val_b, g.val_a, P, 24, g.block_hist, g.global_hist, stream))) return rc;
-    return SEGS_OK;
+    // 4 stable 8-bit digits over (depth_bits, index); values start as 0..P-1 (not read); the
+    // result lands back in (key_a, val_a)
+    return radix_sort_pairs(g.key_a, g.key_b, g.val_a, g.val_b, (size_t)P, 0, 4, true, g.sort_temp, stream);
 }
 
-// Super-tile side (in tiles, power of two) such that there are at most 256 super-tiles, i.e.
-// one 8-bit radix pass groups the candidates.  Deterministic in the tile grid.
 BinningPlan plan_binning(int grid_x, int grid_y)
 {
     BinningPlan p;
-    p.sshift = 1;
-    while (((grid_x + (1 << p.sshift) - 1) >> p.sshift) * ((grid_y + (1 << p.sshift) - 1) >> p.sshift) > RADIX_BINS)
-        ++p.sshift;
-    p.sgrid_x = (grid_x + (1 << p.sshift) - 1) >> p.sshift;
-    p.sgrid_y = (grid_y + (1 << p.sshift) - 1) >> p.sshift;
+    p.sshift = SSHIFT;
+    p.sgrid_x = (grid_x + SSIDE - 1) >> SSHIFT;
+    p.sgrid_y = (grid_y + SSIDE - 1) >> SSHIFT;
+    const int n = p.sgrid_x * p.sgrid_y;
+    p.sort_passes = n <= 256 ? 1 : 2;
     return p;
 }
+
+int emit_blocks(int P) { return (P + EMIT_TILE - 1) / EMIT_TILE; }
 
 int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, BinningState& b,
                    ImageState& img, cudaStream_t stream)
@@ -486,36 +368,48 @@ int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, Bin
         return SEGS_OK;
     }
     const BinningPlan pl = plan_binning(vp.grid_x, vp.grid_y);
-    if (pl.sshift > 4) { set_error("image too large for the two-level tile binning (%d x %d tiles)", vp.grid_x, vp.grid_y); return SEGS_ERR_INVALID_ARG; }
-
-    // coarse: expand depth-ordered Gaussians into (super-tile, id) candidates ...
-    const int nb = (P + SCAN_TILE - 1) / SCAN_TILE;
-    coarse_reduce_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.rect, P, pl.sshift, b.partials);
-    SEGS_LAUNCH_CHECK();
-    coarse_partials_kernel<<<1, SCAN_THREADS, 0, stream>>>(b.partials, nb);
-    SEGS_LAUNCH_CHECK();
-    coarse_emit_kernel<<<nb, SCAN_THREADS, 0, stream>>>(g.val_a, g.rect, P, pl.sshift, pl.sgrid_x, b.partials,
-                                                        b.cand_key_a, b.cand_val_a);
-    SEGS_LAUNCH_CHECK();
-    // ... and group them by super-tile with one stable 8-bit pass (global_hist = candidates per super-tile)
-    int rc = radix_pass(b.cand_key_a, b.cand_key_b, b.cand_val_a, b.cand_val_b, (size_t)Rc, 0, b.block_hist,
-                        b.global_hist, stream);
-    if (rc) return rc;
-
-    // fine: per tile count -> ranges -> ordered write
     const int nst = pl.sgrid_x * pl.sgrid_y;
-    const int tiles_per_st = 1 << (2 * pl.sshift);
-    // warps per CTA: each warp owns up to 8 tiles of the super-tile
-    const int warps = tiles_per_st <= 4 ? 4 : (tiles_per_st <= 128 ? 16 : 32);
-    const size_t fine_smem = size_t(2) * warps * 32 * (sizeof(ushort4) + sizeof(uint32_t));
-    fine_bin_kernel<false><<<nst, warps * 32, fine_smem, stream>>>(pl.sshift, pl.sgrid_x, vp.grid_x, vp.grid_y, b.global_hist,
-                                                          b.cand_val_b, g.rect, b.tile_counts, nullptr, nullptr);
+    if (nst > 65536) { set_error("image too large for the two-level tile binning (%d x %d tiles)", vp.grid_x, vp.grid_y); return SEGS_ERR_INVALID_ARG; }
+
+    // everything the kernels below accumulate into / poll: one memset
+    SEGS_CUDA_CHECK(cudaMemsetAsync(b.zeroed, 0, b.zeroed_bytes, stream));
+
+    // coarse: expand depth-ordered Gaussians into (super-tile | mask, id) candidates ...
+    coarse_emit_kernel<<<emit_blocks(P), EMIT_THREADS, 0, stream>>>(g.val_a, g.rect, P, pl.sgrid_x, b.emit_ticket,
+                                                                   b.emit_look, b.cand_key_a, b.cand_val_a);
+    SEGS_LAUNCH_CHECK();
+    // ... and group them by super-tile (stable; the mask bits ride along in the key)
+    int rc = radix_sort_pairs(b.cand_key_a, b.cand_key_b, b.cand_val_a, b.cand_val_b, (size_t)Rc, 0, pl.sort_passes,
+                              false, b.sort_temp, stream);
+    if (rc) return rc;
+    const uint32_t* keys = (pl.sort_passes & 1) ? b.cand_key_b : b.cand_key_a;
+    const uint32_t* vals = (pl.sort_passes & 1) ? b.cand_val_b : b.cand_val_a;
+
+    const int cnt_warps = (Rc + CNT_WARP_RUN - 1) / CNT_WARP_RUN;
+    count_bounds_kernel<<<(cnt_warps * 32 + CNT_THREADS - 1) / CNT_THREADS, CNT_THREADS, 0, stream>>>(
+        keys, (uint32_t)Rc, pl.sgrid_x, vp.grid_x, vp.grid_y, b.st_begin, b.st_end, b.tile_counts);
     SEGS_LAUNCH_CHECK();
     tile_scan_kernel<<<1, 1024, 0, stream>>>(T, b.tile_counts, img.ranges, g.counters + 3);
     SEGS_LAUNCH_CHECK();
-    fine_bin_kernel<true><<<nst, warps * 32, fine_smem, stream>>>(pl.sshift, pl.sgrid_x, vp.grid_x, vp.grid_y, b.global_hist,
-                                                         b.cand_val_b, g.rect, nullptr, img.ranges, b.point_list);
+    fine_write_kernel<<<nst * SSIDE, FINE_WARPS * 32, 0, stream>>>(pl.sgrid_x, vp.grid_x, vp.grid_y, b.st_begin, b.st_end,
+                                                                  keys, vals, img.ranges, b.point_list);
     SEGS_LAUNCH_CHECK();
+    if (getenv("SEGS_DEBUG_BINNING")) {
+        cudaStreamSynchronize(stream);
+        std::vector<uint32_t> hk(Rc), hb(nst), he(nst), tc(T);
+        cudaMemcpy(hk.data(), keys, Rc * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(hb.data(), b.st_begin, nst * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(he.data(), b.st_end, nst * 4, cudaMemcpyDeviceToHost);
+        cudaMemcpy(tc.data(), b.tile_counts, T * 4, cudaMemcpyDeviceToHost);
+        fprintf(stderr, "DEBUG P=%d R=%d Rc=%d nst=%d passes=%d\n", P, R, Rc, nst, pl.sort_passes);
+        for (int i = 0; i < nst && i < 8; ++i) fprintf(stderr, "  st %d: [%u, %u)\n", i, hb[i], he[i]);
+        int unsorted = 0; for (int i = 1; i < Rc; ++i) if ((hk[i] & 0xFFFF) < (hk[i-1] & 0xFFFF)) ++unsorted;
+        fprintf(stderr, "  unsorted pairs %d; keys[0..3] %08x %08x %08x last %08x\n", unsorted, hk[0], hk[1], hk[2], hk[Rc-1]);
+        unsigned long long sum = 0; for (int i = 0; i < T; ++i) sum += tc[i];
+        fprintf(stderr, "  sum tile_counts %llu\n", sum);
+        for (int i = 0; i < T && i < 24; ++i) fprintf(stderr, " %u", tc[i]);
+        fprintf(stderr, "\n");
+    }
     return SEGS_OK;
 }
 

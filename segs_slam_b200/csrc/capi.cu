@@ -40,25 +40,31 @@ GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
     g.key_b = c.take<uint32_t>(P);
     g.val_a = c.take<uint32_t>(P);
     g.val_b = c.take<uint32_t>(P);
-    g.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(P));
-    g.global_hist = c.take<uint32_t>(RADIX_BINS);
+    g.sort_temp = c.take<uint32_t>(radix_sort_temp_words(P, 4));
     g.counters = c.take<uint32_t>(8);
     if (bytes) *bytes = c.used(base) + 128;
     return g;
 }
 
-BinningState BinningState::carve(char* base, size_t R, size_t Rc, size_t P, size_t T, size_t* bytes) {
+BinningState BinningState::carve(char* base, size_t R, size_t Rc, size_t P, int grid_x, int grid_y, size_t* bytes) {
     Carver c(base);
     BinningState b;
+    const BinningPlan pl = plan_binning(grid_x, grid_y);
+    const size_t nst = size_t(pl.sgrid_x) * pl.sgrid_y, T = size_t(grid_x) * grid_y;
     b.point_list = c.take<uint32_t>(R);      // first: the only section the backward reads
     b.cand_key_a = c.take<uint32_t>(Rc);
     b.cand_key_b = c.take<uint32_t>(Rc);
     b.cand_val_a = c.take<uint32_t>(Rc);
     b.cand_val_b = c.take<uint32_t>(Rc);
-    b.block_hist = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(Rc));
-    b.global_hist = c.take<uint32_t>(RADIX_BINS);
-    b.partials = c.take<uint32_t>(P / 2048 + 2);
-    b.tile_counts = c.take<uint32_t>(T);
+    b.sort_temp = c.take<uint32_t>(radix_sort_temp_words(Rc, pl.sort_passes));
+    const size_t nz = 1 + size_t(emit_blocks((int)P)) + 2 * nst + T;
+    b.zeroed = c.take<uint32_t>(nz);
+    b.zeroed_bytes = nz * sizeof(uint32_t);
+    b.emit_ticket = b.zeroed;
+    b.emit_look = b.emit_ticket + 1;
+    b.st_begin = b.emit_look + emit_blocks((int)P);
+    b.st_end = b.st_begin + nst;
+    b.tile_counts = b.st_end + nst;
     if (bytes) *bytes = c.used(base) + 128;
     return b;
 }
@@ -237,10 +243,10 @@ int segs_raster_forward(
     }
     if (R > 0x7FFFFFFFu) { set_error("num_rendered %u overflows int", R); return SEGS_ERR_INVALID_ARG; }
 
-    BinningState::carve(nullptr, R, Rc, P, T, &bin_bytes);
+    BinningState::carve(nullptr, R, Rc, P, vp.grid_x, vp.grid_y, &bin_bytes);
     char* bin_ptr = binning_alloc(binning_user, bin_bytes);
     if (!bin_ptr) { set_error("binning buffer allocation of %zu bytes failed", bin_bytes); return SEGS_ERR_ALLOC; }
-    BinningState b = BinningState::carve(bin_ptr, R, Rc, P, T, nullptr);
+    BinningState b = BinningState::carve(bin_ptr, R, Rc, P, vp.grid_x, vp.grid_y, nullptr);
 
     prof_begin(2, stream);
     if ((rc = launch_binning(P, (int)R, (int)Rc, vp, g, b, img, stream))) return rc;
@@ -276,7 +282,7 @@ int segs_raster_backward(
     const ViewParams vp = make_view(width, height, tan_fovx, tan_fovy, scale_modifier);
     const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
     GeomState g = GeomState::carve(geom_buffer, P, nullptr);
-    BinningState b = BinningState::carve(binning_buffer, R, 0, P, T, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, 0, P, vp.grid_x, vp.grid_y, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
     int rc;
     if (R > 0) {
@@ -356,7 +362,7 @@ int segs_buffer_section(const char* name, char* geom_buffer, char* binning_buffe
     const ViewParams vp = make_view(width, height, 1.f, 1.f, 1.f);
     const size_t N = size_t(width) * height, T = size_t(vp.grid_x) * vp.grid_y;
     GeomState g = GeomState::carve(geom_buffer, P, nullptr);
-    BinningState b = BinningState::carve(binning_buffer, R, 0, P, T, nullptr);
+    BinningState b = BinningState::carve(binning_buffer, R, 0, P, vp.grid_x, vp.grid_y, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
     const std::string n(name);
     auto out = [&](void* p, size_t sz) { *ptr = p; *bytes = sz; return SEGS_OK; };

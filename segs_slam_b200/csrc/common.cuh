@@ -52,12 +52,14 @@ struct Carver {
 
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX_BINS = 1 << RADIX_BITS;
-constexpr int SORT_THREADS = 256;
-constexpr int SORT_ITEMS = 4;                        // items per thread per block
-constexpr int SORT_TILE = SORT_THREADS * SORT_ITEMS; // 1024 elements per block (P-sized sorts:
-                                                     // many small CTAs hide latency better)
 
-inline int sort_blocks(size_t n) { return int((n + SORT_TILE - 1) / SORT_TILE); }
+// stable LSD radix sort of (u32 key, u32 value) pairs (radix_sort.cu): `npasses` 8-bit digits
+// starting at `begin_bit`; ping-pongs between (key_a,val_a) and (key_b,val_b), the result is in
+// the a-buffers for an even number of passes and in the b-buffers otherwise.  `iota_values`:
+// val_a is not read, values start as 0..n-1.  temp: radix_sort_temp_words(n, npasses) u32 words.
+size_t radix_sort_temp_words(size_t n, int npasses);
+int radix_sort_pairs(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, size_t n,
+                     int begin_bit, int npasses, bool iota_values, uint32_t* temp, cudaStream_t stream);
 
 // Per-Gaussian render record, 48 bytes (three float4):
 //   rec[3i+0] = { x, y, hx, hy }            2D mean (pixels), conservative half extents
@@ -79,8 +81,7 @@ struct GeomState {
     uint32_t* key_b;          // [P] depth-sort pong
     uint32_t* val_a;          // [P]
     uint32_t* val_b;          // [P]  -> depth order after 4 passes lives in val_a
-    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(P)]
-    uint32_t* global_hist;    // [RADIX_BINS]
+    uint32_t* sort_temp;      // [radix_sort_temp_words(P, 4)]
     uint32_t* counters;       // [8]: 0 = num_rendered (sum of tiles_touched), 1 = error flag,
                               //      2 = number of coarse (super-tile, Gaussian) candidates,
                               //      3 = num_rendered as seen by the tile scan (cross-check)
@@ -88,20 +89,26 @@ struct GeomState {
 };
 
 // two-level tile binning (binning.cu): super-tiles of (1 << sshift)^2 tiles
-struct BinningPlan { int sshift, sgrid_x, sgrid_y; };
+struct BinningPlan { int sshift, sgrid_x, sgrid_y, sort_passes; };
 BinningPlan plan_binning(int grid_x, int grid_y);
+int emit_blocks(int P);       // CTAs of the candidate expansion (one look-back word each)
 
 struct BinningState {
     uint32_t* point_list;     // [R]   Gaussian ids, tile-major, depth-minor
-    uint32_t* cand_key_a;     // [Rc]  super-tile id of each candidate (depth order)
+    uint32_t* cand_key_a;     // [Rc]  super-tile id | 16-bit tile mask << 16 of each candidate (depth order)
     uint32_t* cand_key_b;     // [Rc]
     uint32_t* cand_val_a;     // [Rc]  Gaussian id of each candidate
     uint32_t* cand_val_b;     // [Rc]  -> grouped by super-tile, depth order inside
-    uint32_t* block_hist;     // [RADIX_BINS * sort_blocks(Rc)]
-    uint32_t* global_hist;    // [RADIX_BINS] candidates per super-tile
-    uint32_t* partials;       // [scan blocks]
+    uint32_t* sort_temp;      // [radix_sort_temp_words(Rc, passes)]
+    // ---- zeroed with one memset before the binning kernels run ----
+    uint32_t* zeroed;
+    size_t    zeroed_bytes;
+    uint32_t* emit_ticket;    // [1]
+    uint32_t* emit_look;      // [emit_blocks(P)]
+    uint32_t* st_begin;       // [super-tiles] candidate range of every super-tile
+    uint32_t* st_end;         // [super-tiles]
     uint32_t* tile_counts;    // [T]
-    static BinningState carve(char* base, size_t R, size_t Rc, size_t P, size_t T, size_t* bytes);
+    static BinningState carve(char* base, size_t R, size_t Rc, size_t P, int grid_x, int grid_y, size_t* bytes);
 };
 
 struct ImageState {
@@ -166,10 +173,5 @@ int launch_preprocess_backward(int P, int D, int M, const float* means3D, const 
                                float* dL_dcolor, float* dL_dmean3D, float* dL_dcov3D,
                                float* dL_dsh, float* dL_dscale, float* dL_drot,
                                cudaStream_t stream);
-
-// generic device primitives (binning.cu)
-int radix_pass(const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in,
-               uint32_t* val_out, size_t n, int shift, uint32_t* block_hist,
-               uint32_t* global_hist, cudaStream_t stream);
 
 }  // namespace segs

@@ -284,8 +284,8 @@ extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists
                      uint32_t*& gh, float*& partial, float4*& sorted, Box*& boxes) {
         ka = c.take<uint32_t>(P); kb = c.take<uint32_t>(P);
         va = c.take<uint32_t>(P); vb = c.take<uint32_t>(P);
-        bh = c.take<uint32_t>(size_t(RADIX_BINS) * sort_blocks(P));
-        gh = c.take<uint32_t>(RADIX_BINS);
+        bh = c.take<uint32_t>(radix_sort_temp_words(P, 4));
+        gh = nullptr;
         partial = c.take<float>(size_t(npartial) * 6);
         sorted = c.take<float4>(P);
         boxes = c.take<Box>(nboxes);
@@ -302,11 +302,9 @@ extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists
     SEGS_LAUNCH_CHECK();
     morton_kernel<<<(P + 255) / 256, 256, 0, stream>>>(P, points, partial, npartial, ka, va);
     SEGS_LAUNCH_CHECK();
-    int rc;
-    if ((rc = radix_pass(ka, kb, va, vb, P, 0, bh, gh, stream))) return rc;
-    if ((rc = radix_pass(kb, ka, vb, va, P, 8, bh, gh, stream))) return rc;
-    if ((rc = radix_pass(ka, kb, va, vb, P, 16, bh, gh, stream))) return rc;
-    if ((rc = radix_pass(kb, ka, vb, va, P, 24, bh, gh, stream))) return rc;
+    // Morton order: 4 stable digits over the 30-bit codes; the result is back in (ka, va)
+    const int rc = radix_sort_pairs(ka, kb, va, vb, (size_t)P, 0, 4, false, bh, stream);
+    if (rc) return rc;
     gather_box_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, points, va, sorted, boxes);
     SEGS_LAUNCH_CHECK();
     knn_search_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, sorted, boxes, nboxes, mean_dists);

@@ -360,7 +360,6 @@ preprocess_kernel(int P, int D, int M,
     // ---- Mode::Render -------------------------------------------------------------
     if (radii != nullptr) radii[idx] = visible ? pr.radius : 0;
     tiles_touched[idx] = visible ? pr.tiles : 0u;
-    sort_val[idx] = (uint32_t)idx;
     if (!visible) {
         sort_key[idx] = 0xFFFFFFFFu;   // sorts behind every real depth (depth > 0.2 => sign bit 0)
         depths[idx] = 0.f;
