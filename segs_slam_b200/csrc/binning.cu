@@ -300,38 +300,66 @@ tile_scan_kernel(int T, const uint32_t* __restrict__ tile_counts, uint2* __restr
 // ---------------------------------------------------------------------------------------
 // fine level: warp = tile, ordered ballot compaction of the super-tile's candidate list
 // ---------------------------------------------------------------------------------------
-constexpr int FINE_WARPS = 4;       // CTA = one tile row of a super-tile
+constexpr int FINE_SEGS = 8;        // the candidate list is cut into 8 contiguous segments ...
+constexpr int FINE_THREADS = SSIDE * FINE_SEGS * 32;   // ... one warp per (tile of the row, segment)
 
-__global__ void __launch_bounds__(FINE_WARPS * 32)
+// CTA = one tile row (4 tiles) of a super-tile.  Phase 1: every warp counts its tile's hits in its
+// segment; phase 2: it compacts them behind the hits of the earlier segments.  32 warps share the
+// list through L1, and no warp walks more than 1/8 of it.
+__global__ void __launch_bounds__(FINE_THREADS)
 fine_write_kernel(int sgrid_x, int grid_x, int grid_y, const uint32_t* __restrict__ st_begin,
                   const uint32_t* __restrict__ st_end, const uint32_t* __restrict__ keys,
                   const uint32_t* __restrict__ vals, const uint2* __restrict__ ranges,
                   uint32_t* __restrict__ point_list)
 {
-    const int lane = threadIdx.x & 31, lx = threadIdx.x >> 5;
+    __shared__ uint32_t s_cnt[SSIDE][FINE_SEGS];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int lx = warp & (SSIDE - 1), seg = warp >> SSHIFT;
     const int st = blockIdx.x >> SSHIFT, ly = blockIdx.x & (SSIDE - 1);
     const int tx = ((st % sgrid_x) << SSHIFT) + lx, ty = ((st / sgrid_x) << SSHIFT) + ly;
-    if (tx >= grid_x || ty >= grid_y) return;
-    const uint2 range = ranges[ty * grid_x + tx];
-    if (range.x == range.y) return;
+    const bool live = tx < grid_x && ty < grid_y;
     const uint32_t begin = st_begin[st], end = st_end[st];
+    // segment length: a multiple of 32 so every warp reads whole aligned-to-begin chunks
+    const uint32_t seg_len = (((end - begin + FINE_SEGS - 1) / FINE_SEGS) + 31u) & ~31u;
+    const uint32_t s0 = min(end, begin + seg * seg_len), s1 = min(end, s0 + seg_len);
     const int bit = 16 + ly * SSIDE + lx;
-    const uint32_t lt = (1u << lane) - 1u;
-    uint32_t* out = point_list + range.x;
-    uint32_t run = 0;
     constexpr int UNROLL = 4;
-    for (uint32_t c = begin; c < end; c += 32 * UNROLL) {
-        uint32_t k[UNROLL];
+
+    uint32_t cnt = 0;
+    if (live) {
+        for (uint32_t c = s0; c < s1; c += 32 * UNROLL) {
+            uint32_t k[UNROLL];
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) {
+                const uint32_t e = c + u * 32 + lane;
+                k[u] = (e < s1) ? __ldg(keys + e) : 0u;
+            }
+#pragma unroll
+            for (int u = 0; u < UNROLL; ++u) cnt += (k[u] >> bit) & 1u;
+        }
+        cnt = __reduce_add_sync(FULL, cnt);
+    }
+    if (lane == 0) s_cnt[lx][seg] = cnt;
+    __syncthreads();
+    if (!live || cnt == 0) return;
+    uint32_t run = ranges[ty * grid_x + tx].x;
+#pragma unroll
+    for (int q = 0; q < FINE_SEGS; ++q)
+        if (q < seg) run += s_cnt[lx][q];
+    const uint32_t lt = (1u << lane) - 1u;
+    for (uint32_t c = s0; c < s1; c += 32 * UNROLL) {
+        uint32_t k[UNROLL], v[UNROLL];
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const uint32_t e = c + u * 32 + lane;
-            k[u] = (e < end) ? __ldg(keys + e) : 0u;
+            k[u] = (e < s1) ? __ldg(keys + e) : 0u;
+            v[u] = (e < s1) ? __ldg(vals + e) : 0u;
         }
 #pragma unroll
         for (int u = 0; u < UNROLL; ++u) {
             const bool hit = (k[u] >> bit) & 1u;
             const unsigned m = __ballot_sync(FULL, hit);
-            if (hit) out[run + __popc(m & lt)] = __ldg(vals + c + u * 32 + lane);
+            if (hit) point_list[run + __popc(m & lt)] = v[u];
             run += __popc(m);
         }
     }
@@ -391,7 +419,7 @@ int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, Bin
     SEGS_LAUNCH_CHECK();
     tile_scan_kernel<<<1, 1024, 0, stream>>>(T, b.tile_counts, img.ranges, g.counters + 3);
     SEGS_LAUNCH_CHECK();
-    fine_write_kernel<<<nst * SSIDE, FINE_WARPS * 32, 0, stream>>>(pl.sgrid_x, vp.grid_x, vp.grid_y, b.st_begin, b.st_end,
+    fine_write_kernel<<<nst * SSIDE, FINE_THREADS, 0, stream>>>(pl.sgrid_x, vp.grid_x, vp.grid_y, b.st_begin, b.st_end,
                                                                   keys, vals, img.ranges, b.point_list);
     SEGS_LAUNCH_CHECK();
     if (getenv("SEGS_DEBUG_BINNING")) {

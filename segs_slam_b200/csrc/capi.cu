@@ -95,15 +95,21 @@ static ViewParams make_view(int width, int height, float tan_fovx, float tan_fov
     return vp;
 }
 
-// One pinned word per host thread for the num_rendered / error-flag readback.
-static uint32_t* pinned_words() {
-    static thread_local uint32_t* p = nullptr;
-    if (!p) {
-        if (cudaHostAlloc(reinterpret_cast<void**>(&p), 8 * sizeof(uint32_t), cudaHostAllocDefault) != cudaSuccess) {
-            p = nullptr;
+// A few words of MAPPED pinned memory per host thread: the preprocess kernel stores
+// num_rendered / the error flag / the candidate count there directly (no copy engine).
+struct HostWords { uint32_t* host = nullptr; uint32_t* dev = nullptr; };
+static HostWords pinned_words() {
+    static thread_local HostWords w;
+    if (!w.host) {
+        void* h = nullptr;
+        void* d = nullptr;
+        if (cudaHostAlloc(&h, 8 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&d, h, 0) == cudaSuccess) {
+            w.host = static_cast<uint32_t*>(h);
+            w.dev = static_cast<uint32_t*>(d);
         }
     }
-    return p;
+    return w;
 }
 
 // One event per host thread marking "num_rendered has landed in pinned memory".
@@ -215,20 +221,21 @@ int segs_raster_forward(
     if (!img_ptr) { set_error("image buffer allocation of %zu bytes failed", img_bytes); return SEGS_ERR_ALLOC; }
     ImageState img = ImageState::carve(img_ptr, N, T, nullptr);
 
-    uint32_t* host_words = pinned_words();
-    if (!host_words) { set_error("cudaHostAlloc for the readback word failed"); return SEGS_ERR_CUDA; }
+    const HostWords hw = pinned_words();
+    if (!hw.host) { set_error("cudaHostAlloc for the readback words failed"); return SEGS_ERR_CUDA; }
+    volatile uint32_t* host_words = hw.host;
 
     SEGS_CUDA_CHECK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), stream));
     int rc;
     prof_begin(0, stream);
     if ((rc = launch_preprocess(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,
                                 colors_precomp, viewmatrix, projmatrix, cam_pos, vp, prefiltered != 0,
-                                radii, g, stream))) return rc;
+                                radii, g, hw.dev, stream))) return rc;
     prof_end(0, stream);
-    // num_rendered (accumulated by the preprocess) sizes the binning buffer, so it has to reach
-    // the host (rasterizer_impl.cu:279-285) — but only the preprocess is waited for: the depth
-    // sort is already queued behind the copy and runs while the host allocates.
-    SEGS_CUDA_CHECK(cudaMemcpyAsync(host_words, g.counters, 3 * sizeof(uint32_t), cudaMemcpyDeviceToHost, stream));
+    // num_rendered (accumulated by the preprocess and stored to mapped host memory by its last
+    // CTA) sizes the binning buffer, so the host has to see it (rasterizer_impl.cu:279-285) — but
+    // only the preprocess is waited for: the depth sort is already queued and runs while the
+    // host allocates.
     cudaEvent_t ready = readback_event();
     if (!ready) { set_error("cudaEventCreate failed"); return SEGS_ERR_CUDA; }
     SEGS_CUDA_CHECK(cudaEventRecord(ready, stream));

@@ -84,7 +84,8 @@ struct GeomState {
     uint32_t* sort_temp;      // [radix_sort_temp_words(P, 4)]
     uint32_t* counters;       // [8]: 0 = num_rendered (sum of tiles_touched), 1 = error flag,
                               //      2 = number of coarse (super-tile, Gaussian) candidates,
-                              //      3 = num_rendered as seen by the tile scan (cross-check)
+                              //      3 = num_rendered as seen by the tile scan (cross-check),
+                              //      4 = preprocess CTAs finished (the last one publishes 0-2 to the host)
     static GeomState carve(char* base, size_t P, size_t* bytes);
 };
 
@@ -133,7 +134,7 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sc
                       const float* cov3D_precomp, const float* colors_precomp,
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
                       const ViewParams& vp, bool prefiltered, int* radii, GeomState& g,
-                      cudaStream_t stream);
+                      uint32_t* host_counters /* mapped pinned memory, device address */, cudaStream_t stream);
 
 int launch_filter(int P, const float* means3D, const float* scales, const float* rotations,
                   const float* cov3D_precomp, const float* viewmatrix, const float* projmatrix,

@@ -266,6 +266,7 @@ preprocess_kernel(int P, int D, int M,
                   float4* __restrict__ acc, uint8_t* __restrict__ clamped,
                   uint32_t* __restrict__ sort_key, uint32_t* __restrict__ sort_val,
                   uint32_t* __restrict__ err_flag, uint32_t* __restrict__ num_rendered,
+                  volatile uint32_t* __restrict__ host_counters,
                   // Project outputs
                   float* __restrict__ out_rgb, float* __restrict__ points_image)
 {
@@ -325,6 +326,20 @@ preprocess_kernel(int P, int D, int M,
         if ((threadIdx.x & 31) == 0 && warp_tiles) {
             atomicAdd(num_rendered, warp_tiles);
             atomicAdd(num_rendered + 2, warp_cand);
+        }
+        // The host needs the totals to size the binning buffer (rasterizer_impl.cu:279-285).  The
+        // last CTA to get here stores them straight into mapped pinned host memory: no copy
+        // engine is involved, so the read-back never queues behind a caller's bulk D2H copies.
+        __syncthreads();
+        if (threadIdx.x == 0 && host_counters != nullptr) {
+            __threadfence();
+            if (atomicAdd(num_rendered + 4, 1u) == gridDim.x - 1) {
+                __threadfence();
+                host_counters[0] = atomicAdd(num_rendered, 0u);
+                host_counters[1] = atomicAdd(num_rendered + 1, 0u);
+                host_counters[2] = atomicAdd(num_rendered + 2, 0u);
+                __threadfence_system();
+            }
         }
     }
     if (!in_range) return;
@@ -420,13 +435,13 @@ int launch_preprocess(int P, int D, int M, const float* means3D, const float* sc
                       const float* cov3D_precomp, const float* colors_precomp,
                       const float* viewmatrix, const float* projmatrix, const float* cam_pos,
                       const ViewParams& vp, bool prefiltered, int* radii, GeomState& g,
-                      cudaStream_t stream)
+                      uint32_t* host_counters, cudaStream_t stream)
 {
     preprocess_kernel<Mode::Render><<<grid_for(P), PRE_THREADS, 0, stream>>>(
         P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
         viewmatrix, projmatrix, cam_pos, vp, prefiltered ? 1 : 0, radii, g.depths,
         g.tiles_touched, g.rect, g.rec, g.cov3D, g.acc, g.clamped, g.key_a, g.val_a,
-        g.counters + 1, g.counters, nullptr, nullptr);
+        g.counters + 1, g.counters, host_counters, nullptr, nullptr);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
@@ -439,7 +454,7 @@ int launch_filter(int P, const float* means3D, const float* scales, const float*
     preprocess_kernel<Mode::Filter><<<grid_for(P), PRE_THREADS, 0, stream>>>(
         P, 0, 0, means3D, scales, rotations, nullptr, nullptr, cov3D_precomp, nullptr,
         viewmatrix, projmatrix, nullptr, vp, prefiltered ? 1 : 0, radii, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, nullptr, nullptr, nullptr);
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, err_flag, nullptr, nullptr, nullptr, nullptr);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
@@ -454,7 +469,7 @@ int launch_project(int P, int D, int M, const float* means3D, const float* scale
     preprocess_kernel<Mode::Project><<<grid_for(P), PRE_THREADS, 0, stream>>>(
         P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp, colors_precomp,
         viewmatrix, projmatrix, cam_pos, vp, prefiltered ? 1 : 0, radii, nullptr, nullptr,
-        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_rgb,
+        nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, out_rgb,
         points_image);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
