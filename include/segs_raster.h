@@ -191,6 +191,77 @@ int segs_knn_mean_dist2(
     segs_alloc_fn scratch_alloc, void* scratch_user,
     void* stream);
 
+/* ---- structure-enhanced anchor decode -------------------------------------------------- */
+/* Replaces GaussianRenderer::generate_neural_gaussians (src/gaussian_renderer.cpp:214-334): the
+ * visible-anchor gather, the optional feature-bank mix, the pose "appearance" Linear(7 -> app), the
+ * opacity / covariance / colour MLPs (module shapes: src/gaussian_model.cpp:60-98; feat_dim = 32,
+ * n_offsets = 10 as in every shipped config), the opacity > 0 mask and the assembly of the
+ * surviving neural Gaussians — one fused kernel instead of ~40 ATen launches and the
+ * [A*10, 22] temporary.
+ *
+ * Weights use torch::nn::Linear's layout: weight [out, in] row-major, bias [out]; all DEVICE
+ * pointers.  Input column order of the first layers: [feat(32), ob_view(3), ob_dist(1, only with
+ * the add_*_dist flag), appearance(appearance_dim, colour MLP only)].  app_* may be NULL when
+ * appearance_dim == 0, bank_* when use_feat_bank == 0. */
+typedef struct segs_decode_params {
+    const float* opacity_w1; const float* opacity_b1; const float* opacity_w2; const float* opacity_b2; /* [32,35+d] [32] [10,32] [10] */
+    const float* cov_w1;     const float* cov_b1;     const float* cov_w2;     const float* cov_b2;     /* [32,35+d] [32] [70,32] [70] */
+    const float* color_w1;   const float* color_b1;   const float* color_w2;   const float* color_b2;   /* [32,35+d+app] [32] [30,32] [30] */
+    const float* app_w;      const float* app_b;                                                        /* [app,7] [app] */
+    const float* bank_w1;    const float* bank_b1;    const float* bank_w2;    const float* bank_b2;    /* [32,4] [32] [3,32] [3] */
+    int appearance_dim;      /* 0..32 */
+    int use_feat_bank;
+    int add_opacity_dist, add_cov_dist, add_color_dist;
+} segs_decode_params;
+
+/* Gradient outputs of segs_decode_backward, same shapes as the weights; fully written. */
+typedef struct segs_decode_grads {
+    float* opacity_w1; float* opacity_b1; float* opacity_w2; float* opacity_b2;
+    float* cov_w1;     float* cov_b1;     float* cov_w2;     float* cov_b2;
+    float* color_w1;   float* color_b1;   float* color_w2;   float* color_b2;
+    float* app_w;      float* app_b;
+    float* bank_w1;    float* bank_b1;    float* bank_w2;    float* bank_b2;
+} segs_decode_grads;
+
+/* Bytes of caller-owned state that forward fills and backward reads (anchor ordinals, row starts,
+ * masks, look-back words). */
+size_t segs_decode_state_bytes(int A);
+
+/* visible_mask: [A] bytes (C++ bool) or NULL = all visible.  scaling = exp(_scaling) [A,6]
+ * (GaussianModel::get_scaling).  pose = {t.x, t.y, t.z, q.w, q.x, q.y, q.z} of the keyframe (HOST
+ * floats, gaussian_renderer.cpp:258-261).  Row outputs have capacity n_vis*10 <= A*10 rows and are
+ * written compacted, in (anchor, offset) order: xyz [.,3], color [.,3], opacity [.,1],
+ * out_scaling [.,3], rot [.,4].  neural_opacity [A*10] and mask [A*10] (bytes) are indexed by
+ * (visible-anchor ordinal * 10 + offset).  counts (HOST) receives {visible anchors, emitted
+ * Gaussians}; the call waits for the kernel, like the reference's boolean indexing does. */
+int segs_decode_forward(
+    int A, const unsigned char* visible_mask,
+    const float* anchor, const float* anchor_feat, const float* offset, const float* scaling,
+    const float* camera_center, const float* pose,
+    const segs_decode_params* params,
+    float* xyz, float* color, float* opacity, float* out_scaling, float* rot,
+    float* neural_opacity, unsigned char* mask,
+    char* state, int* counts,
+    void* stream);
+
+/* g_* are the gradients w.r.t. the compacted row outputs (n_out rows); g_neural_opacity
+ * ([n_vis*10], may be NULL) the gradient w.r.t. the un-masked opacity output.  d_anchor [A,3],
+ * d_anchor_feat [A,32], d_offset [A,10,3], d_scaling [A,6] (w.r.t. the `scaling` input) and every
+ * tensor of *dparams are fully written (zeros for invisible anchors).  scratch grows one opaque
+ * device buffer for the per-anchor factors of the weight gradients. */
+int segs_decode_backward(
+    int A, const unsigned char* visible_mask,
+    const float* anchor, const float* anchor_feat, const float* offset, const float* scaling,
+    const float* camera_center, const float* pose,
+    const segs_decode_params* params,
+    const char* state, int n_vis, int n_out,
+    const float* g_xyz, const float* g_color, const float* g_opacity, const float* g_scaling, const float* g_rot,
+    const float* g_neural_opacity,
+    float* d_anchor, float* d_anchor_feat, float* d_offset, float* d_scaling,
+    const segs_decode_grads* dparams,
+    segs_alloc_fn scratch_alloc, void* scratch_user,
+    void* stream);
+
 /* ---- per-stage device timing (bench.py roofline) -------------------------------------- */
 /* When enabled (per host thread), segs_raster_forward / segs_raster_backward bracket their
  * stages with CUDA events on the caller's stream.  segs_profile_read synchronises those

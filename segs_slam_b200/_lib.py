@@ -17,6 +17,23 @@ ALLOC_FN = C.CFUNCTYPE(C.c_void_p, C.c_void_p, C.c_size_t)
 _f32p = C.c_void_p  # device pointers travel as plain addresses
 _i32p = C.c_void_p
 
+_PARAM_NAMES = ("opacity_w1", "opacity_b1", "opacity_w2", "opacity_b2", "cov_w1", "cov_b1", "cov_w2", "cov_b2",
+                "color_w1", "color_b1", "color_w2", "color_b2", "app_w", "app_b", "bank_w1", "bank_b1", "bank_w2",
+                "bank_b2")
+
+
+class DecodeParams(C.Structure):
+    """segs_decode_params (include/segs_raster.h)."""
+    _fields_ = [(n, C.c_void_p) for n in _PARAM_NAMES] + [
+        ("appearance_dim", C.c_int), ("use_feat_bank", C.c_int), ("add_opacity_dist", C.c_int),
+        ("add_cov_dist", C.c_int), ("add_color_dist", C.c_int)]
+
+
+class DecodeGrads(C.Structure):
+    """segs_decode_grads (include/segs_raster.h)."""
+    _fields_ = [(n, C.c_void_p) for n in _PARAM_NAMES]
+
+
 _PROTOTYPES = {
     "segs_version": (C.c_int, []),
     "segs_last_error": (C.c_char_p, []),
@@ -52,6 +69,18 @@ _PROTOTYPES = {
          C.c_float, C.c_float, C.c_int, _f32p, _f32p, _i32p, C.c_void_p],
     ),
     "segs_knn_mean_dist2": (C.c_int, [C.c_int, _f32p, _f32p, ALLOC_FN, C.c_void_p, C.c_void_p]),
+    "segs_decode_state_bytes": (C.c_size_t, [C.c_int]),
+    "segs_decode_forward": (
+        C.c_int,
+        [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),
+         _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_void_p, C.c_void_p, C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "segs_decode_backward": (
+        C.c_int,
+        [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),
+         C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+         _f32p, _f32p, _f32p, _f32p, C.POINTER(DecodeGrads), ALLOC_FN, C.c_void_p, C.c_void_p],
+    ),
     "segs_launch_count": (C.c_ulonglong, []),
     "segs_profile_enable": (C.c_int, [C.c_int]),
     "segs_profile_read": (C.c_int, [C.POINTER(C.c_float)]),

@@ -1,0 +1,952 @@
+// Structure-enhanced anchor decode for sm_100a.
+//
+// Replaces GaussianRenderer::generate_neural_gaussians of the reference
+// (src/gaussian_renderer.cpp:214-334; module shapes src/gaussian_model.cpp:60-98): boolean-mask
+// gathers of the anchor tensors, the feature-bank mix, the pose-appearance Linear, three small
+// MLPs, the opacity > 0 mask, repeat/cat into a [A*10, 22] temporary and a second boolean gather —
+// about 40 ATen kernels and ~1 GB of temporaries at 200k anchors.
+//
+// Forward (ONE kernel, thread = visible anchor, CTA = 128 consecutive anchors):
+//   * all weights (7.5k floats) live in shared memory, rows padded to float4 so that every
+//     weight fetch is one broadcast LDS.128 feeding four FFMAs; the appearance columns of the
+//     colour MLP are view-constant and are folded into its bias once per CTA;
+//   * both compactions (visible anchors, surviving offsets) are done in-kernel: CTA-local ballot
+//     scans plus a decoupled look-back over the preceding CTAs (atomic ticket => only running
+//     CTAs are waited for), so rows come out in the reference's (anchor, offset) order with no
+//     temporaries and no second pass.  The two totals are stored to mapped host memory by the last
+//     CTA (the host needs them to shape the outputs, as the reference's boolean indexing does).
+// Backward (two kernels):
+//   1. thread = visible anchor: recomputes the forward, back-propagates the row gradients to
+//      d_anchor / d_offset / d_anchor_feat / d_scaling and stores the per-anchor factors of the
+//      weight gradients (layer inputs and pre-activation gradients) feature-major in scratch;
+//   2. persistent CTAs turn those factors into the weight gradients: every job is
+//      dW[p][q] = sum_k U[k][p] * V[k][q] with q on the 32 lanes, accumulated in registers over
+//      all anchors and flushed once with atomics.
+// FP32 FFMA throughout (accumulation order differs from cuBLAS sgemm at the 1e-6 level).  The two
+// GEMM-shaped parts (layer products, weight-gradient sums) are the tcgen05 candidates of the path;
+// see DESIGN.md §decode.
+#include <algorithm>
+#include "common.cuh"
+
+namespace segs {
+
+namespace {
+
+constexpr unsigned FULL = 0xFFFFFFFFu;
+constexpr int FEAT = 32;        // Model.feat_dim
+constexpr int NOFF = 10;        // Model.n_offsets
+constexpr int XDIM = 36;        // feat(32) + view(3) + dist(1)
+constexpr int DEC_THREADS = 128;
+constexpr uint32_t FLAG_AGG = 1u << 30;
+constexpr uint32_t FLAG_PREFIX = 2u << 30;
+constexpr uint32_t FLAG_MASK = 3u << 30;
+
+struct Pose7 { float v[7]; };
+
+// shared-memory copy of the weights
+struct SW {
+    float w1[3][FEAT][XDIM];     // 0 opacity, 1 cov, 2 colour: first 35(+dist) input columns, zero padded
+    float b1[3][FEAT];           // colour: b1 + W1[:, appearance columns] * appearance
+    float w2o[NOFF][FEAT];
+    float w2s[7 * NOFF][FEAT];
+    float w2c[3 * NOFF][FEAT];
+    float b2o[12];
+    float b2s[72];
+    float b2c[32];
+    float wb1[FEAT][4];
+    float bb1[FEAT];
+    float wb2[3][FEAT];
+    float bb2[4];
+    float app[32];               // appearance vector of this view
+};
+
+// opaque state shared by forward and backward
+struct DecodeState {
+    uint32_t* counters;       // [8]: 0 ticket
+    uint32_t* look_vis;       // [tiles]
+    uint32_t* look_row;       // [tiles]
+    uint32_t* anchor_index;   // [A] anchor id of every visible ordinal
+    uint32_t* row_start;      // [A] first output row of every visible ordinal
+    uint32_t* mask_bits;      // [A] surviving-offset bits of every visible ordinal
+    size_t zero_bytes;        // counters + look words
+    static DecodeState carve(char* base, size_t A, size_t* bytes) {
+        Carver c(base);
+        DecodeState s;
+        const size_t tiles = (A + DEC_THREADS - 1) / DEC_THREADS;
+        s.counters = c.take<uint32_t>(8 + 2 * tiles);
+        s.look_vis = s.counters + 8;
+        s.look_row = s.look_vis + tiles;
+        s.zero_bytes = (8 + 2 * tiles) * sizeof(uint32_t);
+        s.anchor_index = c.take<uint32_t>(A);
+        s.row_start = c.take<uint32_t>(A);
+        s.mask_bits = c.take<uint32_t>(A);
+        if (bytes) *bytes = c.used(base) + 128;
+        return s;
+    }
+};
+
+__device__ __forceinline__ void stage_weights(SW& s, const segs_decode_params& p, const Pose7& pose)
+{
+    const int tid = threadIdx.x, nt = blockDim.x;
+    const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
+    const int in_c = 35 + (p.add_color_dist ? 1 : 0);
+    const int ld_c = in_c + p.appearance_dim;
+    for (int e = tid; e < FEAT * XDIM; e += nt) {
+        const int j = e / XDIM, i = e % XDIM;
+        s.w1[0][j][i] = i < in_o ? __ldg(p.opacity_w1 + j * in_o + i) : 0.f;
+        s.w1[1][j][i] = i < in_s ? __ldg(p.cov_w1 + j * in_s + i) : 0.f;
+        s.w1[2][j][i] = i < in_c ? __ldg(p.color_w1 + j * ld_c + i) : 0.f;
+    }
+    for (int e = tid; e < NOFF * FEAT; e += nt) (&s.w2o[0][0])[e] = __ldg(p.opacity_w2 + e);
+    for (int e = tid; e < 7 * NOFF * FEAT; e += nt) (&s.w2s[0][0])[e] = __ldg(p.cov_w2 + e);
+    for (int e = tid; e < 3 * NOFF * FEAT; e += nt) (&s.w2c[0][0])[e] = __ldg(p.color_w2 + e);
+    for (int e = tid; e < 72; e += nt) {
+        if (e < 12) s.b2o[e] = e < NOFF ? __ldg(p.opacity_b2 + e) : 0.f;
+        s.b2s[e] = e < 7 * NOFF ? __ldg(p.cov_b2 + e) : 0.f;
+        if (e < 32) s.b2c[e] = e < 3 * NOFF ? __ldg(p.color_b2 + e) : 0.f;
+    }
+    if (tid < FEAT) {
+        s.b1[0][tid] = __ldg(p.opacity_b1 + tid);
+        s.b1[1][tid] = __ldg(p.cov_b1 + tid);
+        // appearance = Linear(7 -> app)(pose)   (gaussian_renderer.cpp:256-270)
+        float a = 0.f;
+        if (tid < p.appearance_dim) {
+            a = __ldg(p.app_b + tid);
+#pragma unroll
+            for (int q = 0; q < 7; ++q) a = fmaf(__ldg(p.app_w + tid * 7 + q), pose.v[q], a);
+        }
+        s.app[tid] = a;
+        if (p.use_feat_bank) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) s.wb1[tid][i] = __ldg(p.bank_w1 + tid * 4 + i);
+            s.bb1[tid] = __ldg(p.bank_b1 + tid);
+#pragma unroll
+            for (int m = 0; m < 3; ++m) s.wb2[m][tid] = __ldg(p.bank_w2 + m * FEAT + tid);
+            if (tid < 4) s.bb2[tid] = tid < 3 ? __ldg(p.bank_b2 + tid) : 0.f;
+        }
+    }
+    __syncthreads();
+    if (tid < FEAT) {
+        // the appearance input is the same for every anchor of the view: fold its columns into the bias
+        float b = __ldg(p.color_b1 + tid);
+        for (int k = 0; k < p.appearance_dim; ++k) b = fmaf(__ldg(p.color_w1 + tid * ld_c + in_c + k), s.app[k], b);
+        s.b1[2][tid] = b;
+    }
+    __syncthreads();
+}
+
+// h = relu(W1 x + b1)
+__device__ __forceinline__ void layer1(const float (*w)[XDIM], const float* b, const float (&x)[XDIM], float (&h)[FEAT])
+{
+#pragma unroll
+    for (int j = 0; j < FEAT; ++j) {
+        float acc = b[j];
+        const float4* row = reinterpret_cast<const float4*>(w[j]);
+#pragma unroll
+        for (int q = 0; q < XDIM / 4; ++q) {
+            const float4 w4 = row[q];
+            acc = fmaf(w4.x, x[4 * q], acc);
+            acc = fmaf(w4.y, x[4 * q + 1], acc);
+            acc = fmaf(w4.z, x[4 * q + 2], acc);
+            acc = fmaf(w4.w, x[4 * q + 3], acc);
+        }
+        h[j] = fmaxf(acc, 0.f);
+    }
+}
+
+__device__ __forceinline__ float dot32(const float* wrow, float bias, const float (&h)[FEAT])
+{
+    float acc = bias;
+    const float4* row = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int q = 0; q < FEAT / 4; ++q) {
+        const float4 w4 = row[q];
+        acc = fmaf(w4.x, h[4 * q], acc);
+        acc = fmaf(w4.y, h[4 * q + 1], acc);
+        acc = fmaf(w4.z, h[4 * q + 2], acc);
+        acc = fmaf(w4.w, h[4 * q + 3], acc);
+    }
+    return acc;
+}
+
+// v[j] += s * wrow[j]
+__device__ __forceinline__ void axpy32(const float* wrow, float s, float (&v)[FEAT])
+{
+    const float4* row = reinterpret_cast<const float4*>(wrow);
+#pragma unroll
+    for (int q = 0; q < FEAT / 4; ++q) {
+        const float4 w4 = row[q];
+        v[4 * q] = fmaf(w4.x, s, v[4 * q]);
+        v[4 * q + 1] = fmaf(w4.y, s, v[4 * q + 1]);
+        v[4 * q + 2] = fmaf(w4.z, s, v[4 * q + 2]);
+        v[4 * q + 3] = fmaf(w4.w, s, v[4 * q + 3]);
+    }
+}
+
+__device__ __forceinline__ float sigmoidf_(float z) { return 1.f / (1.f + expf(-z)); }
+
+struct AnchorIn {
+    float ax, ay, az;      // anchor
+    float vx, vy, vz;      // anchor - camera centre
+    float dist;
+    float s[6];            // exp(_scaling)
+};
+
+// D1 + D2: inputs of the three MLPs for one anchor.  x = [feat'(32), ob_view(3), ob_dist]
+__device__ __forceinline__ void build_input(const SW& sw, bool use_bank, const float* __restrict__ feat_row,
+                                            const AnchorIn& in, float (&x)[XDIM], float (&bankw)[3])
+{
+    const float ux = in.vx / in.dist, uy = in.vy / in.dist, uz = in.vz / in.dist;
+    float f[FEAT];
+#pragma unroll
+    for (int q = 0; q < FEAT / 4; ++q) {
+        const float4 t = __ldg(reinterpret_cast<const float4*>(feat_row) + q);
+        f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+    }
+    bankw[0] = 0.f; bankw[1] = 0.f; bankw[2] = 1.f;
+    if (use_bank) {
+        // bank weights = softmax(W2 relu(W1 [view, dist] + b1) + b2)   (gaussian_renderer.cpp:236-239)
+        float l0 = sw.bb2[0], l1 = sw.bb2[1], l2 = sw.bb2[2];
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sw.wb1[j]);
+            float hb = sw.bb1[j];
+            hb = fmaf(w4.x, ux, hb); hb = fmaf(w4.y, uy, hb); hb = fmaf(w4.z, uz, hb); hb = fmaf(w4.w, in.dist, hb);
+            hb = fmaxf(hb, 0.f);
+            l0 = fmaf(sw.wb2[0][j], hb, l0); l1 = fmaf(sw.wb2[1][j], hb, l1); l2 = fmaf(sw.wb2[2][j], hb, l2);
+        }
+        const float mx = fmaxf(l0, fmaxf(l1, l2));
+        const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+        const float den = e0 + e1 + e2;
+        bankw[0] = e0 / den; bankw[1] = e1 / den; bankw[2] = e2 / den;
+        // feat'[j] = feat[4 (j mod 8)] w0 + feat[2 (j mod 16)] w1 + feat[j] w2   (:241-248; repeat = tiling)
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j)
+            x[j] = f[4 * (j & 7)] * bankw[0] + f[2 * (j & 15)] * bankw[1] + f[j] * bankw[2];
+    } else {
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) x[j] = f[j];
+    }
+    x[32] = ux; x[33] = uy; x[34] = uz; x[35] = in.dist;
+}
+
+__device__ __forceinline__ AnchorIn load_anchor(const float* __restrict__ anchor, const float* __restrict__ scaling,
+                                                const float* __restrict__ cam, size_t a)
+{
+    AnchorIn in;
+    in.ax = __ldg(anchor + 3 * a); in.ay = __ldg(anchor + 3 * a + 1); in.az = __ldg(anchor + 3 * a + 2);
+    in.vx = in.ax - __ldg(cam); in.vy = in.ay - __ldg(cam + 1); in.vz = in.az - __ldg(cam + 2);
+    in.dist = sqrtf(in.vx * in.vx + in.vy * in.vy + in.vz * in.vz);
+#pragma unroll
+    for (int k = 0; k < 6; ++k) in.s[k] = __ldg(scaling + 6 * a + k);
+    return in;
+}
+
+// decoupled look-back of one running total (executed by warp 0); returns the exclusive prefix
+__device__ __forceinline__ uint32_t lookback(volatile uint32_t* look, uint32_t tile, uint32_t total, int lane)
+{
+    if (lane == 0) look[tile] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | total;
+    uint32_t excl = 0;
+    if (tile != 0) {
+        for (int t = (int)tile - 1;; t -= 32) {
+            uint32_t w = FLAG_PREFIX;
+            if (t - lane >= 0) {
+                do { w = look[t - lane]; } while ((w & FLAG_MASK) == 0u);
+            }
+            const unsigned pref = __ballot_sync(FULL, (w & FLAG_MASK) == FLAG_PREFIX);
+            const int stop = __ffs(pref) - 1;
+            const uint32_t v = (stop < 0 || lane <= stop) ? (w & ~FLAG_MASK) : 0u;
+            excl += __reduce_add_sync(FULL, v);
+            if (stop >= 0) break;
+        }
+        if (lane == 0) look[tile] = FLAG_PREFIX | (excl + total);
+    }
+    return excl;
+}
+
+// CTA-wide exclusive scan of one value per thread (DEC_THREADS threads); *total = CTA sum
+__device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_warp, uint32_t* total)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t inc = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t y = __shfl_up_sync(FULL, inc, o);
+        if (lane >= o) inc += y;
+    }
+    __syncthreads();                 // s_warp may still be read from a previous scan
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    uint32_t woff = 0, tot = 0;
+#pragma unroll
+    for (int w = 0; w < DEC_THREADS / 32; ++w) {
+        const uint32_t c = s_warp[w];
+        if (w < warp) woff += c;
+        tot += c;
+    }
+    *total = tot;
+    return woff + inc - v;
+}
+
+// =======================================================================================
+// forward
+// =======================================================================================
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, const float* __restrict__ anchor,
+                      const float* __restrict__ anchor_feat, const float* __restrict__ offset,
+                      const float* __restrict__ scaling, const float* __restrict__ cam, const Pose7 pose,
+                      const segs_decode_params p, float* __restrict__ out_xyz, float* __restrict__ out_color,
+                      float* __restrict__ out_opacity, float* __restrict__ out_scaling, float* __restrict__ out_rot,
+                      float* __restrict__ neural_opacity, unsigned char* __restrict__ out_mask, DecodeState st,
+                      volatile uint32_t* __restrict__ host_counts)
+{
+    __shared__ __align__(16) SW sw;
+    __shared__ uint32_t s_aid[DEC_THREADS];
+    __shared__ uint32_t s_warp[DEC_THREADS / 32];
+    __shared__ uint32_t s_tile, s_vis_base, s_row_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+
+    if (tid == 0) s_tile = atomicAdd(st.counters, 1u);
+    stage_weights(sw, p, pose);          // (contains __syncthreads)
+    const uint32_t tile = s_tile;
+
+    // ---- D1: compact the visible anchors of this tile (ascending anchor index) ----
+    const size_t a0 = size_t(tile) * DEC_THREADS + tid;
+    const bool vis = a0 < (size_t)A && (visible_mask == nullptr || visible_mask[a0] != 0);
+    uint32_t n_vis;
+    const uint32_t ord = cta_exclusive_scan(vis ? 1u : 0u, s_warp, &n_vis);
+    if (vis) s_aid[ord] = (uint32_t)a0;
+    __syncthreads();
+    const bool active = (uint32_t)tid < n_vis;
+    const size_t a = active ? s_aid[tid] : 0;
+
+    // ---- D2-D4 (opacity): inputs + opacity MLP -> mask ----
+    AnchorIn in;
+    float x[XDIM];
+    float op[NOFF];
+    uint32_t m = 0;
+    if (active) {
+        in = load_anchor(anchor, scaling, cam, a);
+        float bankw[3];
+        build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
+        float h[FEAT];
+        layer1(sw.w1[0], sw.b1[0], x, h);
+#pragma unroll
+        for (int o = 0; o < NOFF; ++o) {
+            op[o] = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+            if (op[o] > 0.0f) m |= 1u << o;               // mask = neural_opacity > 0   (:278-279)
+        }
+    }
+    uint32_t n_rows;
+    const uint32_t row_off = cta_exclusive_scan(__popc(m), s_warp, &n_rows);
+
+    // ---- order across CTAs: exclusive prefixes of visible anchors and surviving rows ----
+    if (tid < 32) {
+        const uint32_t vb = lookback(st.look_vis, tile, n_vis, lane);
+        const uint32_t rb = lookback(st.look_row, tile, n_rows, lane);
+        if (lane == 0) {
+            s_vis_base = vb;
+            s_row_base = rb;
+            if (tile == gridDim.x - 1 && host_counts != nullptr) {
+                host_counts[0] = vb + n_vis;
+                host_counts[1] = rb + n_rows;
+                __threadfence_system();
+            }
+        }
+    }
+    __syncthreads();
+    if (!active) return;
+    const size_t ordinal = size_t(s_vis_base) + tid;
+    const size_t row0 = size_t(s_row_base) + row_off;
+    st.anchor_index[ordinal] = (uint32_t)a;
+    st.row_start[ordinal] = (uint32_t)row0;
+    st.mask_bits[ordinal] = m;
+#pragma unroll
+    for (int o = 0; o < NOFF; ++o) {
+        neural_opacity[ordinal * NOFF + o] = op[o];
+        out_mask[ordinal * NOFF + o] = (m >> o) & 1u;
+    }
+    if (m == 0) return;
+
+    // ---- D4 (cov) + D5: geometry rows ----
+    {
+        float h[FEAT];
+        layer1(sw.w1[1], sw.b1[1], x, h);
+        size_t r = row0;
+#pragma unroll 1
+        for (int o = 0; o < NOFF; ++o) {
+            if (!((m >> o) & 1u)) continue;
+            float sr[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+            const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
+                        oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
+            // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
+            out_xyz[3 * r] = in.ax + ox * in.s[0];
+            out_xyz[3 * r + 1] = in.ay + oy * in.s[1];
+            out_xyz[3 * r + 2] = in.az + oz * in.s[2];
+            out_scaling[3 * r] = in.s[3] * sigmoidf_(sr[0]);
+            out_scaling[3 * r + 1] = in.s[4] * sigmoidf_(sr[1]);
+            out_scaling[3 * r + 2] = in.s[5] * sigmoidf_(sr[2]);
+            const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
+            *reinterpret_cast<float4*>(out_rot + 4 * r) = make_float4(sr[3] / nrm, sr[4] / nrm, sr[5] / nrm, sr[6] / nrm);
+            out_opacity[r] = op[o];
+            ++r;
+        }
+    }
+    // ---- D4 (colour) ----
+    {
+        float h[FEAT];
+        layer1(sw.w1[2], sw.b1[2], x, h);
+        size_t r = row0;
+#pragma unroll 1
+        for (int o = 0; o < NOFF; ++o) {
+            if (!((m >> o) & 1u)) continue;
+#pragma unroll
+            for (int k = 0; k < 3; ++k) out_color[3 * r + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
+            ++r;
+        }
+    }
+}
+
+// =======================================================================================
+// backward, kernel 1: per-anchor back-propagation + factors of the weight gradients
+// =======================================================================================
+// scratch: [tile of 64 ordinals][FACT_ROWS][64] floats (feature-major inside a tile)
+constexpr int FT = 64;                 // ordinals per scratch tile
+constexpr int F_X = 0;                 // x[36]
+constexpr int F_H = F_X + XDIM;        // h of opacity / cov / colour [3][32]
+constexpr int F_DPRE = F_H + 3 * FEAT; // pre-activation gradients [3][32]
+constexpr int F_D2O = F_DPRE + 3 * FEAT;   // d(pre-tanh) [10]
+constexpr int F_D2S = F_D2O + NOFF;        // d(scale_rot) [70]
+constexpr int F_D2C = F_D2S + 7 * NOFF;    // d(pre-sigmoid colour) [30]
+constexpr int F_HB = F_D2C + 3 * NOFF;     // bank hidden [32]
+constexpr int F_DPREB = F_HB + FEAT;       // bank pre-activation gradient [32]
+constexpr int F_DLOG = F_DPREB + FEAT;     // bank logit gradients [3]
+constexpr int F_CAT = F_DLOG + 3;          // bank input [view, dist] [4]
+constexpr int FACT_ROWS = F_CAT + 4;       // 409
+
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float* __restrict__ anchor_feat,
+                       const float* __restrict__ offset, const float* __restrict__ scaling,
+                       const float* __restrict__ cam, const Pose7 pose, const segs_decode_params p, DecodeState st,
+                       const float* __restrict__ g_xyz, const float* __restrict__ g_color,
+                       const float* __restrict__ g_opacity, const float* __restrict__ g_scaling,
+                       const float* __restrict__ g_rot, const float* __restrict__ g_nop,
+                       float* __restrict__ d_anchor, float* __restrict__ d_feat, float* __restrict__ d_offset,
+                       float* __restrict__ d_scaling, float* __restrict__ fact)
+{
+    __shared__ __align__(16) SW sw;
+    stage_weights(sw, p, pose);
+    const size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x;
+    if (ordinal >= (size_t)n_vis) return;
+    const size_t a = st.anchor_index[ordinal];
+    const uint32_t m = st.mask_bits[ordinal];
+    const size_t row0 = st.row_start[ordinal];
+    float* F = fact + (ordinal / FT) * size_t(FACT_ROWS) * FT + (ordinal % FT);
+    auto put = [&](int row, float v) { F[size_t(row) * FT] = v; };
+
+    const AnchorIn in = load_anchor(anchor, scaling, cam, a);
+    float x[XDIM], bankw[3];
+    build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
+#pragma unroll
+    for (int i = 0; i < XDIM; ++i) put(F_X + i, x[i]);
+
+    float dx[XDIM];
+#pragma unroll
+    for (int i = 0; i < XDIM; ++i) dx[i] = 0.f;
+    float ds[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    float dax = 0.f, day = 0.f, daz = 0.f;
+
+    // back-propagate one MLP's hidden gradient through ReLU and its first layer
+    auto finish_mlp = [&](int mlp, const float (&h)[FEAT], float (&dh)[FEAT]) {
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) {
+            const float dpre = h[j] > 0.f ? dh[j] : 0.f;
+            put(F_H + mlp * FEAT + j, h[j]);
+            put(F_DPRE + mlp * FEAT + j, dpre);
+            const float4* row = reinterpret_cast<const float4*>(sw.w1[mlp][j]);
+#pragma unroll
+            for (int q = 0; q < XDIM / 4; ++q) {
+                const float4 w4 = row[q];
+                dx[4 * q] = fmaf(w4.x, dpre, dx[4 * q]);
+                dx[4 * q + 1] = fmaf(w4.y, dpre, dx[4 * q + 1]);
+                dx[4 * q + 2] = fmaf(w4.z, dpre, dx[4 * q + 2]);
+                dx[4 * q + 3] = fmaf(w4.w, dpre, dx[4 * q + 3]);
+            }
+        }
+    };
+
+    // ---- opacity MLP ----
+    {
+        float h[FEAT], dh[FEAT];
+        layer1(sw.w1[0], sw.b1[0], x, h);
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
+        size_t r = row0;
+#pragma unroll 1
+        for (int o = 0; o < NOFF; ++o) {
+            const float t = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+            float g = g_nop ? __ldg(g_nop + ordinal * NOFF + o) : 0.f;
+            if ((m >> o) & 1u) { g += __ldg(g_opacity + r); ++r; }
+            const float dz = g * (1.f - t * t);
+            put(F_D2O + o, dz);
+            axpy32(sw.w2o[o], dz, dh);
+        }
+        finish_mlp(0, h, dh);
+    }
+    // ---- covariance MLP + geometry assembly ----
+    {
+        float h[FEAT], dh[FEAT];
+        layer1(sw.w1[1], sw.b1[1], x, h);
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
+        size_t r = row0;
+#pragma unroll 1
+        for (int o = 0; o < NOFF; ++o) {
+            float* dof = d_offset + (a * NOFF + o) * 3;
+            if (!((m >> o) & 1u)) {
+#pragma unroll
+                for (int k = 0; k < 7; ++k) put(F_D2S + 7 * o + k, 0.f);
+                dof[0] = 0.f; dof[1] = 0.f; dof[2] = 0.f;
+                continue;
+            }
+            float sr[7], dsr[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+            const float gx = __ldg(g_xyz + 3 * r), gy = __ldg(g_xyz + 3 * r + 1), gz = __ldg(g_xyz + 3 * r + 2);
+            const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
+                        oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
+            // xyz = anchor + offset * s[:3]
+            dax += gx; day += gy; daz += gz;
+            dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2];
+            ds[0] = fmaf(gx, ox, ds[0]); ds[1] = fmaf(gy, oy, ds[1]); ds[2] = fmaf(gz, oz, ds[2]);
+            // scaling = s[3:] * sigmoid(sr[:3])
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float sg = sigmoidf_(sr[k]);
+                const float g = __ldg(g_scaling + 3 * r + k);
+                ds[3 + k] = fmaf(g, sg, ds[3 + k]);
+                dsr[k] = g * in.s[3 + k] * sg * (1.f - sg);
+            }
+            // rot = v / max(|v|, 1e-12)
+            {
+                const float4 g = __ldg(reinterpret_cast<const float4*>(g_rot + 4 * r));
+                const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
+                const float nrm = sqrtf(n2);
+                if (nrm > 1e-12f) {
+                    const float inv = 1.f / nrm;
+                    const float u0 = sr[3] * inv, u1 = sr[4] * inv, u2 = sr[5] * inv, u3 = sr[6] * inv;
+                    const float ug = u0 * g.x + u1 * g.y + u2 * g.z + u3 * g.w;
+                    dsr[3] = (g.x - u0 * ug) * inv; dsr[4] = (g.y - u1 * ug) * inv;
+                    dsr[5] = (g.z - u2 * ug) * inv; dsr[6] = (g.w - u3 * ug) * inv;
+                } else {
+                    dsr[3] = g.x * 1e12f; dsr[4] = g.y * 1e12f; dsr[5] = g.z * 1e12f; dsr[6] = g.w * 1e12f;
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < 7; ++k) {
+                put(F_D2S + 7 * o + k, dsr[k]);
+                axpy32(sw.w2s[7 * o + k], dsr[k], dh);
+            }
+            ++r;
+        }
+        finish_mlp(1, h, dh);
+    }
+    // ---- colour MLP ----
+    {
+        float h[FEAT], dh[FEAT];
+        layer1(sw.w1[2], sw.b1[2], x, h);
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
+        size_t r = row0;
+#pragma unroll 1
+        for (int o = 0; o < NOFF; ++o) {
+            if (!((m >> o) & 1u)) {
+#pragma unroll
+                for (int k = 0; k < 3; ++k) put(F_D2C + 3 * o + k, 0.f);
+                continue;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) {
+                const float c = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
+                const float dz = __ldg(g_color + 3 * r + k) * c * (1.f - c);
+                put(F_D2C + 3 * o + k, dz);
+                axpy32(sw.w2c[3 * o + k], dz, dh);
+            }
+            ++r;
+        }
+        finish_mlp(2, h, dh);
+    }
+
+    // ---- inputs: dx = [d feat'(32), d view(3), d dist] ----
+    const float ux = x[32], uy = x[33], uz = x[34];
+    float dux = dx[32], duy = dx[33], duz = dx[34], ddist = dx[35];
+    float df[FEAT];
+    if (p.use_feat_bank) {
+        float f[FEAT];
+#pragma unroll
+        for (int q = 0; q < FEAT / 4; ++q) {
+            const float4 t = __ldg(reinterpret_cast<const float4*>(anchor_feat + a * FEAT) + q);
+            f[4 * q] = t.x; f[4 * q + 1] = t.y; f[4 * q + 2] = t.z; f[4 * q + 3] = t.w;
+        }
+        float dw0 = 0.f, dw1 = 0.f, dw2 = 0.f;
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) df[j] = 0.f;
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) {
+            dw0 = fmaf(dx[j], f[4 * (j & 7)], dw0);
+            dw1 = fmaf(dx[j], f[2 * (j & 15)], dw1);
+            dw2 = fmaf(dx[j], f[j], dw2);
+            df[4 * (j & 7)] = fmaf(dx[j], bankw[0], df[4 * (j & 7)]);
+            df[2 * (j & 15)] = fmaf(dx[j], bankw[1], df[2 * (j & 15)]);
+            df[j] = fmaf(dx[j], bankw[2], df[j]);
+        }
+        // softmax backward
+        const float dot = bankw[0] * dw0 + bankw[1] * dw1 + bankw[2] * dw2;
+        const float dl[3] = {bankw[0] * (dw0 - dot), bankw[1] * (dw1 - dot), bankw[2] * (dw2 - dot)};
+        put(F_DLOG + 0, dl[0]); put(F_DLOG + 1, dl[1]); put(F_DLOG + 2, dl[2]);
+        put(F_CAT + 0, ux); put(F_CAT + 1, uy); put(F_CAT + 2, uz); put(F_CAT + 3, in.dist);
+        float dc0 = 0.f, dc1 = 0.f, dc2 = 0.f, dc3 = 0.f;
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) {
+            const float4 w4 = *reinterpret_cast<const float4*>(sw.wb1[j]);
+            float hb = sw.bb1[j];
+            hb = fmaf(w4.x, ux, hb); hb = fmaf(w4.y, uy, hb); hb = fmaf(w4.z, uz, hb); hb = fmaf(w4.w, in.dist, hb);
+            hb = fmaxf(hb, 0.f);
+            const float dhb = sw.wb2[0][j] * dl[0] + sw.wb2[1][j] * dl[1] + sw.wb2[2][j] * dl[2];
+            const float dpre = hb > 0.f ? dhb : 0.f;
+            put(F_HB + j, hb);
+            put(F_DPREB + j, dpre);
+            dc0 = fmaf(w4.x, dpre, dc0); dc1 = fmaf(w4.y, dpre, dc1); dc2 = fmaf(w4.z, dpre, dc2); dc3 = fmaf(w4.w, dpre, dc3);
+        }
+        dux += dc0; duy += dc1; duz += dc2; ddist += dc3;
+    } else {
+#pragma unroll
+        for (int j = 0; j < FEAT; ++j) df[j] = dx[j];
+    }
+#pragma unroll
+    for (int q = 0; q < FEAT / 4; ++q)
+        reinterpret_cast<float4*>(d_feat + a * FEAT)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+
+    // ob_view = v / |v|, ob_dist = |v|, v = anchor - camera
+    {
+        const float inv = 1.f / in.dist;
+        const float ud = ux * dux + uy * duy + uz * duz;
+        dax += (dux - ux * ud) * inv + ddist * ux;
+        day += (duy - uy * ud) * inv + ddist * uy;
+        daz += (duz - uz * ud) * inv + ddist * uz;
+    }
+    d_anchor[3 * a] = dax; d_anchor[3 * a + 1] = day; d_anchor[3 * a + 2] = daz;
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] = ds[k];
+}
+
+// =======================================================================================
+// backward, kernel 2: weight gradients  dW[p][q] = sum_k U[k][p] V[k][q]
+// =======================================================================================
+constexpr int WG_THREADS = 256;
+constexpr int WG_STRIDE = FT + 4;      // floats per factor row in shared memory (conflict-free LDS.128)
+
+struct WJob {            // one outer-product sum: rows U = factor rows [u0, u0+np), lanes V = factor rows [v0, v0+32)
+    int u0, np, v0;      // v0 < 0: V == 1 (bias sums), lanes index the U rows instead
+    float* out;          // out[p * ld + q]
+    int ld, nq;          // columns actually stored
+};
+constexpr int MAX_JOBS = 16;
+struct WJobs { WJob j[MAX_JOBS]; int n; };
+
+// Every warp walks the flattened list of (job, p) rows with stride 8; a thread keeps one
+// accumulator per row it owns.
+constexpr int WG_ROWS_MAX = 40;
+
+__global__ void __launch_bounds__(WG_THREADS)
+decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs)
+{
+    extern __shared__ __align__(16) float s_f[];          // [FACT_ROWS][WG_STRIDE]
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int ntiles = (n_vis + FT - 1) / FT;
+
+    // rows owned by this warp: global row index g = warp + 8 * i
+    int total_rows = 0;
+    for (int j = 0; j < jobs.n; ++j) total_rows += jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
+    float acc[WG_ROWS_MAX];
+#pragma unroll
+    for (int i = 0; i < WG_ROWS_MAX; ++i) acc[i] = 0.f;
+
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int nk = min(FT, n_vis - t * FT);
+        __syncthreads();
+        const float* src = fact + size_t(t) * FACT_ROWS * FT;
+        for (int e = threadIdx.x; e < FACT_ROWS * FT; e += WG_THREADS) {
+            const int row = e / FT, k = e % FT;
+            s_f[row * WG_STRIDE + k] = k < nk ? __ldg(src + e) : 0.f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < WG_ROWS_MAX; ++i) {
+            const int g = warp + 8 * i;
+            if (g >= total_rows) break;
+            // locate (job, p) of flattened row g   (warp-uniform)
+            int j = 0, base = 0;
+            for (;; ++j) {
+                const int n = jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
+                if (g < base + n) break;
+                base += n;
+            }
+            const WJob& job = jobs.j[j];
+            const int pidx = g - base;
+            float a = acc[i];
+            if (job.v0 >= 0) {
+                const float4* u = reinterpret_cast<const float4*>(s_f + (job.u0 + pidx) * WG_STRIDE);
+                const float4* v = reinterpret_cast<const float4*>(s_f + (job.v0 + (lane < job.nq ? lane : 0)) * WG_STRIDE);
+#pragma unroll
+                for (int k4 = 0; k4 < FT / 4; ++k4) {
+                    const float4 uu = u[k4], vv = v[k4];
+                    a = fmaf(uu.x, vv.x, a); a = fmaf(uu.y, vv.y, a); a = fmaf(uu.z, vv.z, a); a = fmaf(uu.w, vv.w, a);
+                }
+            } else {
+                const int r = pidx * 32 + lane;
+                if (r < job.np) {
+                    const float4* u = reinterpret_cast<const float4*>(s_f + (job.u0 + r) * WG_STRIDE);
+#pragma unroll
+                    for (int k4 = 0; k4 < FT / 4; ++k4) {
+                        const float4 uu = u[k4];
+                        a += uu.x + uu.y + uu.z + uu.w;
+                    }
+                }
+            }
+            acc[i] = a;
+        }
+    }
+    // flush
+#pragma unroll
+    for (int i = 0; i < WG_ROWS_MAX; ++i) {
+        const int g = warp + 8 * i;
+        if (g >= total_rows) break;
+        int j = 0, base = 0;
+        for (;; ++j) {
+            const int n = jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
+            if (g < base + n) break;
+            base += n;
+        }
+        const WJob& job = jobs.j[j];
+        const int pidx = g - base;
+        if (job.v0 >= 0) {
+            if (lane < job.nq) atomicAdd(job.out + pidx * job.ld + lane, acc[i]);
+        } else {
+            const int r = pidx * 32 + lane;
+            if (r < job.np) atomicAdd(job.out + r, acc[i]);
+        }
+    }
+}
+
+// appearance path: the appearance vector is the same for all anchors, so its gradients follow from
+// db1_colour:  d_app = W1c[:, app cols]^T db1c ;  dW1c[:, app cols] = db1c (x) app ;
+// d app_w = d_app (x) pose ; d app_b = d_app
+__global__ void __launch_bounds__(32)
+decode_appgrad_kernel(const segs_decode_params p, const segs_decode_grads d, const Pose7 pose)
+{
+    __shared__ float s_app[32], s_dapp[32];
+    const int t = threadIdx.x;
+    const int in_c = 35 + (p.add_color_dist ? 1 : 0), ld_c = in_c + p.appearance_dim;
+    float a = 0.f;
+    if (t < p.appearance_dim) {
+        a = p.app_b[t];
+        for (int q = 0; q < 7; ++q) a = fmaf(p.app_w[t * 7 + q], pose.v[q], a);
+    }
+    s_app[t] = a;
+    float da = 0.f;
+    if (t < p.appearance_dim)
+        for (int j = 0; j < FEAT; ++j) da = fmaf(p.color_w1[j * ld_c + in_c + t], d.color_b1[j], da);
+    s_dapp[t] = da;
+    __syncwarp();
+    for (int k = 0; k < p.appearance_dim; ++k) d.color_w1[t * ld_c + in_c + k] = d.color_b1[t] * s_app[k];
+    if (t < p.appearance_dim) {
+        d.app_b[t] = da;
+        for (int q = 0; q < 7; ++q) d.app_w[t * 7 + q] = da * pose.v[q];
+    }
+}
+
+struct HostCounts { uint32_t* host = nullptr; uint32_t* dev = nullptr; cudaEvent_t ev = nullptr; };
+HostCounts decode_host_counts()
+{
+    static thread_local HostCounts h;
+    if (!h.host) {
+        void *hp = nullptr, *dp = nullptr;
+        if (cudaHostAlloc(&hp, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
+            cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess &&
+            cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming) == cudaSuccess) {
+            h.host = static_cast<uint32_t*>(hp);
+            h.dev = static_cast<uint32_t*>(dp);
+        }
+    }
+    return h;
+}
+
+int check_params(const segs_decode_params* p)
+{
+    if (!p) { set_error("decode: params must not be NULL"); return SEGS_ERR_INVALID_ARG; }
+    if (p->appearance_dim < 0 || p->appearance_dim > 32) { set_error("decode: appearance_dim must be in [0, 32]"); return SEGS_ERR_INVALID_ARG; }
+    if (!p->opacity_w1 || !p->opacity_b1 || !p->opacity_w2 || !p->opacity_b2 || !p->cov_w1 || !p->cov_b1 || !p->cov_w2 ||
+        !p->cov_b2 || !p->color_w1 || !p->color_b1 || !p->color_w2 || !p->color_b2) {
+        set_error("decode: NULL MLP weight"); return SEGS_ERR_INVALID_ARG;
+    }
+    if (p->appearance_dim > 0 && (!p->app_w || !p->app_b)) { set_error("decode: NULL appearance weight"); return SEGS_ERR_INVALID_ARG; }
+    if (p->use_feat_bank && (!p->bank_w1 || !p->bank_b1 || !p->bank_w2 || !p->bank_b2)) { set_error("decode: NULL feature-bank weight"); return SEGS_ERR_INVALID_ARG; }
+    return SEGS_OK;
+}
+
+}  // namespace
+}  // namespace segs
+
+using namespace segs;
+
+extern "C" size_t segs_decode_state_bytes(int A)
+{
+    size_t bytes = 0;
+    DecodeState::carve(nullptr, A > 0 ? A : 0, &bytes);
+    return bytes;
+}
+
+extern "C" int segs_decode_forward(
+    int A, const unsigned char* visible_mask, const float* anchor, const float* anchor_feat, const float* offset,
+    const float* scaling, const float* camera_center, const float* pose, const segs_decode_params* params,
+    float* xyz, float* color, float* opacity, float* out_scaling, float* rot, float* neural_opacity,
+    unsigned char* mask, char* state, int* counts, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (counts) { counts[0] = 0; counts[1] = 0; }
+    if (A == 0) return SEGS_OK;
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (A < 0 || !anchor || !anchor_feat || !offset || !scaling || !camera_center || !pose || !xyz || !color || !opacity ||
+        !out_scaling || !rot || !neural_opacity || !mask || !state || !counts) {
+        set_error("decode: invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    const HostCounts hc = decode_host_counts();
+    if (!hc.host) { set_error("decode: mapped host memory allocation failed"); return SEGS_ERR_CUDA; }
+    DecodeState st = DecodeState::carve(state, A, nullptr);
+    SEGS_CUDA_CHECK(cudaMemsetAsync(st.counters, 0, st.zero_bytes, stream));
+    Pose7 p7;
+    for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
+    const int tiles = (A + DEC_THREADS - 1) / DEC_THREADS;
+    decode_forward_kernel<<<tiles, DEC_THREADS, 0, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
+                                                            camera_center, p7, *params, xyz, color, opacity, out_scaling,
+                                                            rot, neural_opacity, mask, st, hc.dev);
+    SEGS_LAUNCH_CHECK();
+    SEGS_CUDA_CHECK(cudaEventRecord(hc.ev, stream));
+    SEGS_CUDA_CHECK(cudaEventSynchronize(hc.ev));
+    counts[0] = (int)((volatile uint32_t*)hc.host)[0];
+    counts[1] = (int)((volatile uint32_t*)hc.host)[1];
+    return SEGS_OK;
+}
+
+extern "C" int segs_decode_backward(
+    int A, const unsigned char* visible_mask, const float* anchor, const float* anchor_feat, const float* offset,
+    const float* scaling, const float* camera_center, const float* pose, const segs_decode_params* params,
+    const char* state, int n_vis, int n_out, const float* g_xyz, const float* g_color, const float* g_opacity,
+    const float* g_scaling, const float* g_rot, const float* g_neural_opacity, float* d_anchor, float* d_anchor_feat,
+    float* d_offset, float* d_scaling, const segs_decode_grads* dp, segs_alloc_fn scratch_alloc, void* scratch_user,
+    void* stream_)
+{
+    (void)visible_mask;
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (A == 0) return SEGS_OK;
+    int rc = check_params(params);
+    if (rc) return rc;
+    if (A < 0 || n_vis < 0 || n_vis > A || n_out < 0 || !anchor || !anchor_feat || !offset || !scaling || !camera_center ||
+        !pose || !state || !d_anchor || !d_anchor_feat || !d_offset || !d_scaling || !dp || !scratch_alloc) {
+        set_error("decode backward: invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    if (n_out > 0 && (!g_xyz || !g_color || !g_opacity || !g_scaling || !g_rot)) { set_error("decode backward: NULL row gradient"); return SEGS_ERR_INVALID_ARG; }
+    const segs_decode_params& p = *params;
+    const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
+    const int in_c = 35 + (p.add_color_dist ? 1 : 0), ld_c = in_c + p.appearance_dim;
+    if (!dp->opacity_w1 || !dp->opacity_b1 || !dp->opacity_w2 || !dp->opacity_b2 || !dp->cov_w1 || !dp->cov_b1 || !dp->cov_w2 ||
+        !dp->cov_b2 || !dp->color_w1 || !dp->color_b1 || !dp->color_w2 || !dp->color_b2 ||
+        (p.appearance_dim > 0 && (!dp->app_w || !dp->app_b)) ||
+        (p.use_feat_bank && (!dp->bank_w1 || !dp->bank_b1 || !dp->bank_w2 || !dp->bank_b2))) {
+        set_error("decode backward: NULL weight-gradient output"); return SEGS_ERR_INVALID_ARG;
+    }
+    // invisible anchors and the weight accumulators start from zero
+    SEGS_CUDA_CHECK(cudaMemsetAsync(d_anchor, 0, size_t(A) * 3 * sizeof(float), stream));
+    SEGS_CUDA_CHECK(cudaMemsetAsync(d_anchor_feat, 0, size_t(A) * FEAT * sizeof(float), stream));
+    SEGS_CUDA_CHECK(cudaMemsetAsync(d_offset, 0, size_t(A) * NOFF * 3 * sizeof(float), stream));
+    SEGS_CUDA_CHECK(cudaMemsetAsync(d_scaling, 0, size_t(A) * 6 * sizeof(float), stream));
+    auto zero = [&](float* ptr, size_t n) { return cudaMemsetAsync(ptr, 0, n * sizeof(float), stream); };
+    SEGS_CUDA_CHECK(zero(dp->opacity_w1, size_t(FEAT) * in_o)); SEGS_CUDA_CHECK(zero(dp->opacity_b1, FEAT));
+    SEGS_CUDA_CHECK(zero(dp->opacity_w2, NOFF * FEAT));         SEGS_CUDA_CHECK(zero(dp->opacity_b2, NOFF));
+    SEGS_CUDA_CHECK(zero(dp->cov_w1, size_t(FEAT) * in_s));     SEGS_CUDA_CHECK(zero(dp->cov_b1, FEAT));
+    SEGS_CUDA_CHECK(zero(dp->cov_w2, 7 * NOFF * FEAT));         SEGS_CUDA_CHECK(zero(dp->cov_b2, 7 * NOFF));
+    SEGS_CUDA_CHECK(zero(dp->color_w1, size_t(FEAT) * ld_c));   SEGS_CUDA_CHECK(zero(dp->color_b1, FEAT));
+    SEGS_CUDA_CHECK(zero(dp->color_w2, 3 * NOFF * FEAT));       SEGS_CUDA_CHECK(zero(dp->color_b2, 3 * NOFF));
+    if (p.appearance_dim > 0) { SEGS_CUDA_CHECK(zero(dp->app_w, size_t(p.appearance_dim) * 7)); SEGS_CUDA_CHECK(zero(dp->app_b, p.appearance_dim)); }
+    if (p.use_feat_bank) {
+        SEGS_CUDA_CHECK(zero(dp->bank_w1, FEAT * 4)); SEGS_CUDA_CHECK(zero(dp->bank_b1, FEAT));
+        SEGS_CUDA_CHECK(zero(dp->bank_w2, 3 * FEAT)); SEGS_CUDA_CHECK(zero(dp->bank_b2, 3));
+    }
+    if (n_vis == 0) return SEGS_OK;
+
+    const size_t ntiles = (size_t(n_vis) + FT - 1) / FT;
+    const size_t fact_bytes = ntiles * FACT_ROWS * FT * sizeof(float) + 256;
+    char* scratch = scratch_alloc(scratch_user, fact_bytes);
+    if (!scratch) { set_error("decode backward: scratch allocation of %zu bytes failed", fact_bytes); return SEGS_ERR_ALLOC; }
+    float* fact = reinterpret_cast<float*>((reinterpret_cast<uintptr_t>(scratch) + 127) & ~uintptr_t(127));
+    if (!p.use_feat_bank) {
+        // the bank rows are never written in this mode; the job list below skips them
+    }
+    DecodeState st = DecodeState::carve(const_cast<char*>(state), A, nullptr);
+    Pose7 p7;
+    for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
+    decode_backward_kernel<<<(n_vis + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, stream>>>(
+        n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
+        g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact);
+    SEGS_LAUNCH_CHECK();
+
+    WJobs jobs;
+    int n = 0;
+    auto add = [&](int u0, int np, int v0, float* out, int ld, int nq) { jobs.j[n++] = WJob{u0, np, v0, out, ld, nq}; };
+    // second layers: dW2[n][j] = sum d2[n] h[j]
+    add(F_D2O, NOFF, F_H + 0 * FEAT, dp->opacity_w2, FEAT, FEAT);
+    add(F_D2S, 7 * NOFF, F_H + 1 * FEAT, dp->cov_w2, FEAT, FEAT);
+    add(F_D2C, 3 * NOFF, F_H + 2 * FEAT, dp->color_w2, FEAT, FEAT);
+    // first layers, stored transposed by the job shape: rows p = hidden unit j ... we need dW1[j][i] = sum dpre[j] x[i]:
+    // U = dpre (32 rows), V = x (lanes i < in) handled in two lane groups (i < 32, then i = 32..35)
+    add(F_DPRE + 0 * FEAT, FEAT, F_X, dp->opacity_w1, in_o, 32);
+    add(F_DPRE + 1 * FEAT, FEAT, F_X, dp->cov_w1, in_s, 32);
+    add(F_DPRE + 2 * FEAT, FEAT, F_X, dp->color_w1, ld_c, 32);
+    add(F_DPRE + 0 * FEAT, FEAT, F_X + 32, dp->opacity_w1 + 32, in_o, in_o - 32);
+    add(F_DPRE + 1 * FEAT, FEAT, F_X + 32, dp->cov_w1 + 32, in_s, in_s - 32);
+    add(F_DPRE + 2 * FEAT, FEAT, F_X + 32, dp->color_w1 + 32, ld_c, in_c - 32);
+    // biases
+    add(F_D2O, NOFF, -1, dp->opacity_b2, 0, 0);
+    add(F_D2S, 7 * NOFF, -1, dp->cov_b2, 0, 0);
+    add(F_D2C, 3 * NOFF, -1, dp->color_b2, 0, 0);
+    add(F_DPRE + 0 * FEAT, FEAT, -1, dp->opacity_b1, 0, 0);
+    add(F_DPRE + 1 * FEAT, FEAT, -1, dp->cov_b1, 0, 0);
+    add(F_DPRE + 2 * FEAT, FEAT, -1, dp->color_b1, 0, 0);
+    jobs.n = n;
+    const size_t smem = size_t(FACT_ROWS) * WG_STRIDE * sizeof(float);
+    SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    const int grid = (int)std::min<size_t>(ntiles, SM_COUNT);
+    decode_wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(fact, n_vis, jobs);
+    SEGS_LAUNCH_CHECK();
+    if (p.use_feat_bank) {
+        WJobs bj;
+        n = 0;
+        auto addb = [&](int u0, int np, int v0, float* out, int ld, int nq) { bj.j[n++] = WJob{u0, np, v0, out, ld, nq}; };
+        addb(F_DLOG, 3, F_HB, dp->bank_w2, FEAT, FEAT);          // dW2b[m][j] = sum dlog[m] hb[j]
+        addb(F_DPREB, FEAT, F_CAT, dp->bank_w1, 4, 4);           // dW1b[j][i] = sum dpreb[j] cat[i]
+        addb(F_DLOG, 3, -1, dp->bank_b2, 0, 0);
+        addb(F_DPREB, FEAT, -1, dp->bank_b1, 0, 0);
+        bj.n = n;
+        decode_wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(fact, n_vis, bj);
+        SEGS_LAUNCH_CHECK();
+    }
+    if (p.appearance_dim > 0) {
+        decode_appgrad_kernel<<<1, 32, 0, stream>>>(p, *dp, p7);
+        SEGS_LAUNCH_CHECK();
+    }
+    return SEGS_OK;
+}
