@@ -291,7 +291,7 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w
 // =======================================================================================
 // forward
 // =======================================================================================
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 4)
 decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, const float* __restrict__ anchor,
                       const float* __restrict__ anchor_feat, const float* __restrict__ offset,
                       const float* __restrict__ scaling, const float* __restrict__ cam, const Pose7 pose,
@@ -305,106 +305,113 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
     __shared__ uint32_t s_warp[DEC_THREADS / 32];
     __shared__ uint32_t s_tile, s_vis_base, s_row_base;
     const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t ntiles = (uint32_t)((A + DEC_THREADS - 1) / DEC_THREADS);
 
-    if (tid == 0) s_tile = atomicAdd(st.counters, 1u);
-    stage_weights(sw, p, pose);          // (contains __syncthreads)
-    const uint32_t tile = s_tile;
+    stage_weights(sw, p, pose);          // once per (persistent) CTA; contains __syncthreads
 
-    // ---- D1: compact the visible anchors of this tile (ascending anchor index) ----
-    const size_t a0 = size_t(tile) * DEC_THREADS + tid;
-    const bool vis = a0 < (size_t)A && (visible_mask == nullptr || visible_mask[a0] != 0);
-    uint32_t n_vis;
-    const uint32_t ord = cta_exclusive_scan(vis ? 1u : 0u, s_warp, &n_vis);
-    if (vis) s_aid[ord] = (uint32_t)a0;
-    __syncthreads();
-    const bool active = (uint32_t)tid < n_vis;
-    const size_t a = active ? s_aid[tid] : 0;
+    for (;;) {
+        __syncthreads();                 // previous tile is done with s_tile / s_aid / the bases
+        if (tid == 0) s_tile = atomicAdd(st.counters, 1u);
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) break;
 
-    // ---- D2-D4 (opacity): inputs + opacity MLP -> mask ----
-    AnchorIn in;
-    float x[XDIM];
-    float op[NOFF];
-    uint32_t m = 0;
-    if (active) {
-        in = load_anchor(anchor, scaling, cam, a);
-        float bankw[3];
-        build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
-        float h[FEAT];
-        layer1(sw.w1[0], sw.b1[0], x, h);
+        // ---- D1: compact the visible anchors of this tile (ascending anchor index) ----
+        const size_t a0 = size_t(tile) * DEC_THREADS + tid;
+        const bool vis = a0 < (size_t)A && (visible_mask == nullptr || visible_mask[a0] != 0);
+        uint32_t n_vis;
+        const uint32_t ord = cta_exclusive_scan(vis ? 1u : 0u, s_warp, &n_vis);
+        if (vis) s_aid[ord] = (uint32_t)a0;
+        __syncthreads();
+        const bool active = (uint32_t)tid < n_vis;
+        const size_t a = active ? s_aid[tid] : 0;
+
+        // ---- D2-D4 (opacity): inputs + opacity MLP -> mask ----
+        AnchorIn in;
+        float x[XDIM];
+        float op[NOFF];
+        uint32_t m = 0;
+        if (active) {
+            in = load_anchor(anchor, scaling, cam, a);
+            float bankw[3];
+            build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
+            float h[FEAT];
+            layer1(sw.w1[0], sw.b1[0], x, h);
 #pragma unroll
-        for (int o = 0; o < NOFF; ++o) {
-            op[o] = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
-            if (op[o] > 0.0f) m |= 1u << o;               // mask = neural_opacity > 0   (:278-279)
-        }
-    }
-    uint32_t n_rows;
-    const uint32_t row_off = cta_exclusive_scan(__popc(m), s_warp, &n_rows);
-
-    // ---- order across CTAs: exclusive prefixes of visible anchors and surviving rows ----
-    if (tid < 32) {
-        const uint32_t vb = lookback(st.look_vis, tile, n_vis, lane);
-        const uint32_t rb = lookback(st.look_row, tile, n_rows, lane);
-        if (lane == 0) {
-            s_vis_base = vb;
-            s_row_base = rb;
-            if (tile == gridDim.x - 1 && host_counts != nullptr) {
-                host_counts[0] = vb + n_vis;
-                host_counts[1] = rb + n_rows;
-                __threadfence_system();
+            for (int o = 0; o < NOFF; ++o) {
+                op[o] = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+                if (op[o] > 0.0f) m |= 1u << o;               // mask = neural_opacity > 0   (:278-279)
             }
         }
-    }
-    __syncthreads();
-    if (!active) return;
-    const size_t ordinal = size_t(s_vis_base) + tid;
-    const size_t row0 = size_t(s_row_base) + row_off;
-    st.anchor_index[ordinal] = (uint32_t)a;
-    st.row_start[ordinal] = (uint32_t)row0;
-    st.mask_bits[ordinal] = m;
-#pragma unroll
-    for (int o = 0; o < NOFF; ++o) {
-        neural_opacity[ordinal * NOFF + o] = op[o];
-        out_mask[ordinal * NOFF + o] = (m >> o) & 1u;
-    }
-    if (m == 0) return;
+        uint32_t n_rows;
+        const uint32_t row_off = cta_exclusive_scan(__popc(m), s_warp, &n_rows);
 
-    // ---- D4 (cov) + D5: geometry rows ----
-    {
-        float h[FEAT];
-        layer1(sw.w1[1], sw.b1[1], x, h);
-        size_t r = row0;
-#pragma unroll 1
-        for (int o = 0; o < NOFF; ++o) {
-            if (!((m >> o) & 1u)) continue;
-            float sr[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
-            const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
-                        oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
-            // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
-            out_xyz[3 * r] = in.ax + ox * in.s[0];
-            out_xyz[3 * r + 1] = in.ay + oy * in.s[1];
-            out_xyz[3 * r + 2] = in.az + oz * in.s[2];
-            out_scaling[3 * r] = in.s[3] * sigmoidf_(sr[0]);
-            out_scaling[3 * r + 1] = in.s[4] * sigmoidf_(sr[1]);
-            out_scaling[3 * r + 2] = in.s[5] * sigmoidf_(sr[2]);
-            const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
-            *reinterpret_cast<float4*>(out_rot + 4 * r) = make_float4(sr[3] / nrm, sr[4] / nrm, sr[5] / nrm, sr[6] / nrm);
-            out_opacity[r] = op[o];
-            ++r;
+        // ---- order across CTAs: exclusive prefixes of visible anchors and surviving rows ----
+        if (tid < 32) {
+            const uint32_t vb = lookback(st.look_vis, tile, n_vis, lane);
+            const uint32_t rb = lookback(st.look_row, tile, n_rows, lane);
+            if (lane == 0) {
+                s_vis_base = vb;
+                s_row_base = rb;
+                if (tile == ntiles - 1 && host_counts != nullptr) {
+                    host_counts[0] = vb + n_vis;
+                    host_counts[1] = rb + n_rows;
+                    __threadfence_system();
+                }
+            }
         }
-    }
-    // ---- D4 (colour) ----
-    {
-        float h[FEAT];
-        layer1(sw.w1[2], sw.b1[2], x, h);
-        size_t r = row0;
-#pragma unroll 1
-        for (int o = 0; o < NOFF; ++o) {
-            if (!((m >> o) & 1u)) continue;
+        __syncthreads();
+        if (!active) continue;
+        const size_t ordinal = size_t(s_vis_base) + tid;
+        const size_t row0 = size_t(s_row_base) + row_off;
+        st.anchor_index[ordinal] = (uint32_t)a;
+        st.row_start[ordinal] = (uint32_t)row0;
+        st.mask_bits[ordinal] = m;
 #pragma unroll
-            for (int k = 0; k < 3; ++k) out_color[3 * r + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
-            ++r;
+        for (int o = 0; o < NOFF; ++o) {
+            neural_opacity[ordinal * NOFF + o] = op[o];
+            out_mask[ordinal * NOFF + o] = (m >> o) & 1u;
+        }
+        if (m == 0) continue;
+
+        // ---- D4 (cov) + D5: geometry rows ----
+        {
+            float h[FEAT];
+            layer1(sw.w1[1], sw.b1[1], x, h);
+            size_t r = row0;
+#pragma unroll
+            for (int o = 0; o < NOFF; ++o) {
+                if (!((m >> o) & 1u)) continue;
+                float sr[7];
+#pragma unroll
+                for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+                const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
+                            oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
+                // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
+                out_xyz[3 * r] = in.ax + ox * in.s[0];
+                out_xyz[3 * r + 1] = in.ay + oy * in.s[1];
+                out_xyz[3 * r + 2] = in.az + oz * in.s[2];
+                out_scaling[3 * r] = in.s[3] * sigmoidf_(sr[0]);
+                out_scaling[3 * r + 1] = in.s[4] * sigmoidf_(sr[1]);
+                out_scaling[3 * r + 2] = in.s[5] * sigmoidf_(sr[2]);
+                const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
+                *reinterpret_cast<float4*>(out_rot + 4 * r) = make_float4(sr[3] / nrm, sr[4] / nrm, sr[5] / nrm, sr[6] / nrm);
+                out_opacity[r] = op[o];
+                ++r;
+            }
+        }
+        // ---- D4 (colour) ----
+        {
+            float h[FEAT];
+            layer1(sw.w1[2], sw.b1[2], x, h);
+            size_t r = row0;
+#pragma unroll
+            for (int o = 0; o < NOFF; ++o) {
+                if (!((m >> o) & 1u)) continue;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) out_color[3 * r + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
+                ++r;
+            }
         }
     }
 }
@@ -426,7 +433,7 @@ constexpr int F_DLOG = F_DPREB + FEAT;     // bank logit gradients [3]
 constexpr int F_CAT = F_DLOG + 3;          // bank input [view, dist] [4]
 constexpr int FACT_ROWS = F_CAT + 4;       // 409
 
-__global__ void __launch_bounds__(DEC_THREADS)
+__global__ void __launch_bounds__(DEC_THREADS, 3)
 decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float* __restrict__ anchor_feat,
                        const float* __restrict__ offset, const float* __restrict__ scaling,
                        const float* __restrict__ cam, const Pose7 pose, const segs_decode_params p, DecodeState st,
@@ -438,8 +445,8 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
 {
     __shared__ __align__(16) SW sw;
     stage_weights(sw, p, pose);
-    const size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x;
-    if (ordinal >= (size_t)n_vis) return;
+  for (size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x; ordinal < (size_t)n_vis;
+       ordinal += size_t(gridDim.x) * DEC_THREADS) {
     const size_t a = st.anchor_index[ordinal];
     const uint32_t m = st.mask_bits[ordinal];
     const size_t row0 = st.row_start[ordinal];
@@ -640,6 +647,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     d_anchor[3 * a] = dax; d_anchor[3 * a + 1] = day; d_anchor[3 * a + 2] = daz;
 #pragma unroll
     for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] = ds[k];
+  }
 }
 
 // =======================================================================================
@@ -653,15 +661,15 @@ struct WJob {            // one outer-product sum: rows U = factor rows [u0, u0+
     float* out;          // out[p * ld + q]
     int ld, nq;          // columns actually stored
 };
-constexpr int MAX_JOBS = 16;
+constexpr int MAX_JOBS = 20;
 struct WJobs { WJob j[MAX_JOBS]; int n; };
 
 // Every warp walks the flattened list of (job, p) rows with stride 8; a thread keeps one
 // accumulator per row it owns.
-constexpr int WG_ROWS_MAX = 40;
+constexpr int WG_ROWS_MAX = 44;
 
 __global__ void __launch_bounds__(WG_THREADS)
-decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs)
+decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs, const int nrows_used)
 {
     extern __shared__ __align__(16) float s_f[];          // [FACT_ROWS][WG_STRIDE]
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -678,11 +686,23 @@ decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs)
         const int nk = min(FT, n_vis - t * FT);
         __syncthreads();
         const float* src = fact + size_t(t) * FACT_ROWS * FT;
-        for (int e = threadIdx.x; e < FACT_ROWS * FT; e += WG_THREADS) {
-            const int row = e / FT, k = e % FT;
-            s_f[row * WG_STRIDE + k] = k < nk ? __ldg(src + e) : 0.f;
+        // 16-byte asynchronous copies, one factor row = 16 of them (rows land WG_STRIDE apart)
+        for (int e = threadIdx.x; e < nrows_used * (FT / 4); e += WG_THREADS) {
+            const int row = e / (FT / 4), k4 = e % (FT / 4);
+            const unsigned dst = (unsigned)__cvta_generic_to_shared(s_f + row * WG_STRIDE + 4 * k4);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(dst), "l"(src + row * FT + 4 * k4));
         }
+        asm volatile("cp.async.commit_group;\n" ::);
+        asm volatile("cp.async.wait_group 0;\n" ::);
         __syncthreads();
+        if (nk < FT) {
+            // tail tile: the unused ordinals hold whatever the scratch held — zero them
+            for (int e = threadIdx.x; e < nrows_used * FT; e += WG_THREADS) {
+                const int row = e / FT, k = e % FT;
+                if (k >= nk) s_f[row * WG_STRIDE + k] = 0.f;
+            }
+            __syncthreads();
+        }
 #pragma unroll
         for (int i = 0; i < WG_ROWS_MAX; ++i) {
             const int g = warp + 8 * i;
@@ -831,7 +851,7 @@ extern "C" int segs_decode_forward(
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
     const int tiles = (A + DEC_THREADS - 1) / DEC_THREADS;
-    decode_forward_kernel<<<tiles, DEC_THREADS, 0, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
+    decode_forward_kernel<<<std::min(tiles, SM_COUNT * 4), DEC_THREADS, 0, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
                                                             camera_center, p7, *params, xyz, color, opacity, out_scaling,
                                                             rot, neural_opacity, mask, st, hc.dev);
     SEGS_LAUNCH_CHECK();
@@ -899,7 +919,7 @@ extern "C" int segs_decode_backward(
     DecodeState st = DecodeState::carve(const_cast<char*>(state), A, nullptr);
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
-    decode_backward_kernel<<<(n_vis + DEC_THREADS - 1) / DEC_THREADS, DEC_THREADS, 0, stream>>>(
+    decode_backward_kernel<<<std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 3), DEC_THREADS, 0, stream>>>(
         n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
         g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact);
     SEGS_LAUNCH_CHECK();
@@ -926,24 +946,19 @@ extern "C" int segs_decode_backward(
     add(F_DPRE + 0 * FEAT, FEAT, -1, dp->opacity_b1, 0, 0);
     add(F_DPRE + 1 * FEAT, FEAT, -1, dp->cov_b1, 0, 0);
     add(F_DPRE + 2 * FEAT, FEAT, -1, dp->color_b1, 0, 0);
+    if (p.use_feat_bank) {
+        add(F_DLOG, 3, F_HB, dp->bank_w2, FEAT, FEAT);          // dW2b[m][j] = sum dlog[m] hb[j]
+        add(F_DPREB, FEAT, F_CAT, dp->bank_w1, 4, 4);           // dW1b[j][i] = sum dpreb[j] cat[i]
+        add(F_DLOG, 3, -1, dp->bank_b2, 0, 0);
+        add(F_DPREB, FEAT, -1, dp->bank_b1, 0, 0);
+    }
     jobs.n = n;
+    const int nrows_used = p.use_feat_bank ? FACT_ROWS : F_HB;     // the bank rows are only written in bank mode
     const size_t smem = size_t(FACT_ROWS) * WG_STRIDE * sizeof(float);
     SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    const int grid = (int)std::min<size_t>(ntiles, SM_COUNT);
-    decode_wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(fact, n_vis, jobs);
+    const int grid = (int)std::min<size_t>(ntiles, SM_COUNT * 2);   // 2 x 111 KB of shared memory per SM
+    decode_wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(fact, n_vis, jobs, nrows_used);
     SEGS_LAUNCH_CHECK();
-    if (p.use_feat_bank) {
-        WJobs bj;
-        n = 0;
-        auto addb = [&](int u0, int np, int v0, float* out, int ld, int nq) { bj.j[n++] = WJob{u0, np, v0, out, ld, nq}; };
-        addb(F_DLOG, 3, F_HB, dp->bank_w2, FEAT, FEAT);          // dW2b[m][j] = sum dlog[m] hb[j]
-        addb(F_DPREB, FEAT, F_CAT, dp->bank_w1, 4, 4);           // dW1b[j][i] = sum dpreb[j] cat[i]
-        addb(F_DLOG, 3, -1, dp->bank_b2, 0, 0);
-        addb(F_DPREB, FEAT, -1, dp->bank_b1, 0, 0);
-        bj.n = n;
-        decode_wgrad_kernel<<<grid, WG_THREADS, smem, stream>>>(fact, n_vis, bj);
-        SEGS_LAUNCH_CHECK();
-    }
     if (p.appearance_dim > 0) {
         decode_appgrad_kernel<<<1, 32, 0, stream>>>(p, *dp, p7);
         SEGS_LAUNCH_CHECK();
