@@ -259,3 +259,20 @@ def test_full_size_C2(device):
     torch.cuda.synchronize()
     _compare_forward(scene, a, m, r, "C2")
     _compare_backward(m, r, r2, "C2")
+
+
+@needs_ref
+@pytest.mark.slow
+def test_large_scene_C5(device):
+    """BASELINE config 5 (5M Gaussians @ 1920x1080, ~81M instances, lists of ~10k per tile; 510
+    super-tiles => the two-digit super-tile sort): bit-exact sort/tile outputs at stress size."""
+    scene = synth.config("C5")
+    t = scene.to_torch(device)
+    a = common.scene_args(t, scene, device)
+    m = common.run_mine(a, t["dL_dout"])
+    r = common.run_ref(a, t["dL_dout"])
+    torch.cuda.synchronize()
+    _compare_forward(scene, a, m, r, "C5")
+    r2 = common.run_ref(a, t["dL_dout"])
+    torch.cuda.synchronize()
+    _compare_backward(m, r, r2, "C5")
