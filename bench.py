@@ -140,7 +140,8 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if distributed and args.impl == "ours":
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=120))
 
     from segs_slam_b200 import synth
     import common
@@ -227,7 +228,17 @@ def main():
     # clocks and the caching allocator are in steady state (the count actually run is reported)
     warm = 0
     t_warm = time.perf_counter()
-    while warm < max(3, args.warmup) or (time.perf_counter() - t_warm < 1.5 and warm < 200):
+    for _ in range(max(3, args.warmup)):
+        step()
+        torch.cuda.synchronize()
+        warm += 1
+    # ... continued until ~1.5 s of GPU work; the extra count is agreed across ranks (the step
+    # contains a collective, so every rank must run the same number of steps)
+    per_step = (time.perf_counter() - t_warm) / warm
+    extra = torch.tensor([max(0, min(200 - warm, int(math.ceil(1.5 / max(per_step, 1e-4))) - warm))], device=dev)
+    if distributed and args.impl == "ours":
+        dist.all_reduce(extra, op=dist.ReduceOp.MAX)
+    for _ in range(int(extra.item())):
         step()
         torch.cuda.synchronize()
         warm += 1
