@@ -234,8 +234,13 @@ def main():
         warm += 1
     # ... continued until ~1.5 s of GPU work; the extra count is agreed across ranks (the step
     # contains a collective, so every rank must run the same number of steps)
-    per_step = (time.perf_counter() - t_warm) / warm
-    extra = torch.tensor([max(0, min(200 - warm, int(math.ceil(1.5 / max(per_step, 1e-4))) - warm))], device=dev)
+    t_two = time.perf_counter()
+    for _ in range(2):                      # steady-state step time (the first steps pay for allocation)
+        step()
+        torch.cuda.synchronize()
+        warm += 1
+    per_step = (time.perf_counter() - t_two) / 2
+    extra = torch.tensor([max(0, min(200 - warm, int(math.ceil(1.5 / max(per_step, 1e-4)))))], device=dev)
     if distributed and args.impl == "ours":
         dist.all_reduce(extra, op=dist.ReduceOp.MAX)
     for _ in range(int(extra.item())):

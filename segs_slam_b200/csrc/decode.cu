@@ -36,6 +36,7 @@ constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int FEAT = 32;        // Model.feat_dim
 constexpr int NOFF = 10;        // Model.n_offsets
 constexpr int XDIM = 36;        // feat(32) + view(3) + dist(1)
+constexpr int W2S = 36;         // shared-memory row stride of the second-layer weights
 constexpr int DEC_THREADS = 128;
 constexpr uint32_t FLAG_AGG = 1u << 30;
 constexpr uint32_t FLAG_PREFIX = 2u << 30;
@@ -47,9 +48,9 @@ struct Pose7 { float v[7]; };
 struct SW {
     float w1[3][FEAT][XDIM];     // 0 opacity, 1 cov, 2 colour: first 35(+dist) input columns, zero padded
     float b1[3][FEAT];           // colour: b1 + W1[:, appearance columns] * appearance
-    float w2o[NOFF][FEAT];
-    float w2s[7 * NOFF][FEAT];
-    float w2c[3 * NOFF][FEAT];
+    float w2o[NOFF][W2S];        // second layers: rows padded to W2S floats (conflict-free when lanes
+    float w2s[7 * NOFF][W2S];    // of a warp read the rows of different offsets)
+    float w2c[3 * NOFF][W2S];
     float b2o[12];
     float b2s[72];
     float b2c[32];
@@ -97,9 +98,9 @@ __device__ __forceinline__ void stage_weights(SW& s, const segs_decode_params& p
         s.w1[1][j][i] = i < in_s ? __ldg(p.cov_w1 + j * in_s + i) : 0.f;
         s.w1[2][j][i] = i < in_c ? __ldg(p.color_w1 + j * ld_c + i) : 0.f;
     }
-    for (int e = tid; e < NOFF * FEAT; e += nt) (&s.w2o[0][0])[e] = __ldg(p.opacity_w2 + e);
-    for (int e = tid; e < 7 * NOFF * FEAT; e += nt) (&s.w2s[0][0])[e] = __ldg(p.cov_w2 + e);
-    for (int e = tid; e < 3 * NOFF * FEAT; e += nt) (&s.w2c[0][0])[e] = __ldg(p.color_w2 + e);
+    for (int e = tid; e < NOFF * FEAT; e += nt) s.w2o[e / FEAT][e % FEAT] = __ldg(p.opacity_w2 + e);
+    for (int e = tid; e < 7 * NOFF * FEAT; e += nt) s.w2s[e / FEAT][e % FEAT] = __ldg(p.cov_w2 + e);
+    for (int e = tid; e < 3 * NOFF * FEAT; e += nt) s.w2c[e / FEAT][e % FEAT] = __ldg(p.color_w2 + e);
     for (int e = tid; e < 72; e += nt) {
         if (e < 12) s.b2o[e] = e < NOFF ? __ldg(p.opacity_b2 + e) : 0.f;
         s.b2s[e] = e < 7 * NOFF ? __ldg(p.cov_b2 + e) : 0.f;
@@ -291,7 +292,10 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w
 // =======================================================================================
 // forward
 // =======================================================================================
-__global__ void __launch_bounds__(DEC_THREADS, 4)
+constexpr int H_W = 2 * FEAT + 4;      // floats per anchor in s_h (68: conflict-free float4 reads across anchors)
+constexpr int REC_W = 20;
+constexpr size_t FWD_SMEM = sizeof(SW) + sizeof(float) * DEC_THREADS * (H_W + REC_W) + sizeof(uint32_t) * (DEC_THREADS + 4);
+__global__ void __launch_bounds__(DEC_THREADS, 2)
 decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, const float* __restrict__ anchor,
                       const float* __restrict__ anchor_feat, const float* __restrict__ offset,
                       const float* __restrict__ scaling, const float* __restrict__ cam, const Pose7 pose,
@@ -300,7 +304,11 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
                       float* __restrict__ neural_opacity, unsigned char* __restrict__ out_mask, DecodeState st,
                       volatile uint32_t* __restrict__ host_counts)
 {
-    __shared__ __align__(16) SW sw;
+    extern __shared__ __align__(16) unsigned char s_dec[];
+    SW& sw = *reinterpret_cast<SW*>(s_dec);
+    float* s_h = reinterpret_cast<float*>(s_dec + sizeof(SW));            // [128][H_W]: h_cov | h_colour per anchor
+    float* s_rec = s_h + DEC_THREADS * H_W;                                // [128][REC_W]: anchor, scaling, opacities, mask
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_rec + DEC_THREADS * REC_W);   // [129] first row of every anchor
     __shared__ uint32_t s_aid[DEC_THREADS];
     __shared__ uint32_t s_warp[DEC_THREADS / 32];
     __shared__ uint32_t s_tile, s_vis_base, s_row_base;
@@ -360,58 +368,84 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
                 }
             }
         }
+        // ---- phase A tail: hidden layers of the covariance and colour MLPs -> shared memory ----
+        if (active) {
+            s_row[tid] = row_off;
+            float* rec = s_rec + tid * REC_W;
+            rec[0] = in.ax; rec[1] = in.ay; rec[2] = in.az;
+#pragma unroll
+            for (int k = 0; k < 6; ++k) rec[3 + k] = in.s[k];
+#pragma unroll
+            for (int o = 0; o < NOFF; ++o) rec[9 + o] = op[o];
+            rec[19] = __uint_as_float(m);
+            if (m != 0) {
+                float h[FEAT];
+                layer1(sw.w1[1], sw.b1[1], x, h);
+#pragma unroll
+                for (int q = 0; q < FEAT / 4; ++q)
+                    *reinterpret_cast<float4*>(s_h + tid * H_W + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+                layer1(sw.w1[2], sw.b1[2], x, h);
+#pragma unroll
+                for (int q = 0; q < FEAT / 4; ++q)
+                    *reinterpret_cast<float4*>(s_h + tid * H_W + FEAT + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
+            }
+        }
+        if (tid == 0) s_row[n_vis] = n_rows;                  // sentinel for the search below
         __syncthreads();
-        if (!active) continue;
-        const size_t ordinal = size_t(s_vis_base) + tid;
-        const size_t row0 = size_t(s_row_base) + row_off;
-        st.anchor_index[ordinal] = (uint32_t)a;
-        st.row_start[ordinal] = (uint32_t)row0;
-        st.mask_bits[ordinal] = m;
+        const size_t vis_base = s_vis_base, row_base = s_row_base;
+        if (active) {
+            const size_t ordinal = vis_base + tid;
+            st.anchor_index[ordinal] = (uint32_t)a;
+            st.row_start[ordinal] = (uint32_t)(row_base + row_off);
+            st.mask_bits[ordinal] = m;
 #pragma unroll
-        for (int o = 0; o < NOFF; ++o) {
-            neural_opacity[ordinal * NOFF + o] = op[o];
-            out_mask[ordinal * NOFF + o] = (m >> o) & 1u;
+            for (int o = 0; o < NOFF; ++o) {
+                neural_opacity[ordinal * NOFF + o] = op[o];
+                out_mask[ordinal * NOFF + o] = (m >> o) & 1u;
+            }
         }
-        if (m == 0) continue;
 
-        // ---- D4 (cov) + D5: geometry rows ----
-        {
-            float h[FEAT];
-            layer1(sw.w1[1], sw.b1[1], x, h);
-            size_t r = row0;
+        // ---- phase B (D4 second layers + D5): thread = output row; consecutive threads write
+        //      consecutive rows, and no lane idles on a masked-out offset ----
+        for (uint32_t r = tid; r < n_rows; r += DEC_THREADS) {
+            int lo = 0, hi = (int)n_vis;                 // s_row[lo] <= r < s_row[hi]
 #pragma unroll
-            for (int o = 0; o < NOFF; ++o) {
-                if (!((m >> o) & 1u)) continue;
-                float sr[7];
-#pragma unroll
-                for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
-                const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
-                            oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
-                // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
-                out_xyz[3 * r] = in.ax + ox * in.s[0];
-                out_xyz[3 * r + 1] = in.ay + oy * in.s[1];
-                out_xyz[3 * r + 2] = in.az + oz * in.s[2];
-                out_scaling[3 * r] = in.s[3] * sigmoidf_(sr[0]);
-                out_scaling[3 * r + 1] = in.s[4] * sigmoidf_(sr[1]);
-                out_scaling[3 * r + 2] = in.s[5] * sigmoidf_(sr[2]);
-                const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
-                *reinterpret_cast<float4*>(out_rot + 4 * r) = make_float4(sr[3] / nrm, sr[4] / nrm, sr[5] / nrm, sr[6] / nrm);
-                out_opacity[r] = op[o];
-                ++r;
+            for (int step = 0; step < 7; ++step) {
+                const int mid = (lo + hi) >> 1;
+                if (mid > lo && s_row[mid] <= r) lo = mid; else if (mid > lo) hi = mid;
             }
-        }
-        // ---- D4 (colour) ----
-        {
+            const float* rec = s_rec + lo * REC_W;
+            const uint32_t mm = __float_as_uint(rec[19]);
+            const int o = __fns(mm, 0, (int)(r - s_row[lo]) + 1);     // the (r - first)-th surviving offset
+            const size_t aid = s_aid[lo];
             float h[FEAT];
-            layer1(sw.w1[2], sw.b1[2], x, h);
-            size_t r = row0;
 #pragma unroll
-            for (int o = 0; o < NOFF; ++o) {
-                if (!((m >> o) & 1u)) continue;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) out_color[3 * r + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
-                ++r;
+            for (int q = 0; q < FEAT / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(s_h + lo * H_W + 4 * q);
+                h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
             }
+            float sr[7];
+#pragma unroll
+            for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+            const size_t row = row_base + r;
+            const float* off = offset + (aid * NOFF + o) * 3;
+            // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
+            out_xyz[3 * row] = rec[0] + __ldg(off) * rec[3];
+            out_xyz[3 * row + 1] = rec[1] + __ldg(off + 1) * rec[4];
+            out_xyz[3 * row + 2] = rec[2] + __ldg(off + 2) * rec[5];
+            out_scaling[3 * row] = rec[6] * sigmoidf_(sr[0]);
+            out_scaling[3 * row + 1] = rec[7] * sigmoidf_(sr[1]);
+            out_scaling[3 * row + 2] = rec[8] * sigmoidf_(sr[2]);
+            const float nrm = fmaxf(sqrtf(sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6]), 1e-12f);
+            *reinterpret_cast<float4*>(out_rot + 4 * row) = make_float4(sr[3] / nrm, sr[4] / nrm, sr[5] / nrm, sr[6] / nrm);
+            out_opacity[row] = rec[9 + o];
+#pragma unroll
+            for (int q = 0; q < FEAT / 4; ++q) {
+                const float4 t = *reinterpret_cast<const float4*>(s_h + lo * H_W + FEAT + 4 * q);
+                h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
+            }
+#pragma unroll
+            for (int k = 0; k < 3; ++k) out_color[3 * row + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
         }
     }
 }
@@ -851,7 +885,8 @@ extern "C" int segs_decode_forward(
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
     const int tiles = (A + DEC_THREADS - 1) / DEC_THREADS;
-    decode_forward_kernel<<<std::min(tiles, SM_COUNT * 4), DEC_THREADS, 0, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
+    SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+    decode_forward_kernel<<<std::min(tiles, SM_COUNT * 2), DEC_THREADS, FWD_SMEM, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
                                                             camera_center, p7, *params, xyz, color, opacity, out_scaling,
                                                             rot, neural_opacity, mask, st, hc.dev);
     SEGS_LAUNCH_CHECK();
