@@ -44,10 +44,10 @@ constexpr uint32_t FLAG_MASK = 3u << 30;
 
 struct Pose7 { float v[7]; };
 
-// shared-memory copy of the weights
-struct SW {
-    float w1[3][FEAT][XDIM];     // 0 opacity, 1 cov, 2 colour: first 35(+dist) input columns, zero padded
-    float b1[3][FEAT];           // colour: b1 + W1[:, appearance columns] * appearance
+// shared-memory copy of the weights.  SWF: everything except the first-layer matrices (the forward
+// feeds those to the tensor cores from its own operand tiles); SW adds them for the backward.
+struct SWF {
+    float b1[3][FEAT];           // 0 opacity, 1 cov, 2 colour (colour: b1 + W1[:, appearance columns] * appearance)
     float w2o[NOFF][W2S];        // second layers: rows padded to W2S floats (conflict-free when lanes
     float w2s[7 * NOFF][W2S];    // of a warp read the rows of different offsets)
     float w2c[3 * NOFF][W2S];
@@ -59,6 +59,9 @@ struct SW {
     float wb2[3][FEAT];
     float bb2[4];
     float app[32];               // appearance vector of this view
+};
+struct SW : SWF {
+    float w1[3][FEAT][XDIM];     // first 35(+dist) input columns, zero padded
 };
 
 // opaque state shared by forward and backward
@@ -86,17 +89,22 @@ struct DecodeState {
     }
 };
 
-__device__ __forceinline__ void stage_weights(SW& s, const segs_decode_params& p, const Pose7& pose)
+template <class SWT>
+__device__ __forceinline__ void stage_weights(SWT& s, const segs_decode_params& p, const Pose7& pose)
 {
     const int tid = threadIdx.x, nt = blockDim.x;
     const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
     const int in_c = 35 + (p.add_color_dist ? 1 : 0);
     const int ld_c = in_c + p.appearance_dim;
-    for (int e = tid; e < FEAT * XDIM; e += nt) {
-        const int j = e / XDIM, i = e % XDIM;
-        s.w1[0][j][i] = i < in_o ? __ldg(p.opacity_w1 + j * in_o + i) : 0.f;
-        s.w1[1][j][i] = i < in_s ? __ldg(p.cov_w1 + j * in_s + i) : 0.f;
-        s.w1[2][j][i] = i < in_c ? __ldg(p.color_w1 + j * ld_c + i) : 0.f;
+    if constexpr (sizeof(SWT) == sizeof(SW)) {
+        for (int e = tid; e < FEAT * XDIM; e += nt) {
+            const int j = e / XDIM, i = e % XDIM;
+            s.w1[0][j][i] = i < in_o ? __ldg(p.opacity_w1 + j * in_o + i) : 0.f;
+            s.w1[1][j][i] = i < in_s ? __ldg(p.cov_w1 + j * in_s + i) : 0.f;
+            s.w1[2][j][i] = i < in_c ? __ldg(p.color_w1 + j * ld_c + i) : 0.f;
+        }
+    } else {
+        (void)in_o; (void)in_s;
     }
     for (int e = tid; e < NOFF * FEAT; e += nt) s.w2o[e / FEAT][e % FEAT] = __ldg(p.opacity_w2 + e);
     for (int e = tid; e < 7 * NOFF * FEAT; e += nt) s.w2s[e / FEAT][e % FEAT] = __ldg(p.cov_w2 + e);
@@ -194,7 +202,7 @@ struct AnchorIn {
 };
 
 // D1 + D2: inputs of the three MLPs for one anchor.  x = [feat'(32), ob_view(3), ob_dist]
-__device__ __forceinline__ void build_input(const SW& sw, bool use_bank, const float* __restrict__ feat_row,
+__device__ __forceinline__ void build_input(const SWF& sw, bool use_bank, const float* __restrict__ feat_row,
                                             const AnchorIn& in, float (&x)[XDIM], float (&bankw)[3])
 {
     const float ux = in.vx / in.dist, uy = in.vy / in.dist, uz = in.vz / in.dist;
@@ -292,9 +300,115 @@ __device__ __forceinline__ uint32_t cta_exclusive_scan(uint32_t v, uint32_t* s_w
 // =======================================================================================
 // forward
 // =======================================================================================
+// The first layers of the three MLPs are ONE dense contraction per tile of 128 anchors,
+//   H[128 x 96] = X[128 x 40] * W1cat^T[40 x 96]      (X = [feat'(32), view(3), dist, 0-pad]),
+// and run on the 5th-generation tensor cores: tcgen05.mma kind::tf32, M = 128, N = 96, K = 8 per
+// instruction, both operands K-major in shared memory (no-swizzle core-matrix layout), the
+// accumulator in TMEM.  A single TF32 product (10-bit mantissa) is not enough — the opacity > 0
+// mask decides which Gaussians exist, and parity is 1e-5 — so every operand is split into
+// hi = tf32(v) and lo = v - hi and three MMAs (hi*hi + hi*lo + lo*hi) accumulate per K-step
+// (3xTF32, error ~2^-21, the level of FP32 summation-order noise).  The epilogue reads each
+// anchor's 96 pre-activations back with tcgen05.ld (thread = TMEM lane = anchor).
+namespace tc {
+
+constexpr int TM = 128;                  // anchors per tile = MMA M = TMEM lanes
+constexpr int TN = 3 * FEAT;             // 96 hidden units of the three MLPs
+constexpr int TK = 40;                   // XDIM padded to a multiple of 8
+constexpr int KB = TK / 4;               // 16-byte K-blocks per row
+constexpr int CORE = 128;                // bytes of one 8 x 16 B core matrix
+constexpr uint32_t SBO = KB * CORE;      // byte stride between 8-row groups
+constexpr uint32_t LBO = CORE;           // byte stride between K-blocks
+constexpr int A_BYTES = TM * TK * 4;     // 20480
+constexpr int B_BYTES = TN * TK * 4;     // 15360
+constexpr int TMEM_COLS = 128;           // power of two >= TN
+// instruction descriptor (cute::UMMA::InstrDescriptor): D = F32, A = B = TF32, both K-major
+constexpr uint32_t IDESC = (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(TN >> 3) << 17) | (uint32_t(TM >> 4) << 24);
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// byte offset of element (row, k) in the K-major no-swizzle canonical layout
+__device__ __forceinline__ uint32_t canon_off(int row, int k) {
+    return uint32_t(((row >> 3) * KB + (k >> 2)) * CORE + (row & 7) * 16 + (k & 3) * 4);
+}
+
+// shared-memory matrix descriptor (cute::UMMA::SmemDescriptor), no swizzle, version 1
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(LBO >> 4) << 16) | (uint64_t(SBO >> 4) << 32) | (uint64_t(1) << 46);
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;\n" ::"r"(smem_u32(dst_smem)), "r"(ncols));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;\n" ::);
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;\n" ::"r"(taddr), "r"(ncols));
+}
+__device__ __forceinline__ void fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_after_sync() { asm volatile("tcgen05.fence::after_thread_sync;\n" ::: "memory"); }
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;\n" ::: "memory"); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count));
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "WAIT_LOOP_%=:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+        "@p bra WAIT_DONE_%=;\n"
+        "bra WAIT_LOOP_%=;\n"
+        "WAIT_DONE_%=:\n"
+        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], issued by ONE thread
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(IDESC), "r"(accumulate) : "memory");
+}
+// arrive on the mbarrier when every MMA issued so far by this thread has completed
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n" ::"r"(smem_u32(bar)) : "memory");
+}
+// 32 consecutive columns of this thread's TMEM lane (warp-collective)
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+        "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];\n"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;\n" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+__device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+
+}  // namespace tc
+
 constexpr int H_W = 2 * FEAT + 4;      // floats per anchor in s_h (68: conflict-free float4 reads across anchors)
 constexpr int REC_W = 20;
-constexpr size_t FWD_SMEM = sizeof(SW) + sizeof(float) * DEC_THREADS * (H_W + REC_W) + sizeof(uint32_t) * (DEC_THREADS + 4);
+constexpr size_t align128(size_t x) { return (x + 127) & ~size_t(127); }
+constexpr size_t OFF_B_HI = align128(sizeof(SWF));
+constexpr size_t OFF_B_LO = OFF_B_HI + tc::B_BYTES;
+constexpr size_t OFF_A_HI = OFF_B_LO + tc::B_BYTES;          // A operand tiles; re-used as s_h once the MMAs are done
+constexpr size_t OFF_A_LO = OFF_A_HI + tc::A_BYTES;
+constexpr size_t OFF_REC = OFF_A_HI + 2 * tc::A_BYTES;
+constexpr size_t OFF_ROW = OFF_REC + sizeof(float) * DEC_THREADS * REC_W;
+constexpr size_t FWD_SMEM = OFF_ROW + sizeof(uint32_t) * (DEC_THREADS + 4);
+static_assert(sizeof(float) * DEC_THREADS * H_W <= 2 * tc::A_BYTES, "s_h must fit in the A operand tiles");
+static_assert(DEC_THREADS == tc::TM, "one thread per TMEM lane");
+
 __global__ void __launch_bounds__(DEC_THREADS, 2)
 decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, const float* __restrict__ anchor,
                       const float* __restrict__ anchor_feat, const float* __restrict__ offset,
@@ -304,21 +418,51 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
                       float* __restrict__ neural_opacity, unsigned char* __restrict__ out_mask, DecodeState st,
                       volatile uint32_t* __restrict__ host_counts)
 {
-    extern __shared__ __align__(16) unsigned char s_dec[];
-    SW& sw = *reinterpret_cast<SW*>(s_dec);
-    float* s_h = reinterpret_cast<float*>(s_dec + sizeof(SW));            // [128][H_W]: h_cov | h_colour per anchor
-    float* s_rec = s_h + DEC_THREADS * H_W;                                // [128][REC_W]: anchor, scaling, opacities, mask
-    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_rec + DEC_THREADS * REC_W);   // [129] first row of every anchor
+    extern __shared__ __align__(1024) unsigned char s_dec[];
+    SWF& sw = *reinterpret_cast<SWF*>(s_dec);
+    unsigned char* sB_hi = s_dec + OFF_B_HI;
+    unsigned char* sB_lo = s_dec + OFF_B_LO;
+    unsigned char* sA_hi = s_dec + OFF_A_HI;
+    unsigned char* sA_lo = s_dec + OFF_A_LO;
+    float* s_h = reinterpret_cast<float*>(s_dec + OFF_A_HI);               // [128][H_W]: h_cov | h_colour per anchor
+    float* s_rec = reinterpret_cast<float*>(s_dec + OFF_REC);              // [128][REC_W]: anchor, scaling, opacities, mask
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_dec + OFF_ROW);        // [129] first row of every anchor
     __shared__ uint32_t s_aid[DEC_THREADS];
     __shared__ uint32_t s_warp[DEC_THREADS / 32];
-    __shared__ uint32_t s_tile, s_vis_base, s_row_base;
-    const int tid = threadIdx.x, lane = tid & 31;
+    __shared__ uint32_t s_tile, s_vis_base, s_row_base, s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const uint32_t ntiles = (uint32_t)((A + DEC_THREADS - 1) / DEC_THREADS);
 
-    stage_weights(sw, p, pose);          // once per (persistent) CTA; contains __syncthreads
+    // ---- once per (persistent) CTA: TMEM, mbarrier, weights ----
+    if (warp == 0) tc::tmem_alloc(&s_tmem, tc::TMEM_COLS);
+    if (tid == 0) tc::mbar_init(&s_bar, 1);
+    {
+        // B operand: W1cat[n][k], n = 32 * mlp + hidden unit, k = input column; hi/lo TF32 split
+        const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
+        const int in_c = 35 + (p.add_color_dist ? 1 : 0), ld_c = in_c + p.appearance_dim;
+        for (int e = tid; e < tc::TN * tc::TK; e += DEC_THREADS) {
+            const int n = e / tc::TK, k = e % tc::TK, j = n & 31;
+            float w = 0.f;
+            if (n < 32) { if (k < in_o) w = __ldg(p.opacity_w1 + j * in_o + k); }
+            else if (n < 64) { if (k < in_s) w = __ldg(p.cov_w1 + j * in_s + k); }
+            else { if (k < in_c) w = __ldg(p.color_w1 + j * ld_c + k); }
+            const float hi = tc::tf32_hi(w);
+            const uint32_t off = tc::canon_off(n, k);
+            *reinterpret_cast<float*>(sB_hi + off) = hi;
+            *reinterpret_cast<float*>(sB_lo + off) = w - hi;
+        }
+    }
+    stage_weights(sw, p, pose);          // contains __syncthreads
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    uint32_t phase = 0;
 
     for (;;) {
-        __syncthreads();                 // previous tile is done with s_tile / s_aid / the bases
+        __syncthreads();                 // previous tile is done with s_tile / s_aid / the bases / s_h
         if (tid == 0) s_tile = atomicAdd(st.counters, 1u);
         __syncthreads();
         const uint32_t tile = s_tile;
@@ -334,23 +478,80 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
         const bool active = (uint32_t)tid < n_vis;
         const size_t a = active ? s_aid[tid] : 0;
 
-        // ---- D2-D4 (opacity): inputs + opacity MLP -> mask ----
+        // ---- D2/D3: MLP input row of this anchor -> A operand tiles (hi / lo) ----
         AnchorIn in;
-        float x[XDIM];
-        float op[NOFF];
-        uint32_t m = 0;
         if (active) {
             in = load_anchor(anchor, scaling, cam, a);
-            float bankw[3];
+            float x[XDIM], bankw[3];
             build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
-            float h[FEAT];
-            layer1(sw.w1[0], sw.b1[0], x, h);
 #pragma unroll
-            for (int o = 0; o < NOFF; ++o) {
-                op[o] = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
-                if (op[o] > 0.0f) m |= 1u << o;               // mask = neural_opacity > 0   (:278-279)
+            for (int kb = 0; kb < tc::KB; ++kb) {
+                float4 hi = make_float4(0.f, 0.f, 0.f, 0.f), lo = hi;
+                if (kb < XDIM / 4) {
+                    hi = make_float4(tc::tf32_hi(x[4 * kb]), tc::tf32_hi(x[4 * kb + 1]), tc::tf32_hi(x[4 * kb + 2]), tc::tf32_hi(x[4 * kb + 3]));
+                    lo = make_float4(x[4 * kb] - hi.x, x[4 * kb + 1] - hi.y, x[4 * kb + 2] - hi.z, x[4 * kb + 3] - hi.w);
+                }
+                const uint32_t off = tc::canon_off(tid, 4 * kb);
+                *reinterpret_cast<float4*>(sA_hi + off) = hi;
+                *reinterpret_cast<float4*>(sA_lo + off) = lo;
             }
         }
+        tc::fence_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        tc::fence_before_sync();
+        __syncthreads();
+
+        // ---- D4 first layers on the tensor cores: 5 K-steps x 3 split products ----
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t a_hi = tc::smem_u32(sA_hi), a_lo = tc::smem_u32(sA_lo);
+            const uint32_t b_hi = tc::smem_u32(sB_hi), b_lo = tc::smem_u32(sB_lo);
+#pragma unroll
+            for (int j = 0; j < tc::TK / 8; ++j) {
+                const uint32_t ko = 2 * j * tc::CORE;        // two K-blocks per instruction
+                tc::umma_tf32(tmem, tc::make_desc(a_hi + ko), tc::make_desc(b_hi + ko), j > 0 ? 1u : 0u);
+                tc::umma_tf32(tmem, tc::make_desc(a_hi + ko), tc::make_desc(b_lo + ko), 1u);
+                tc::umma_tf32(tmem, tc::make_desc(a_lo + ko), tc::make_desc(b_hi + ko), 1u);
+            }
+            tc::umma_commit(&s_bar);
+        }
+        tc::mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+
+        // ---- epilogue: thread = TMEM lane = anchor.  (tcgen05.ld is warp-collective: every
+        //      thread loads, only active anchors use the values.)  The A tiles are free now: s_h
+        //      lives there. ----
+        const uint32_t lane_base = tmem + (uint32_t(warp * 32) << 16);
+        float op[NOFF];
+        uint32_t m = 0;
+        {
+            float h[FEAT];
+            tc::tmem_ld32(lane_base + 0, h);
+            if (active) {
+#pragma unroll
+                for (int j = 0; j < FEAT; ++j) h[j] = fmaxf(h[j] + sw.b1[0][j], 0.f);
+#pragma unroll
+                for (int o = 0; o < NOFF; ++o) {
+                    op[o] = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+                    if (op[o] > 0.0f) m |= 1u << o;               // mask = neural_opacity > 0   (:278-279)
+                }
+            }
+        }
+        // (the MMAs — the last readers of the A tiles — have completed: s_h may overwrite them)
+#pragma unroll
+        for (int mlp = 1; mlp < 3; ++mlp) {
+            float h[FEAT];
+            tc::tmem_ld32(lane_base + mlp * FEAT, h);
+            if (active && m != 0) {
+#pragma unroll
+                for (int q = 0; q < FEAT / 4; ++q)
+                    *reinterpret_cast<float4*>(s_h + tid * H_W + (mlp - 1) * FEAT + 4 * q) =
+                        make_float4(fmaxf(h[4 * q] + sw.b1[mlp][4 * q], 0.f), fmaxf(h[4 * q + 1] + sw.b1[mlp][4 * q + 1], 0.f),
+                                    fmaxf(h[4 * q + 2] + sw.b1[mlp][4 * q + 2], 0.f), fmaxf(h[4 * q + 3] + sw.b1[mlp][4 * q + 3], 0.f));
+            }
+        }
+        tc::fence_before_sync();         // TMEM reads are ordered before the next tile's MMAs (across the barriers below)
+
         uint32_t n_rows;
         const uint32_t row_off = cta_exclusive_scan(__popc(m), s_warp, &n_rows);
 
@@ -368,7 +569,6 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
                 }
             }
         }
-        // ---- phase A tail: hidden layers of the covariance and colour MLPs -> shared memory ----
         if (active) {
             s_row[tid] = row_off;
             float* rec = s_rec + tid * REC_W;
@@ -378,17 +578,6 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
 #pragma unroll
             for (int o = 0; o < NOFF; ++o) rec[9 + o] = op[o];
             rec[19] = __uint_as_float(m);
-            if (m != 0) {
-                float h[FEAT];
-                layer1(sw.w1[1], sw.b1[1], x, h);
-#pragma unroll
-                for (int q = 0; q < FEAT / 4; ++q)
-                    *reinterpret_cast<float4*>(s_h + tid * H_W + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-                layer1(sw.w1[2], sw.b1[2], x, h);
-#pragma unroll
-                for (int q = 0; q < FEAT / 4; ++q)
-                    *reinterpret_cast<float4*>(s_h + tid * H_W + FEAT + 4 * q) = make_float4(h[4 * q], h[4 * q + 1], h[4 * q + 2], h[4 * q + 3]);
-            }
         }
         if (tid == 0) s_row[n_vis] = n_rows;                  // sentinel for the search below
         __syncthreads();
@@ -405,8 +594,8 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
             }
         }
 
-        // ---- phase B (D4 second layers + D5): thread = output row; consecutive threads write
-        //      consecutive rows, and no lane idles on a masked-out offset ----
+        // ---- D4 second layers + D5: thread = output row; consecutive threads write consecutive
+        //      rows, and no lane idles on a masked-out offset ----
         for (uint32_t r = tid; r < n_rows; r += DEC_THREADS) {
             int lo = 0, hi = (int)n_vis;                 // s_row[lo] <= r < s_row[hi]
 #pragma unroll
@@ -448,6 +637,11 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
             for (int k = 0; k < 3; ++k) out_color[3 * row + k] = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
         }
     }
+
+    // ---- teardown: the allocating warp frees TMEM once every warp is done with it ----
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tc::TMEM_COLS);
 }
 
 // =======================================================================================
