@@ -110,6 +110,7 @@ class _DecodeFunction(torch.autograd.Function):
                 state.data_ptr(), ctx.n_vis, ctx.n_out, _ptr(g_xyz), _ptr(g_color), _ptr(g_opacity), _ptr(g_scaling),
                 _ptr(g_rot), _ptr(g_nop), _ptr(d_anchor), _ptr(d_feat), _ptr(d_offset), _ptr(d_scaling),
                 C.byref(grads), scratch.cb, None, _stream()))
+        scratch.done()
         return (None, None, None, None, d_anchor, d_feat, d_offset, d_scaling, *d_w)
 
 

@@ -45,6 +45,12 @@ class _Grower:
         self.t.resize_(int(nbytes))
         return self.t.data_ptr()
 
+    def done(self):
+        """Drop the ctypes thunk: it references the bound method, i.e. a reference cycle that would keep
+        the buffer alive until the cyclic GC runs (hundreds of MB per call at C2)."""
+        self.cb = None
+        return self.t
+
 
 def _check_means(means3D: torch.Tensor) -> None:
     if means3D.dim() != 2 or means3D.size(1) != 3:
@@ -83,7 +89,7 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
                 _ptr(cov), _ptr(view), _ptr(proj), _ptr(cam),
                 float(tan_fovx), float(tan_fovy), int(bool(prefiltered)),
                 _ptr(out_color), _ptr(radii), C.byref(rendered), _stream()))
-    return rendered.value, out_color, radii, geom.t, binning.t, img.t
+    return rendered.value, out_color, radii, geom.done(), binning.done(), img.done()
 
 
 def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, rotations, scale_modifier,
@@ -195,6 +201,7 @@ def distCUDA2(points):
         scratch = _Grower(points.device)
         with torch.cuda.device(points.device):
             _lib.check(lib.segs_knn_mean_dist2(P, _ptr(pts), _ptr(means), scratch.cb, None, _stream()))
+            scratch.done()
             # scratch is only referenced by work already queued on the current stream; torch's
             # caching allocator keeps the block stream-ordered, so dropping it here is safe.
     return means

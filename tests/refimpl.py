@@ -65,6 +65,10 @@ class _Grower:
         self.t.resize_(int(n))
         return self.t.data_ptr()
 
+    def done(self):   # break the ctypes-thunk reference cycle (same as the product's binding)
+        self.cb = None
+        return self.t
+
 
 def _empty(dev):
     return torch.empty(0, dtype=torch.float32, device=dev)
@@ -90,7 +94,7 @@ def forward(bg, means3D, colors, opacity, scales, rotations, scale_modifier, cov
                                           _ptr(cov3D_precomp), _ptr(viewmatrix), _ptr(projmatrix), _ptr(campos),
                                           float(tan_fovx), float(tan_fovy), int(prefiltered), _ptr(out_color),
                                           _ptr(radii))
-    return rendered, out_color, radii, g.t, b.t, i.t
+    return rendered, out_color, radii, g.done(), b.done(), i.done()
 
 
 def backward(bg, means3D, radii, colors, scales, rotations, scale_modifier, cov3D_precomp, viewmatrix,
@@ -129,6 +133,7 @@ def visible_filter(means3D, scales, rotations, scale_modifier, cov3D_precomp, vi
                                float(scale_modifier), _ptr(rotations), _ptr(cov3D_precomp), _ptr(viewmatrix),
                                _ptr(projmatrix), float(tan_fovx), float(tan_fovy), 0, _ptr(radii))
         lib.ref_sync()
+    g.done(); b.done(); i.done()
     return radii
 
 
