@@ -174,27 +174,56 @@ preprocess_backward_kernel(int P, int D, int M,
     float d_rot[4] = {0.f, 0.f, 0.f, 0.f};
     bool sh_written = false;
 
-    // Every global load of this thread is issued up front, before the first dependent use, so
-    // the kernel pays ONE memory round trip instead of three serialised ones (visibility flag ->
-    // accumulator/mean/covariance -> scale/rotation).  Out-of-range lanes read element 0.
+    // Every global load of this CTA is issued up front, before the first dependent use, so the
+    // kernel pays ONE memory round trip.  The AoS inputs (48-B accumulators, [P,3] means and scales)
+    // are fetched with fully coalesced loads into the staging buffer that later carries the
+    // outputs: a thread-strided 12/48-B access pattern would touch every sector three times.
     const size_t li = in_range ? idx : 0;
-    float4 a0 = acc[3 * li + 0];
-    float4 a1 = acc[3 * li + 1];
-    float4 a2 = acc[3 * li + 2];
-    float3 mean = make_float3(__ldg(means3D + 3 * li), __ldg(means3D + 3 * li + 1), __ldg(means3D + 3 * li + 2));
+    float4 t0 = make_float4(0.f, 0.f, 0.f, 0.f), t1 = t0, t2 = t0;
+    float m0[3], sc0[3];
+    {
+        const float4* acc_blk = acc + 3 * first;
+        const int n4 = 3 * n_blk;
+        if ((int)threadIdx.x < n4) t0 = acc_blk[threadIdx.x];
+        if ((int)threadIdx.x + BWD_THREADS < n4) t1 = acc_blk[threadIdx.x + BWD_THREADS];
+        if ((int)threadIdx.x + 2 * BWD_THREADS < n4) t2 = acc_blk[threadIdx.x + 2 * BWD_THREADS];
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            const int j = threadIdx.x + k * BWD_THREADS;
+            m0[k] = j < 3 * n_blk ? __ldg(means3D + 3 * first + j) : 0.f;
+            sc0[k] = (scales != nullptr && j < 3 * n_blk) ? __ldg(scales + 3 * first + j) : 1.f;
+        }
+    }
     float c3[6];
 #pragma unroll
     for (int k = 0; k < 6; ++k)
         c3[k] = cov3D_precomp ? __ldg(cov3D_precomp + 6 * li + k) : __ldg(cov3D_planes + size_t(k) * P + li);
     float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
-    float sc3[3] = {1.f, 1.f, 1.f};
-    if (scales != nullptr) {
-        q = __ldg(reinterpret_cast<const float4*>(rotations) + li);
-        sc3[0] = __ldg(scales + 3 * li); sc3[1] = __ldg(scales + 3 * li + 1); sc3[2] = __ldg(scales + 3 * li + 2);
-    }
-    // (loaded last: the SM issues in order, so the first instruction that waits on a load
-    // must come after every other load has been issued)
+    if (scales != nullptr) q = __ldg(reinterpret_cast<const float4*>(rotations) + li);
     const uint32_t touched = __ldg(tiles_touched + li);
+    {
+        // (stores after the last load: the SM issues in order, so nothing that waits on a load may
+        // sit in front of another load)
+        float4* s_acc = reinterpret_cast<float4*>(s_out);                    // [256][3] float4
+        float* s_mean = s_out + BWD_THREADS * 12;                            // [256][3]
+        float* s_scale = s_mean + BWD_THREADS * 3;                           // [256][3]
+        s_acc[threadIdx.x] = t0; s_acc[threadIdx.x + BWD_THREADS] = t1; s_acc[threadIdx.x + 2 * BWD_THREADS] = t2;
+#pragma unroll
+        for (int k = 0; k < 3; ++k) {
+            s_mean[threadIdx.x + k * BWD_THREADS] = m0[k];
+            s_scale[threadIdx.x + k * BWD_THREADS] = sc0[k];
+        }
+    }
+    __syncthreads();
+    const int tl = in_range ? (int)threadIdx.x : 0;
+    const float4 a0 = reinterpret_cast<const float4*>(s_out)[3 * tl + 0];
+    const float4 a1 = reinterpret_cast<const float4*>(s_out)[3 * tl + 1];
+    const float4 a2 = reinterpret_cast<const float4*>(s_out)[3 * tl + 2];
+    const float3 mean = make_float3(s_out[BWD_THREADS * 12 + 3 * tl], s_out[BWD_THREADS * 12 + 3 * tl + 1],
+                                    s_out[BWD_THREADS * 12 + 3 * tl + 2]);
+    const float sc3[3] = {s_out[BWD_THREADS * 15 + 3 * tl], s_out[BWD_THREADS * 15 + 3 * tl + 1],
+                          s_out[BWD_THREADS * 15 + 3 * tl + 2]};
+    __syncthreads();       // everyone holds its inputs in registers: the buffer is free for the outputs
 
     // The chain below runs for EVERY lane (no branch for the loads to sink into; ~11% of the
     // Gaussians are not rendered and compute on don't-care values) and the results are masked

@@ -70,16 +70,16 @@ rs_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int begin_bit, int n
     }
 }
 
-// exclusive prefix over the 256 bins of one digit histogram; thread t returns the base of bin t
-__device__ __forceinline__ uint32_t bin_base_from_hist(const uint32_t* __restrict__ hist, uint32_t* s_warp) {
+// CTA-wide exclusive scan of one value per thread (256 threads); contains two __syncthreads
+__device__ __forceinline__ uint32_t scan256(uint32_t c, uint32_t* s_warp) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const uint32_t c = hist[threadIdx.x];
     uint32_t inc = c;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
         const uint32_t y = __shfl_up_sync(FULL, inc, o);
         if (lane >= o) inc += y;
     }
+    __syncthreads();                     // s_warp may still be read from a previous scan
     if (lane == 31) s_warp[warp] = inc;
     __syncthreads();
     uint32_t woff = 0;
@@ -96,7 +96,10 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
                const uint32_t* __restrict__ hist /*[256] of this digit*/, uint32_t* __restrict__ ticket,
                volatile uint32_t* __restrict__ look /*[tiles][256]*/)
 {
-    __shared__ uint32_t s_wh[RS_WARPS][RADIX_BINS];   // per-warp digit counts -> per-warp scatter bases
+    __shared__ uint32_t s_wh[RS_WARPS][RADIX_BINS];   // per-warp digit counts -> per-warp offsets inside the tile
+    __shared__ uint32_t s_key[RS_TILE], s_val[RS_TILE];   // the tile, reordered by digit
+    __shared__ uint32_t s_tstart[RADIX_BINS];         // first slot of every digit inside the reordered tile
+    __shared__ uint32_t s_gbase[RADIX_BINS];          // global position of that first slot
     __shared__ uint32_t s_warp[RS_WARPS];
     __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -107,12 +110,15 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
     const uint32_t tile = s_tile;
 
     // warp-striped: warp w owns [wbase, wbase + 32*ITEMS); item i of lane l is wbase + 32*i + l
-    const size_t wbase = size_t(tile) * RS_TILE + size_t(warp) * (32 * RS_ITEMS);
-    uint32_t key[RS_ITEMS], rank[RS_ITEMS];
+    const size_t tbase = size_t(tile) * RS_TILE;
+    const size_t wbase = tbase + size_t(warp) * (32 * RS_ITEMS);
+    const uint32_t n_tile = (uint32_t)min(size_t(RS_TILE), n - tbase);
+    uint32_t key[RS_ITEMS], val[RS_ITEMS], rank[RS_ITEMS];
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const size_t e = wbase + size_t(i) * 32 + lane;
         key[i] = (e < n) ? __ldg(key_in + e) : 0xFFFFFFFFu;
+        val[i] = IOTA ? (uint32_t)e : ((e < n) ? __ldg(val_in + e) : 0u);
     }
     const uint32_t lt_mask = (1u << lane) - 1u;
 #pragma unroll
@@ -139,7 +145,7 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
         const uint32_t c = s_wh[w][bin];
-        s_wh[w][bin] = count;          // exclusive over warps (bin base added below)
+        s_wh[w][bin] = count;          // exclusive over warps (the digit's first slot is added below)
         count += c;
     }
     volatile uint32_t* mine = look + size_t(tile) * RADIX_BINS + bin;
@@ -167,19 +173,37 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
         }
         *mine = FLAG_PREFIX | (excl + count);
     }
-    const uint32_t base = bin_base_from_hist(hist, s_warp) + excl;    // (contains a __syncthreads)
+    const uint32_t gbin = scan256(hist[bin], s_warp);          // first global slot of this digit
+    const uint32_t tstart = scan256(count, s_warp);            // first slot of this digit inside the tile
+    s_tstart[bin] = tstart;
+    s_gbase[bin] = gbin + excl;
 #pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) s_wh[w][bin] += base;
+    for (int w = 0; w < RS_WARPS; ++w) s_wh[w][bin] += tstart;
     __syncthreads();
 
+    // reorder the tile by digit in shared memory ...
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const size_t e = wbase + size_t(i) * 32 + lane;
         if (e < n) {
             const uint32_t digit = (key[i] >> shift) & (RADIX_BINS - 1);
-            const uint32_t pos = s_wh[warp][digit] + rank[i];
-            key_out[pos] = key[i];
-            val_out[pos] = IOTA ? (uint32_t)e : __ldg(val_in + e);
+            const uint32_t slot = s_wh[warp][digit] + rank[i];
+            s_key[slot] = key[i];
+            s_val[slot] = val[i];
+        }
+    }
+    __syncthreads();
+    // ... so that consecutive threads store consecutive addresses inside every digit's run
+    // (a direct scatter costs one 32-byte L2 sector write per 4-byte element)
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const uint32_t slot = i * RS_THREADS + threadIdx.x;
+        if (slot < n_tile) {
+            const uint32_t k = s_key[slot];
+            const uint32_t digit = (k >> shift) & (RADIX_BINS - 1);
+            const uint32_t pos = s_gbase[digit] + (slot - s_tstart[digit]);
+            key_out[pos] = k;
+            val_out[pos] = s_val[slot];
         }
     }
 }
