@@ -189,22 +189,20 @@ def main():
                      d["dL_dsh"], d["dL_dscales"], d["dL_drotations"])
             return R, color, grads
 
-    # flat gradient bucket = what the mapper all-reduces (means3D 3, means2D 3, colors 3, opacity 1,
-    # scales 3, rotations 4 floats per Gaussian)
+    # flat gradient bucket = what the mapper all-reduces (segs_slam_b200/mapper.py: one contiguous FP32
+    # slice per tensor: means3D 3, means2D 3, colors 3, opacity 1, scales 3, rotations 4 floats per Gaussian)
+    from segs_slam_b200 import mapper
     GRAD_IDX = (3, 0, 1, 2, 6, 7)
     widths = (3, 3, 3, 1, 3, 4)
-    bucket = torch.zeros((P, sum(widths)), dtype=torch.float32, device=dev)
+    shapes = [torch.empty((P, w), dtype=torch.float32, device=dev) for w in widths]
+    gb = mapper.GradBucket(shapes)
+    bucket = gb.flat
 
     def accumulate(grads, first, into=None):
-        into = bucket if into is None else into
-        col = 0
-        for gi, w in zip(GRAD_IDX, widths):
-            g = grads[gi].view(P, w)
-            if first:
-                into[:, col:col + w].copy_(g)
-            else:
-                into[:, col:col + w].add_(g)
-            col += w
+        b = gb if into is None else into
+        if first:
+            b.zero_()
+        b.accumulate([grads[gi].view(P, w) for gi, w in zip(GRAD_IDX, widths)])
 
     R_seen = []
 
@@ -303,7 +301,7 @@ def main():
     s_in, s_out = torch.cuda.Stream(), torch.cuda.Stream()
     dev_params = [{k: torch.empty_like(base[k]) for k in PKEYS} for _ in range(2)]
     dev_dL = [torch.empty_like(dL) for _ in range(2)]
-    buckets = [bucket, torch.zeros_like(bucket)]
+    buckets = [gb, mapper.GradBucket(shapes)]
     Ev = torch.cuda.Event
     ev_par_ready, ev_par_free = [Ev(), Ev()], [Ev(), Ev()]
     ev_dL_ready, ev_dL_free = [Ev(), Ev()], [Ev(), Ev()]
@@ -355,12 +353,12 @@ def main():
                 ev_img_done[r].record(s_out)
         ev_par_free[p].record(cur)
         if distributed and args.impl == "ours":
-            dist.all_reduce(buckets[p])
+            dist.all_reduce(buckets[p].flat)
         done = Ev()
         done.record(cur)
         with torch.cuda.stream(s_out):
             s_out.wait_event(done)
-            host_grads[p].copy_(buckets[p], non_blocking=True)
+            host_grads[p].copy_(buckets[p].flat, non_blocking=True)
             ev_grads_done[p].record(s_out)
         ev_grads_done[p ^ 1].synchronize()            # the host owns the previous step's results
 

@@ -292,6 +292,9 @@ int segs_raster_backward(
     BinningState b = BinningState::carve(binning_buffer, R, 0, P, vp.grid_x, vp.grid_y, nullptr);
     ImageState img = ImageState::carve(image_buffer, N, T, nullptr);
     int rc;
+    // the 48-byte gradient accumulators start from zero (one bulk memset instead of strided clears
+    // in the per-Gaussian kernels; forward-only renders never pay for it)
+    SEGS_CUDA_CHECK(cudaMemsetAsync(g.acc, 0, size_t(P) * 3 * sizeof(float4), stream));
     if (R > 0) {
         prof_begin(4, stream);
         if ((rc = launch_blend_backward(vp, g, b, img, background, dL_dpix, stream))) return rc;

@@ -273,6 +273,7 @@ preprocess_kernel(int P, int D, int M,
     __shared__ float s_mean[3 * PRE_THREADS];
     __shared__ float s_scale[3 * PRE_THREADS];
     __shared__ float s_color[3 * PRE_THREADS];
+    __shared__ float4 s_rec[3 * PRE_THREADS];          // render records of the CTA, staged for coalesced stores
     __shared__ float s_view[16], s_proj[16];
 
     const size_t first = size_t(blockIdx.x) * PRE_THREADS;
@@ -342,7 +343,7 @@ preprocess_kernel(int P, int D, int M,
             }
         }
     }
-    if (!in_range) return;
+    if (MODE != Mode::Render && !in_range) return;
 
     if (MODE == Mode::Filter) {
         radii[idx] = visible ? pr.radius : 0;
@@ -373,41 +374,53 @@ preprocess_kernel(int P, int D, int M,
     }
 
     // ---- Mode::Render -------------------------------------------------------------
+    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
+    if (in_range) {
     if (radii != nullptr) radii[idx] = visible ? pr.radius : 0;
     tiles_touched[idx] = visible ? pr.tiles : 0u;
     if (!visible) {
         sort_key[idx] = 0xFFFFFFFFu;   // sorts behind every real depth (depth > 0.2 => sign bit 0)
         depths[idx] = 0.f;
         rect[idx] = make_ushort4(0, 0, 0, 0);
-        return;
-    }
-    depths[idx] = depth;
-    sort_key[idx] = __float_as_uint(depth);
-    rect[idx] = make_ushort4((unsigned short)pr.x0, (unsigned short)pr.y0,
-                             (unsigned short)pr.x1, (unsigned short)pr.y1);
+    } else {
+        depths[idx] = depth;
+        sort_key[idx] = __float_as_uint(depth);
+        rect[idx] = make_ushort4((unsigned short)pr.x0, (unsigned short)pr.y0,
+                                 (unsigned short)pr.x1, (unsigned short)pr.y1);
 
-    const float det_inv = __frcp_rn(pr.det);
-    const float conic_x = __fmul_rn(pr.cov_z, det_inv);
-    const float conic_y = __fmul_rn(det_inv, -pr.cov_y);
-    const float conic_z = __fmul_rn(pr.cov_x, det_inv);
-    const float opacity = __ldg(opacities + idx);
-    const float2 ext = cull_extent(opacity, pr.cov_x, pr.cov_z, pr.det);
-
-    rec[3 * idx + 0] = make_float4(pr.px, pr.py, ext.x, ext.y);
-    rec[3 * idx + 1] = make_float4(conic_x, conic_y, conic_z, opacity);
-    rec[3 * idx + 2] = make_float4(rgb.x, rgb.y, rgb.z, depth);
-    const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-    acc[3 * idx + 0] = z4;
-    acc[3 * idx + 1] = z4;
-    acc[3 * idx + 2] = z4;
-    if (cov3D_precomp == nullptr) {
+        const float det_inv = __frcp_rn(pr.det);
+        const float conic_x = __fmul_rn(pr.cov_z, det_inv);
+        const float conic_y = __fmul_rn(det_inv, -pr.cov_y);
+        const float conic_z = __fmul_rn(pr.cov_x, det_inv);
+        const float opacity = __ldg(opacities + idx);
+        const float2 ext = cull_extent(opacity, pr.cov_x, pr.cov_z, pr.det);
+        r0 = make_float4(pr.px, pr.py, ext.x, ext.y);
+        r1 = make_float4(conic_x, conic_y, conic_z, opacity);
+        r2 = make_float4(rgb.x, rgb.y, rgb.z, depth);
+        if (cov3D_precomp == nullptr) {
 #pragma unroll
-        for (int k = 0; k < 6; ++k) cov3D[size_t(k) * P + idx] = c3[k];
+            for (int k = 0; k < 6; ++k) cov3D[size_t(k) * P + idx] = c3[k];
+        }
+        if (colors_precomp == nullptr) {
+            clamped[3 * idx + 0] = cl[0];
+            clamped[3 * idx + 1] = cl[1];
+            clamped[3 * idx + 2] = cl[2];
+        }
     }
-    if (colors_precomp == nullptr) {
-        clamped[3 * idx + 0] = cl[0];
-        clamped[3 * idx + 1] = cl[1];
-        clamped[3 * idx + 2] = cl[2];
+    }
+    // The CTA's 48-byte records and gradient accumulators are one contiguous 12 KB run each:
+    // staged through shared memory and written with fully coalesced 16-byte stores (a per-thread
+    // 48-byte stride would touch every sector three times).  Records of culled Gaussians are
+    // zeros (never read).
+    s_rec[3 * t + 0] = r0;
+    s_rec[3 * t + 1] = r1;
+    s_rec[3 * t + 2] = r2;
+    __syncthreads();
+    (void)acc;   // the gradient accumulators are cleared by the backward (forward-only renders never touch them)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+        const int j = threadIdx.x + k * PRE_THREADS;
+        if (j < 3 * n) rec[3 * first + j] = s_rec[j];
     }
 }
 

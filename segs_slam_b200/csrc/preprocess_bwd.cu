@@ -10,8 +10,9 @@
 // runs the conic -> cov2D -> cov3D/mean -> scale/rotation chain in registers and writes
 // every output gradient exactly once (zeros for Gaussians that were not rendered), so the
 // caller can hand in uninitialised memory.  dL_dcov3D / dL_dmean3D never make the extra
-// HBM round trip they make between the reference's two kernels.  The accumulator is
-// re-zeroed on the way out so a second backward over the same forward state stays correct.
+// HBM round trip they make between the reference's two kernels.  (The accumulator is cleared
+// by segs_raster_backward before the blend pass, so repeated backwards over one forward state
+// stay correct.)
 //
 // Floating-point outputs only (tolerance 1e-4 relative), so expressions are written
 // plainly, in the reference's evaluation order.
@@ -230,10 +231,6 @@ preprocess_backward_kernel(int P, int D, int M,
     // by `vis` at the end.
     const bool vis = in_range && touched > 0;   // == radii[idx] > 0 of backward.cu:156,367
     {
-        if (vis) {
-            const float4 z4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            acc[3 * idx + 0] = z4; acc[3 * idx + 1] = z4; acc[3 * idx + 2] = z4;
-        }
         d_mean2D[0] = a0.x; d_mean2D[1] = a0.y;
         d_conic[0] = a0.z; d_conic[1] = a0.w; d_conic[2] = a1.x;
         d_opacity = a1.y;

@@ -9,17 +9,15 @@ from segs_slam_b200 import synth, rasterize_points as rp
 dev = torch.device("cuda:0")
 scene = synth.config(sys.argv[1] if len(sys.argv) > 1 else "C2"); t = scene.to_torch(dev); a = common.scene_args(t, scene, dev)
 P = scene.P
-bucket = torch.zeros((P, 17), device=dev)
+from segs_slam_b200 import mapper
+gb = mapper.GradBucket([torch.empty((P, w), device=dev) for w in (3, 3, 3, 1, 3, 4)])
 def view(first):
     st = rp.RasterizeGaussiansCUDA(a["bg"], a["means3D"], a["colors"], a["opacity"], a["scales"], a["rotations"], 1.0,
         a["cov3D_precomp"], a["viewmatrix"], a["projmatrix"], a["tan_fovx"], a["tan_fovy"], a["H"], a["W"], a["sh"], 0, a["campos"], False)
     g = rp.RasterizeGaussiansBackwardCUDA(a["bg"], a["means3D"], st[2], a["colors"], a["scales"], a["rotations"], 1.0,
         a["cov3D_precomp"], a["viewmatrix"], a["projmatrix"], a["tan_fovx"], a["tan_fovy"], t["dL_dout"], a["sh"], 0, a["campos"], st[3], st[0], st[4], st[5])
-    col = 0
-    for gi, w in zip((3, 0, 1, 2, 6, 7), (3, 3, 3, 1, 3, 4)):
-        if first: bucket[:, col:col + w].copy_(g[gi].view(P, w))
-        else: bucket[:, col:col + w].add_(g[gi].view(P, w))
-        col += w
+    if first: gb.zero_()
+    gb.accumulate([g[gi].view(P, w) for gi, w in zip((3, 0, 1, 2, 6, 7), (3, 3, 3, 1, 3, 4))])
 for i in range(30): view(i % 8 == 0)
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
