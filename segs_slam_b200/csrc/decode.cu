@@ -884,28 +884,43 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
 constexpr int WG_THREADS = 256;
 constexpr int WG_STRIDE = FT + 4;      // floats per factor row in shared memory (conflict-free LDS.128)
 
-struct WJob {            // one outer-product sum: rows U = factor rows [u0, u0+np), lanes V = factor rows [v0, v0+32)
-    int u0, np, v0;      // v0 < 0: V == 1 (bias sums), lanes index the U rows instead
-    float* out;          // out[p * ld + q]
-    int ld, nq;          // columns actually stored
+struct WJob {            // one outer-product sum over the anchors k:
+    int u0, np, v0;      //   out[p][q] += U[k][u0 + p] * V[k][v0 + q]   (p < np rows, q < nq lanes)
+    float* out;          //   v0 < 0: V == 1 (bias sums): lanes index the U rows, out[p*32 + lane]
+    int ld, nq;          //   tr != 0: transposed store, out[q * ld + p]
+    int tr, warp;        //   warp that owns the job (its rows share the V operand, cached in registers)
 };
-constexpr int MAX_JOBS = 20;
+constexpr int MAX_JOBS = 24;
 struct WJobs { WJob j[MAX_JOBS]; int n; };
+constexpr int WG_ROWS_MAX = 36;        // rows (accumulators) per warp
 
-// Every warp walks the flattened list of (job, p) rows with stride 8; a thread keeps one
-// accumulator per row it owns.
-constexpr int WG_ROWS_MAX = 44;
-
-__global__ void __launch_bounds__(WG_THREADS)
+__global__ void __launch_bounds__(WG_THREADS, 2)
 decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs, const int nrows_used)
 {
     extern __shared__ __align__(16) float s_f[];          // [FACT_ROWS][WG_STRIDE]
+    __shared__ short s_job[WG_THREADS / 32][WG_ROWS_MAX], s_p[WG_THREADS / 32][WG_ROWS_MAX];
+    __shared__ short s_u[WG_THREADS / 32][WG_ROWS_MAX], s_v[WG_THREADS / 32][WG_ROWS_MAX];
+    __shared__ int s_nrows[WG_THREADS / 32];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int ntiles = (n_vis + FT - 1) / FT;
 
-    // rows owned by this warp: global row index g = warp + 8 * i
-    int total_rows = 0;
-    for (int j = 0; j < jobs.n; ++j) total_rows += jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
+    // row table of this warp: its jobs in list order, one entry per accumulator
+    if (lane == 0) {
+        int r = 0;
+        for (int j = 0; j < jobs.n; ++j) {
+            if (jobs.j[j].warp != warp) continue;
+            const int rows = jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
+            for (int pp = 0; pp < rows && r < WG_ROWS_MAX; ++pp, ++r) {
+                s_job[warp][r] = (short)j;
+                s_p[warp][r] = (short)pp;
+                s_u[warp][r] = (short)(jobs.j[j].v0 >= 0 ? jobs.j[j].u0 + pp : jobs.j[j].u0 + min(pp * 32 + lane, jobs.j[j].np - 1));
+                s_v[warp][r] = (short)(jobs.j[j].v0 >= 0 ? jobs.j[j].v0 : -1 - j);     // distinct negative tag per bias job
+            }
+        }
+        s_nrows[warp] = r;
+    }
+    __syncthreads();
+    const int nrows = s_nrows[warp];
     float acc[WG_ROWS_MAX];
 #pragma unroll
     for (int i = 0; i < WG_ROWS_MAX; ++i) acc[i] = 0.f;
@@ -931,57 +946,53 @@ decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs,
             }
             __syncthreads();
         }
+        int cur_v = -1000;
+        float4 V[FT / 4];
 #pragma unroll
         for (int i = 0; i < WG_ROWS_MAX; ++i) {
-            const int g = warp + 8 * i;
-            if (g >= total_rows) break;
-            // locate (job, p) of flattened row g   (warp-uniform)
-            int j = 0, base = 0;
-            for (;; ++j) {
-                const int n = jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
-                if (g < base + n) break;
-                base += n;
-            }
-            const WJob& job = jobs.j[j];
-            const int pidx = g - base;
-            float a = acc[i];
-            if (job.v0 >= 0) {
-                const float4* u = reinterpret_cast<const float4*>(s_f + (job.u0 + pidx) * WG_STRIDE);
-                const float4* v = reinterpret_cast<const float4*>(s_f + (job.v0 + (lane < job.nq ? lane : 0)) * WG_STRIDE);
+            if (i >= nrows) break;
+            const int vtag = s_v[warp][i];            // warp-uniform
+            if (vtag >= 0) {
+                if (vtag != cur_v) {                   // new V operand: this lane's column, all 64 anchors, into registers
+                    const int nq = jobs.j[s_job[warp][i]].nq;
+                    const float4* v = reinterpret_cast<const float4*>(s_f + (vtag + (lane < nq ? lane : 0)) * WG_STRIDE);
+#pragma unroll
+                    for (int k4 = 0; k4 < FT / 4; ++k4) V[k4] = v[k4];
+                    cur_v = vtag;
+                }
+                const float4* u = reinterpret_cast<const float4*>(s_f + s_u[warp][i] * WG_STRIDE);   // broadcast
+                float a = acc[i];
 #pragma unroll
                 for (int k4 = 0; k4 < FT / 4; ++k4) {
-                    const float4 uu = u[k4], vv = v[k4];
-                    a = fmaf(uu.x, vv.x, a); a = fmaf(uu.y, vv.y, a); a = fmaf(uu.z, vv.z, a); a = fmaf(uu.w, vv.w, a);
+                    const float4 uu = u[k4];
+                    a = fmaf(uu.x, V[k4].x, a); a = fmaf(uu.y, V[k4].y, a); a = fmaf(uu.z, V[k4].z, a); a = fmaf(uu.w, V[k4].w, a);
                 }
+                acc[i] = a;
             } else {
-                const int r = pidx * 32 + lane;
+                // bias sums: lane <-> U row
+                const WJob& job = jobs.j[s_job[warp][i]];
+                const int r = s_p[warp][i] * 32 + lane;
                 if (r < job.np) {
                     const float4* u = reinterpret_cast<const float4*>(s_f + (job.u0 + r) * WG_STRIDE);
+                    float a = acc[i];
 #pragma unroll
                     for (int k4 = 0; k4 < FT / 4; ++k4) {
                         const float4 uu = u[k4];
                         a += uu.x + uu.y + uu.z + uu.w;
                     }
+                    acc[i] = a;
                 }
             }
-            acc[i] = a;
         }
     }
-    // flush
+    // flush: one atomic per accumulator
 #pragma unroll
     for (int i = 0; i < WG_ROWS_MAX; ++i) {
-        const int g = warp + 8 * i;
-        if (g >= total_rows) break;
-        int j = 0, base = 0;
-        for (;; ++j) {
-            const int n = jobs.j[j].v0 >= 0 ? jobs.j[j].np : (jobs.j[j].np + 31) / 32;
-            if (g < base + n) break;
-            base += n;
-        }
-        const WJob& job = jobs.j[j];
-        const int pidx = g - base;
+        if (i >= nrows) break;
+        const WJob& job = jobs.j[s_job[warp][i]];
+        const int pidx = s_p[warp][i];
         if (job.v0 >= 0) {
-            if (lane < job.nq) atomicAdd(job.out + pidx * job.ld + lane, acc[i]);
+            if (lane < job.nq) atomicAdd(job.tr ? job.out + lane * job.ld + pidx : job.out + pidx * job.ld + lane, acc[i]);
         } else {
             const int r = pidx * 32 + lane;
             if (r < job.np) atomicAdd(job.out + r, acc[i]);
@@ -1155,31 +1166,34 @@ extern "C" int segs_decode_backward(
 
     WJobs jobs;
     int n = 0;
-    auto add = [&](int u0, int np, int v0, float* out, int ld, int nq) { jobs.j[n++] = WJob{u0, np, v0, out, ld, nq}; };
-    // second layers: dW2[n][j] = sum d2[n] h[j]
-    add(F_D2O, NOFF, F_H + 0 * FEAT, dp->opacity_w2, FEAT, FEAT);
-    add(F_D2S, 7 * NOFF, F_H + 1 * FEAT, dp->cov_w2, FEAT, FEAT);
-    add(F_D2C, 3 * NOFF, F_H + 2 * FEAT, dp->color_w2, FEAT, FEAT);
-    // first layers, stored transposed by the job shape: rows p = hidden unit j ... we need dW1[j][i] = sum dpre[j] x[i]:
-    // U = dpre (32 rows), V = x (lanes i < in) handled in two lane groups (i < 32, then i = 32..35)
-    add(F_DPRE + 0 * FEAT, FEAT, F_X, dp->opacity_w1, in_o, 32);
-    add(F_DPRE + 1 * FEAT, FEAT, F_X, dp->cov_w1, in_s, 32);
-    add(F_DPRE + 2 * FEAT, FEAT, F_X, dp->color_w1, ld_c, 32);
-    add(F_DPRE + 0 * FEAT, FEAT, F_X + 32, dp->opacity_w1 + 32, in_o, in_o - 32);
-    add(F_DPRE + 1 * FEAT, FEAT, F_X + 32, dp->cov_w1 + 32, in_s, in_s - 32);
-    add(F_DPRE + 2 * FEAT, FEAT, F_X + 32, dp->color_w1 + 32, ld_c, in_c - 32);
+    auto add = [&](int warp, int u0, int np, int v0, float* out, int ld, int nq, int tr = 0) {
+        jobs.j[n++] = WJob{u0, np, v0, out, ld, nq, tr, warp};
+    };
+    // second layers: dW2[n][j] = sum d2[n] h[j]   (lanes = hidden unit j)
+    add(0, F_D2S, 35, F_H + 1 * FEAT, dp->cov_w2, FEAT, FEAT);
+    add(1, F_D2S + 35, 35, F_H + 1 * FEAT, dp->cov_w2 + 35 * FEAT, FEAT, FEAT);
+    add(2, F_D2C, 3 * NOFF, F_H + 2 * FEAT, dp->color_w2, FEAT, FEAT);
+    add(7, F_D2O, NOFF, F_H + 0 * FEAT, dp->opacity_w2, FEAT, FEAT);
+    // first layers: dW1[j][i] = sum dpre[j] x[i]   (rows = hidden unit j, lanes = input column i < 32)
+    add(3, F_DPRE + 0 * FEAT, FEAT, F_X, dp->opacity_w1, in_o, 32);
+    add(4, F_DPRE + 1 * FEAT, FEAT, F_X, dp->cov_w1, in_s, 32);
+    add(5, F_DPRE + 2 * FEAT, FEAT, F_X, dp->color_w1, ld_c, 32);
+    // ... input columns 32.. : rows = input column, lanes = hidden unit, transposed store
+    add(6, F_X + 32, in_o - 32, F_DPRE + 0 * FEAT, dp->opacity_w1 + 32, in_o, FEAT, 1);
+    add(6, F_X + 32, in_s - 32, F_DPRE + 1 * FEAT, dp->cov_w1 + 32, in_s, FEAT, 1);
+    add(6, F_X + 32, in_c - 32, F_DPRE + 2 * FEAT, dp->color_w1 + 32, ld_c, FEAT, 1);
     // biases
-    add(F_D2O, NOFF, -1, dp->opacity_b2, 0, 0);
-    add(F_D2S, 7 * NOFF, -1, dp->cov_b2, 0, 0);
-    add(F_D2C, 3 * NOFF, -1, dp->color_b2, 0, 0);
-    add(F_DPRE + 0 * FEAT, FEAT, -1, dp->opacity_b1, 0, 0);
-    add(F_DPRE + 1 * FEAT, FEAT, -1, dp->cov_b1, 0, 0);
-    add(F_DPRE + 2 * FEAT, FEAT, -1, dp->color_b1, 0, 0);
+    add(6, F_D2O, NOFF, -1, dp->opacity_b2, 0, 0);
+    add(6, F_D2S, 7 * NOFF, -1, dp->cov_b2, 0, 0);
+    add(6, F_D2C, 3 * NOFF, -1, dp->color_b2, 0, 0);
+    add(7, F_DPRE + 0 * FEAT, FEAT, -1, dp->opacity_b1, 0, 0);
+    add(7, F_DPRE + 1 * FEAT, FEAT, -1, dp->cov_b1, 0, 0);
+    add(7, F_DPRE + 2 * FEAT, FEAT, -1, dp->color_b1, 0, 0);
     if (p.use_feat_bank) {
-        add(F_DLOG, 3, F_HB, dp->bank_w2, FEAT, FEAT);          // dW2b[m][j] = sum dlog[m] hb[j]
-        add(F_DPREB, FEAT, F_CAT, dp->bank_w1, 4, 4);           // dW1b[j][i] = sum dpreb[j] cat[i]
-        add(F_DLOG, 3, -1, dp->bank_b2, 0, 0);
-        add(F_DPREB, FEAT, -1, dp->bank_b1, 0, 0);
+        add(7, F_DLOG, 3, F_HB, dp->bank_w2, FEAT, FEAT);                 // dW2b[m][j] = sum dlog[m] hb[j]
+        add(7, F_CAT, 4, F_DPREB, dp->bank_w1, 4, FEAT, 1);               // dW1b[j][i] = sum dpreb[j] cat[i]
+        add(7, F_DLOG, 3, -1, dp->bank_b2, 0, 0);
+        add(7, F_DPREB, FEAT, -1, dp->bank_b1, 0, 0);
     }
     jobs.n = n;
     const int nrows_used = p.use_feat_bank ? FACT_ROWS : F_HB;     // the bank rows are only written in bank mode
