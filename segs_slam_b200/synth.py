@@ -104,20 +104,28 @@ def config(name: str, **kw) -> Scene:
     return synth(P, W, H, fx, fy, seed, **kw)
 
 
-def with_camera(scene: Scene, R: np.ndarray, t: np.ndarray) -> Scene:
-    """Same Gaussians seen from a world->camera pose (R,t): view = [[R,t],[0,1]]."""
+def camera_matrices(R: np.ndarray, t: np.ndarray, tanfovx: float, tanfovy: float):
+    """(world_view_transform_, full_proj_transform_, camera_center_) of a world->camera pose (R, t) in
+    the memory order the kernels read (m[4*col+row]), as GaussianKeyframe::computeTransformTensors
+    builds them (gaussian_keyframe.cpp:151-184); znear 0.01, zfar 100."""
     f32 = np.float32
     Rt = np.eye(4, dtype=f32)
     Rt[:3, :3] = R
     Rt[:3, 3] = t
-    fovx = 2.0 * math.atan(scene.tanfovx)
-    fovy = 2.0 * math.atan(scene.tanfovy)
+    fovx = 2.0 * math.atan(tanfovx)
+    fovy = 2.0 * math.atan(tanfovy)
     proj = projection_matrix(0.01, 100.0, fovx, fovy)
     wvt = Rt.T.copy()                       # world_view_transform_ (memory m[4*col+row])
     full = (wvt @ proj.T).astype(f32)
-    campos = (-R.T @ t).astype(f32)
+    campos = (-np.asarray(R, dtype=f32).T @ np.asarray(t, dtype=f32)).astype(f32)
+    return wvt.astype(f32), full, campos
+
+
+def with_camera(scene: Scene, R: np.ndarray, t: np.ndarray) -> Scene:
+    """Same Gaussians seen from a world->camera pose (R,t): view = [[R,t],[0,1]]."""
+    wvt, full, campos = camera_matrices(R, t, scene.tanfovx, scene.tanfovy)
     import dataclasses
-    return dataclasses.replace(scene, viewmatrix=wvt.astype(f32), projmatrix=full, campos=campos)
+    return dataclasses.replace(scene, viewmatrix=wvt, projmatrix=full, campos=campos)
 
 
 def sh_variant(scene: Scene, degree: int, seed: int = 5) -> Scene:
