@@ -54,6 +54,12 @@ __device__ __forceinline__ float gauss_power(float dx, float dy, float cx, float
     return __fmaf_rn(a, -0.5f, -__fmul_rn(dy, __fmul_rn(dx, cy)));
 }
 
+__device__ __forceinline__ float rcp_approx(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
 // conservative sub-tile test; written so that NaNs never cull
 __device__ __forceinline__ bool extent_hits(float4 g0, float wx0, float wx1, float wy0, float wy1) {
     return !(g0.x + g0.z < wx0 || g0.x - g0.z > wx1 || g0.y + g0.w < wy0 || g0.y - g0.w > wy1);
@@ -345,7 +351,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                     const float G = act ? G_raw : 0.f;
                     const float alpha = act ? alpha_raw : 0.f;
                     const float4 g2 = s_rec[buf][2][slot];
-                    const float rcp_oma = __fdividef(1.f, 1.f - alpha);      // 1 - alpha in [0.01, 1]
+                    const float rcp_oma = rcp_approx(1.f - alpha);           // 1 - alpha in [0.01, 1]: one MUFU.RCP
                     T = T * rcp_oma;                                         // T / (1 - alpha)
                     const float dchannel_dcolor = alpha * T;
                     const float na0 = last_alpha * lastc0 + (1.f - last_alpha) * accum0;
