@@ -262,6 +262,55 @@ int segs_decode_backward(
     segs_alloc_fn scratch_alloc, void* scratch_user,
     void* stream);
 
+/* ---- mapper loss and optimizer ---------------------------------------
+ *   segs_loss_l1_ssim_*   loss_utils::l1_loss / ssim / _ssim           include/loss_utils.h:29-32, 50-127,
+ *                         as combined at                                src/gaussian_mapper.cpp:917-925
+ *   segs_scaling_reg      0.01 * scaling.prod(1).mean()                 src/gaussian_mapper.cpp:922-925
+ *   segs_adam_step        torch::optim::Adam::step over the groups of   src/gaussian_model.cpp:620-872,
+ *                         GaussianModel::trainingSetup                  stepped at src/gaussian_mapper.cpp:1003-1006
+ *   segs_accumulate       gradient accumulation over the keyframe batch (new construct)     */
+
+/* Bytes of caller-owned state the loss forward fills and the backward reads (three derivative maps of
+ * the SSIM index, the per-CTA partial sums). */
+size_t segs_loss_state_bytes(int C, int H, int W);
+
+/* loss = w_l1 * mean|x - y| + w_ssim * mean(SSIM_11x11,sigma1.5(x, y)) + bias over image, gt [C,H,W]
+ * (both multiplied by row_mask [C,H] when it is not NULL — the `mask_rgb` of gaussian_mapper.cpp:911-915).
+ * The mapper's loss is (w_l1, w_ssim, bias) = (1 - lambda_dssim, -lambda_dssim, lambda_dssim).
+ * loss_out (DEVICE, 3 floats) = { mean|x-y|, mean SSIM, loss }.  Deterministic (fixed-order sums). */
+int segs_loss_l1_ssim_forward(
+    int C, int H, int W, const float* image, const float* gt, const float* row_mask,
+    float w_l1, float w_ssim, float bias, float* loss_out, char* state, void* stream);
+
+/* dL_dimage [C,H,W] = dL_dloss * d loss / d image.  dL_dloss: DEVICE scalar, NULL = 1. */
+int segs_loss_l1_ssim_backward(
+    int C, int H, int W, const float* image, const float* gt, const float* row_mask,
+    float w_l1, float w_ssim, const float* dL_dloss, char* state, float* dL_dimage, void* stream);
+
+/* reg = weight * mean_i(s_i0 * s_i1 * s_i2) over scaling [n,3].  reg_out (DEVICE scalar, may be NULL) is
+ * ADDED to; dL_dscaling [n,3] (may be NULL) is ADDED to with dL_dloss (DEVICE scalar, NULL = 1) * d reg. */
+int segs_scaling_reg(int n, const float* scaling, float weight, const float* dL_dloss, float* dL_dscaling,
+                     float* reg_out, void* stream);
+
+/* One tensor (= one parameter group of the reference's optimizer) of a fused Adam step.  `offset`/`count`
+ * locate its gradient and moments in the flat arrays; consecutive tensors must tile them contiguously. */
+typedef struct segs_adam_tensor {
+    float* param;                  /* DEVICE, count floats, updated in place */
+    unsigned long long offset;     /* first element in grad_flat / exp_avg_flat / exp_avg_sq_flat */
+    unsigned long long count;
+    float lr, beta1, beta2, eps, weight_decay;
+    long long step;                /* 1-based step number used for the bias corrections */
+} segs_adam_tensor;
+
+/* tensors: HOST array.  g = grad_flat * grad_scale; Adam (amsgrad off) as LibTorch 2.0.1;
+ * zero_grad != 0 clears grad_flat behind the read (ready for the next batch). */
+int segs_adam_step(int n_tensors, const segs_adam_tensor* tensors, float* grad_flat, float* exp_avg_flat,
+                   float* exp_avg_sq_flat, float grad_scale, int zero_grad, void* stream);
+
+/* dst[k][i] += src[k][i], i < counts[k], for all k in one launch (HOST arrays of DEVICE pointers). */
+int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, const unsigned long long* counts,
+                    void* stream);
+
 /* ---- per-stage device timing (bench.py roofline) -------------------------------------- */
 /* When enabled (per host thread), segs_raster_forward / segs_raster_backward bracket their
  * stages with CUDA events on the caller's stream.  segs_profile_read synchronises those

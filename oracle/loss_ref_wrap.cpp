@@ -1,0 +1,76 @@
+// TEST INFRASTRUCTURE — C veneer over the reference's OWN loss code, compiled where it lies.
+//
+// `#include "loss_utils.h"` resolves to /root/reference/include/loss_utils.h (header-only LibTorch
+// code; -I$(REF)/include in oracle/Makefile) — nothing of it is copied into this repo.  The veneer
+// restates only the CALL SITE (src/gaussian_mapper.cpp:908-925: mask_rgb, Ll1, ssim, the weighted
+// sum, scaling_reg, loss.backward()) and runs it on the CPU (device_type = torch::kCPU), which makes
+// golden vectors for the fused CUDA loss (segs_slam_b200/csrc/loss.cu) without a GPU
+// (tests/golden/make_loss_golden.py).  ref_adam drives torch::optim::Adam — the optimizer class the
+// reference instantiates (src/gaussian_model.cpp:620-872) — for the fused Adam kernel's goldens.
+#include <torch/torch.h>
+#include <vector>
+#include "loss_utils.h"
+
+extern "C" {
+
+// out3 = { Ll1, ssim, loss }; dL_dimage [C,H,W]; scaling [n,3] optional with dL_dscaling [n,3]
+int ref_mapper_loss(int C, int H, int W, const float* image, const float* gt, float lambda_dssim, int apply_mask,
+                    int n_scaling, const float* scaling, float* out3, float* dL_dimage, float* dL_dscaling)
+{
+    auto opts = torch::TensorOptions().dtype(torch::kFloat32);
+    torch::Tensor rendered_image = torch::from_blob(const_cast<float*>(image), {C, H, W}, opts).clone().requires_grad_(true);
+    torch::Tensor gt_image = torch::from_blob(const_cast<float*>(gt), {C, H, W}, opts).clone();
+    torch::Tensor leaf = rendered_image;
+    torch::Tensor masked_image = rendered_image;
+    if (apply_mask) {
+        // gaussian_mapper.cpp:911-915
+        torch::Tensor mask_rgb = (gt_image != 0.0f).any(-1);
+        mask_rgb = mask_rgb.to(torch::kFloat32).unsqueeze(-1);
+        masked_image = masked_image * mask_rgb;
+        rendered_image = rendered_image * mask_rgb;
+        gt_image = gt_image * mask_rgb;
+    }
+    auto Ll1 = loss_utils::l1_loss(rendered_image, gt_image);                       // :917
+    auto ss = loss_utils::ssim(masked_image, gt_image, torch::kCPU);
+    auto loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ss);             // :920-921
+    torch::Tensor sc;
+    if (n_scaling > 0) {
+        sc = torch::from_blob(const_cast<float*>(scaling), {n_scaling, 3}, opts).clone().requires_grad_(true);
+        auto scaling_reg = sc.prod(1).mean();                                       // :919
+        loss = loss + 0.01 * scaling_reg;
+    }
+    loss.backward();
+    out3[0] = Ll1.item<float>();
+    out3[1] = ss.item<float>();
+    out3[2] = loss.item<float>();
+    std::memcpy(dL_dimage, leaf.grad().contiguous().data_ptr<float>(), sizeof(float) * C * H * W);
+    if (n_scaling > 0 && dL_dscaling)
+        std::memcpy(dL_dscaling, sc.grad().contiguous().data_ptr<float>(), sizeof(float) * n_scaling * 3);
+    return 0;
+}
+
+float ref_psnr(int C, int H, int W, const float* a, const float* b)
+{
+    auto opts = torch::TensorOptions().dtype(torch::kFloat32);
+    torch::Tensor x = torch::from_blob(const_cast<float*>(a), {C, H, W}, opts).clone();
+    torch::Tensor y = torch::from_blob(const_cast<float*>(b), {C, H, W}, opts).clone();
+    return loss_utils::psnr(x, y).item<float>();
+}
+
+// `steps` Adam steps on one tensor of n floats; grads [steps, n]; param updated in place
+int ref_adam(int n, float* param, const float* grads, int steps, double lr, double beta1, double beta2, double eps,
+             double weight_decay)
+{
+    auto opts = torch::TensorOptions().dtype(torch::kFloat32);
+    torch::Tensor p = torch::from_blob(param, {n}, opts).clone().requires_grad_(true);
+    torch::optim::Adam opt(std::vector<torch::Tensor>{p},
+                           torch::optim::AdamOptions(lr).betas(std::make_tuple(beta1, beta2)).eps(eps).weight_decay(weight_decay));
+    for (int s = 0; s < steps; ++s) {
+        p.mutable_grad() = torch::from_blob(const_cast<float*>(grads) + size_t(s) * n, {n}, opts).clone();
+        opt.step();
+    }
+    std::memcpy(param, p.detach().contiguous().data_ptr<float>(), sizeof(float) * n);
+    return 0;
+}
+
+}  // extern "C"

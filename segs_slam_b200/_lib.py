@@ -34,6 +34,13 @@ class DecodeGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _PARAM_NAMES]
 
 
+class AdamTensor(C.Structure):
+    """segs_adam_tensor (include/segs_raster.h)."""
+    _fields_ = [("param", C.c_void_p), ("offset", C.c_ulonglong), ("count", C.c_ulonglong), ("lr", C.c_float),
+                ("beta1", C.c_float), ("beta2", C.c_float), ("eps", C.c_float), ("weight_decay", C.c_float),
+                ("step", C.c_longlong)]
+
+
 _PROTOTYPES = {
     "segs_version": (C.c_int, []),
     "segs_last_error": (C.c_char_p, []),
@@ -80,6 +87,24 @@ _PROTOTYPES = {
         [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),
          C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
          _f32p, _f32p, _f32p, _f32p, C.POINTER(DecodeGrads), ALLOC_FN, C.c_void_p, C.c_void_p],
+    ),
+    "segs_loss_state_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
+    "segs_loss_l1_ssim_forward": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, _f32p, C.c_void_p, C.c_void_p],
+    ),
+    "segs_loss_l1_ssim_backward": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, C.c_float, C.c_float, _f32p, C.c_void_p, _f32p, C.c_void_p],
+    ),
+    "segs_scaling_reg": (C.c_int, [C.c_int, _f32p, C.c_float, _f32p, _f32p, _f32p, C.c_void_p]),
+    "segs_adam_step": (
+        C.c_int,
+        [C.c_int, C.POINTER(AdamTensor), _f32p, _f32p, _f32p, C.c_float, C.c_int, C.c_void_p],
+    ),
+    "segs_accumulate": (
+        C.c_int,
+        [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong), C.c_void_p],
     ),
     "segs_launch_count": (C.c_ulonglong, []),
     "segs_profile_enable": (C.c_int, [C.c_int]),

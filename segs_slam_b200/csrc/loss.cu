@@ -1,0 +1,340 @@
+// Fused photometric loss of the mapper for sm_100a:
+//     loss = w_l1 * mean|x - y| + w_ssim * mean(SSIM(x, y)) + bias
+// with the forward pass producing the three per-pixel derivative maps of the SSIM index and the
+// backward pass turning them into dL/dx — the `dL_dout_color` the rasterizer backward consumes —
+// in ONE kernel each.
+//
+// Replaces loss_utils::l1_loss / loss_utils::ssim / loss_utils::_ssim
+// (/root/reference/include/loss_utils.h:29-32, 50-127) as they are combined by the mapper
+// (/root/reference/src/gaussian_mapper.cpp:917-925:
+//   loss = (1 - lambda) * l1(rendered * mask, gt * mask) + lambda * (1 - ssim(rendered * mask, gt))
+//  i.e. w_l1 = 1 - lambda, w_ssim = -lambda, bias = lambda).
+// The reference runs 5 grouped 11x11 conv2d (121 taps each) + ~25 elementwise ATen kernels forward
+// and the same again backward, with ~12 image-sized temporaries; here the 11x11 Gaussian window
+// (sigma 1.5, zero padding 5: loss_utils.h:50-75, 85-87) is applied separably out of shared
+// memory and the only temporaries are the three derivative maps.
+//
+// SSIM algebra (per pixel, per channel; mu = G*x etc., G = the window):
+//   a = 2 mu1 mu2 + C1, b = 2 s12 + C2, c = mu1^2 + mu2^2 + C1, d = s1 + s2 + C2   (s1 = G*x^2 - mu1^2 ...)
+//   ssim = a b / (c d)
+//   d ssim / d mu1     = 2 mu2 (b - a)/(c d) - 2 mu1 ssim (d - c)/(c d)      (holding G*x^2, G*xy fixed)
+//   d ssim / d (G*x^2) = -ssim / d
+//   d ssim / d (G*xy)  = 2 a / (c d)
+//   dL/dx = G*(g m1) + 2 x G*(g m2) + y G*(g m3),   g = w_ssim / (C H W)
+// Both kernels are HBM-streaming: forward reads 2 and writes 3 floats per pixel-channel, backward
+// reads 5 and writes 1.
+#include "common.cuh"
+
+namespace segs {
+
+namespace {
+
+constexpr int LT = 16;                 // tile side
+constexpr int HALO = 5;                // window 11
+constexpr int LW = LT + 2 * HALO;      // 26
+constexpr int WIN = 11;
+constexpr int LS = 48;                 // shared row stride: the two 16-wide half-warps of the horizontal pass hit disjoint banks
+
+struct Window { float w[WIN]; };
+
+// loss_utils::gaussian (loss_utils.h:50-65): exp(-(x-5)^2 / (2 sigma^2)), normalised, sigma = 1.5
+Window make_window() {
+    Window g;
+    float v[WIN];
+    float sum = 0.f;
+    for (int x = 0; x < WIN; ++x) {
+        const int t = x - WIN / 2;
+        v[x] = expf(float(-t * t) / (2.0f * 1.5f * 1.5f));
+        sum += v[x];
+    }
+    for (int x = 0; x < WIN; ++x) g.w[x] = v[x] / sum;
+    return g;
+}
+
+struct LossState {
+    float* m1;        // [C*H*W] d ssim / d mu1
+    float* m2;        // [C*H*W] d ssim / d (G*x^2)
+    float* m3;        // [C*H*W] d ssim / d (G*xy)
+    double* partial;  // [2 * blocks]
+    uint32_t* ticket; // [1]
+    static LossState carve(char* base, size_t n, size_t blocks, size_t* bytes) {
+        Carver c(base);
+        LossState s;
+        s.m1 = c.take<float>(n);
+        s.m2 = c.take<float>(n);
+        s.m3 = c.take<float>(n);
+        s.partial = c.take<double>(2 * blocks);
+        s.ticket = c.take<uint32_t>(1);
+        if (bytes) *bytes = c.used(base) + 128;
+        return s;
+    }
+};
+
+__device__ __forceinline__ float masked_load(const float* __restrict__ img, const float* __restrict__ row_mask,
+                                             int ch, int y, int x, int H, int W) {
+    if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
+    float v = __ldg(img + (size_t(ch) * H + y) * W + x);
+    if (row_mask) v *= __ldg(row_mask + ch * H + y);
+    return v;
+}
+
+__global__ void __launch_bounds__(LT * LT)
+ssim_l1_forward_kernel(int C, int H, int W, const float* __restrict__ image, const float* __restrict__ gt,
+                       const float* __restrict__ row_mask, const Window win, float w_l1, float w_ssim, float bias,
+                       LossState st, float* __restrict__ loss_out)
+{
+    __shared__ float sx[LW][LS];
+    __shared__ float sy[LW][LS];
+    __shared__ float hb[5][LW][LT];
+    __shared__ double s_red[2][LT * LT / 32];
+    __shared__ bool s_last;
+
+    const int tid = threadIdx.x;
+    const int tx = tid & (LT - 1), ty = tid >> 4;
+    const int ch = blockIdx.z;
+    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+
+    for (int i = tid; i < LW * LW; i += LT * LT) {
+        const int r = i / LW, c = i - r * LW;
+        sx[r][c] = masked_load(image, row_mask, ch, y0 + r - HALO, x0 + c - HALO, H, W);
+        // gaussian_mapper.cpp:915: gt * mask == gt (masked rows of gt are all-zero by construction), but the
+        // product is applied anyway so arbitrary masks behave like the reference
+        sy[r][c] = masked_load(gt, row_mask, ch, y0 + r - HALO, x0 + c - HALO, H, W);
+    }
+    __syncthreads();
+    // horizontal pass: 26 rows x 16 columns x 5 quantities
+    for (int i = tid; i < LW * LT; i += LT * LT) {
+        const int r = i >> 4, c = i & (LT - 1);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) {
+            const float x = sx[r][c + k], y = sy[r][c + k], w = win.w[k];
+            a0 = fmaf(w, x, a0);
+            a1 = fmaf(w, y, a1);
+            a2 = fmaf(w, x * x, a2);
+            a3 = fmaf(w, y * y, a3);
+            a4 = fmaf(w, x * y, a4);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2; hb[3][r][c] = a3; hb[4][r][c] = a4;
+    }
+    __syncthreads();
+    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+#pragma unroll
+    for (int k = 0; k < WIN; ++k) {
+        const float w = win.w[k];
+        mu1 = fmaf(w, hb[0][ty + k][tx], mu1);
+        mu2 = fmaf(w, hb[1][ty + k][tx], mu2);
+        e11 = fmaf(w, hb[2][ty + k][tx], e11);
+        e22 = fmaf(w, hb[3][ty + k][tx], e22);
+        e12 = fmaf(w, hb[4][ty + k][tx], e12);
+    }
+    const int px = x0 + tx, py = y0 + ty;
+    const bool inside = px < W && py < H;
+    double l1 = 0.0, ss = 0.0;
+    if (inside) {
+        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;          // loss_utils.h:101-102
+        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+        const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+        const float a = 2.f * mu12 + C1, b = 2.f * s12 + C2;
+        const float c = mu1_sq + mu2_sq + C1, d = s1 + s2 + C2;
+        const float rcd = 1.f / (c * d);
+        const float ssim = a * b * rcd;                              // loss_utils.h:104
+        const size_t o = (size_t(ch) * H + py) * W + px;
+        st.m1[o] = 2.f * mu2 * (b - a) * rcd - 2.f * mu1 * ssim * (d - c) * rcd;
+        st.m2[o] = -ssim / d;
+        st.m3[o] = 2.f * a * rcd;
+        l1 = (double)fabsf(sx[ty + HALO][tx + HALO] - sy[ty + HALO][tx + HALO]);
+        ss = (double)ssim;
+    }
+    // deterministic reduction: lanes -> warps -> CTA partial -> (last CTA) fixed-order total
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        l1 += __shfl_xor_sync(0xFFFFFFFFu, l1, o);
+        ss += __shfl_xor_sync(0xFFFFFFFFu, ss, o);
+    }
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = l1; s_red[1][tid >> 5] = ss; }
+    __syncthreads();
+    const unsigned blocks = gridDim.x * gridDim.y * gridDim.z;
+    const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
+    if (tid == 0) {
+        double t1 = 0.0, t2 = 0.0;
+        for (int w = 0; w < LT * LT / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+        st.partial[2 * bid] = t1;
+        st.partial[2 * bid + 1] = t2;
+        __threadfence();
+        s_last = atomicAdd(st.ticket, 1u) == blocks - 1;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    double t1 = 0.0, t2 = 0.0;
+    for (unsigned i = tid; i < blocks; i += LT * LT) {
+        t1 += __ldcg(st.partial + 2 * i);
+        t2 += __ldcg(st.partial + 2 * i + 1);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        t1 += __shfl_xor_sync(0xFFFFFFFFu, t1, o);
+        t2 += __shfl_xor_sync(0xFFFFFFFFu, t2, o);
+    }
+    __syncthreads();
+    if ((tid & 31) == 0) { s_red[0][tid >> 5] = t1; s_red[1][tid >> 5] = t2; }
+    __syncthreads();
+    if (tid == 0) {
+        t1 = 0.0; t2 = 0.0;
+        for (int w = 0; w < LT * LT / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+        const double n = double(C) * H * W;
+        const float l1_mean = float(t1 / n), ssim_mean = float(t2 / n);
+        loss_out[0] = l1_mean;
+        loss_out[1] = ssim_mean;
+        loss_out[2] = w_l1 * l1_mean + w_ssim * ssim_mean + bias;
+    }
+}
+
+__device__ __forceinline__ float map_load(const float* __restrict__ m, int ch, int y, int x, int H, int W) {
+    if (x < 0 || x >= W || y < 0 || y >= H) return 0.f;
+    return __ldg(m + (size_t(ch) * H + y) * W + x);
+}
+
+__global__ void __launch_bounds__(LT * LT)
+ssim_l1_backward_kernel(int C, int H, int W, const float* __restrict__ image, const float* __restrict__ gt,
+                        const float* __restrict__ row_mask, const Window win, float w_l1, float w_ssim,
+                        const float* __restrict__ dL_dloss, LossState st, float* __restrict__ dL_dimage)
+{
+    __shared__ float sm[3][LW][LS];
+    __shared__ float hb[3][LW][LT];
+
+    const int tid = threadIdx.x;
+    const int tx = tid & (LT - 1), ty = tid >> 4;
+    const int ch = blockIdx.z;
+    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+
+    for (int i = tid; i < LW * LW; i += LT * LT) {
+        const int r = i / LW, c = i - r * LW;
+        const int gy = y0 + r - HALO, gx = x0 + c - HALO;
+        sm[0][r][c] = map_load(st.m1, ch, gy, gx, H, W);
+        sm[1][r][c] = map_load(st.m2, ch, gy, gx, H, W);
+        sm[2][r][c] = map_load(st.m3, ch, gy, gx, H, W);
+    }
+    __syncthreads();
+    for (int i = tid; i < LW * LT; i += LT * LT) {
+        const int r = i >> 4, c = i & (LT - 1);
+        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) {
+            const float w = win.w[k];
+            a0 = fmaf(w, sm[0][r][c + k], a0);
+            a1 = fmaf(w, sm[1][r][c + k], a1);
+            a2 = fmaf(w, sm[2][r][c + k], a2);
+        }
+        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2;
+    }
+    __syncthreads();
+    const int px = x0 + tx, py = y0 + ty;
+    if (px >= W || py >= H) return;
+    float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll
+    for (int k = 0; k < WIN; ++k) {
+        const float w = win.w[k];
+        c1 = fmaf(w, hb[0][ty + k][tx], c1);
+        c2 = fmaf(w, hb[1][ty + k][tx], c2);
+        c3 = fmaf(w, hb[2][ty + k][tx], c3);
+    }
+    const float up = dL_dloss ? __ldg(dL_dloss) : 1.f;
+    const float inv_n = 1.f / (float(C) * float(H) * float(W));
+    const size_t o = (size_t(ch) * H + py) * W + px;
+    const float m = row_mask ? __ldg(row_mask + ch * H + py) : 1.f;
+    const float x = __ldg(image + o) * m, y = __ldg(gt + o) * m;
+    const float diff = x - y;
+    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);   // abs backward: sign(0) = 0
+    const float g = (w_ssim * inv_n) * (c1 + 2.f * x * c2 + y * c3) + (w_l1 * inv_n) * sgn;
+    dL_dimage[o] = up * m * g;
+}
+
+// 0.01 * scaling.prod(1).mean() of gaussian_mapper.cpp:922-925, forward value + gradient added in place
+__global__ void __launch_bounds__(256)
+scaling_reg_kernel(int n, const float* __restrict__ scaling, float weight, const float* __restrict__ dL_dloss,
+                   float* __restrict__ dL_dscaling, float* __restrict__ reg_out)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    float p = 0.f;
+    if (i < n) {
+        const float s0 = scaling[3 * i], s1 = scaling[3 * i + 1], s2 = scaling[3 * i + 2];
+        p = s0 * s1 * s2;
+        if (dL_dscaling) {
+            const float g = (dL_dloss ? __ldg(dL_dloss) : 1.f) * weight / float(n);
+            dL_dscaling[3 * i] += g * s1 * s2;
+            dL_dscaling[3 * i + 1] += g * s0 * s2;
+            dL_dscaling[3 * i + 2] += g * s0 * s1;
+        }
+    }
+    if (reg_out) {
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
+        if ((threadIdx.x & 31) == 0 && p != 0.f) atomicAdd(reg_out, p * (weight / float(n)));
+    }
+}
+
+}  // namespace
+
+}  // namespace segs
+
+using namespace segs;
+
+extern "C" {
+
+size_t segs_loss_state_bytes(int C, int H, int W)
+{
+    if (C <= 0 || H <= 0 || W <= 0) return 0;
+    size_t bytes = 0;
+    const size_t blocks = size_t((W + LT - 1) / LT) * ((H + LT - 1) / LT) * C;
+    LossState::carve(nullptr, size_t(C) * H * W, blocks, &bytes);
+    return bytes;
+}
+
+int segs_loss_l1_ssim_forward(int C, int H, int W, const float* image, const float* gt, const float* row_mask,
+                              float w_l1, float w_ssim, float bias, float* loss_out, char* state, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535) { set_error("loss: invalid sizes C=%d H=%d W=%d", C, H, W); return SEGS_ERR_INVALID_ARG; }
+    if (!image || !gt || !loss_out || !state) { set_error("loss: NULL required pointer"); return SEGS_ERR_INVALID_ARG; }
+    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    if (grid.y > 65535) { set_error("loss: image too tall"); return SEGS_ERR_INVALID_ARG; }
+    const size_t blocks = size_t(grid.x) * grid.y * grid.z;
+    LossState st = LossState::carve(state, size_t(C) * H * W, blocks, nullptr);
+    SEGS_CUDA_CHECK(cudaMemsetAsync(st.ticket, 0, sizeof(uint32_t), stream));
+    static const Window win = make_window();
+    ssim_l1_forward_kernel<<<grid, LT * LT, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, bias, st, loss_out);
+    SEGS_LAUNCH_CHECK();
+    return SEGS_OK;
+}
+
+int segs_loss_l1_ssim_backward(int C, int H, int W, const float* image, const float* gt, const float* row_mask,
+                               float w_l1, float w_ssim, const float* dL_dloss, char* state, float* dL_dimage,
+                               void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (C <= 0 || H <= 0 || W <= 0 || C > 65535) { set_error("loss: invalid sizes C=%d H=%d W=%d", C, H, W); return SEGS_ERR_INVALID_ARG; }
+    if (!image || !gt || !dL_dimage || !state) { set_error("loss: NULL required pointer"); return SEGS_ERR_INVALID_ARG; }
+    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    if (grid.y > 65535) { set_error("loss: image too tall"); return SEGS_ERR_INVALID_ARG; }
+    const size_t blocks = size_t(grid.x) * grid.y * grid.z;
+    LossState st = LossState::carve(state, size_t(C) * H * W, blocks, nullptr);
+    static const Window win = make_window();
+    ssim_l1_backward_kernel<<<grid, LT * LT, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, dL_dloss, st, dL_dimage);
+    SEGS_LAUNCH_CHECK();
+    return SEGS_OK;
+}
+
+int segs_scaling_reg(int n, const float* scaling, float weight, const float* dL_dloss, float* dL_dscaling,
+                     float* reg_out, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (n < 0 || (n > 0 && !scaling)) { set_error("scaling_reg: invalid argument"); return SEGS_ERR_INVALID_ARG; }
+    if (n == 0) return SEGS_OK;
+    scaling_reg_kernel<<<(n + 255) / 256, 256, 0, stream>>>(n, scaling, weight, dL_dloss, dL_dscaling, reg_out);
+    SEGS_LAUNCH_CHECK();
+    return SEGS_OK;
+}
+
+}  // extern "C"

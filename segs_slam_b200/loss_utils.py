@@ -1,0 +1,125 @@
+"""Photometric loss of the mapper, mirroring the reference's `loss_utils` namespace
+(/root/reference/include/loss_utils.h:29-127: l1_loss, psnr, ssim) and the way the mapper combines it
+(/root/reference/src/gaussian_mapper.cpp:908-925) on top of the fused CUDA kernels of
+segs_slam_b200/csrc/loss.cu (C ABI: segs_loss_l1_ssim_forward / _backward, segs_scaling_reg).
+
+torch is used for device memory, the current stream and autograd bookkeeping only; there is no CPU path.
+"""
+from __future__ import annotations
+
+import torch
+
+from . import _lib
+from .rasterize_points import _ptr, _stream
+
+
+def _check(image: torch.Tensor, gt: torch.Tensor):
+    if not image.is_cuda or not gt.is_cuda:
+        raise RuntimeError("segs_slam_b200 has no CPU path: tensors must live on a CUDA device")
+    if image.dim() != 3 or image.shape != gt.shape:
+        raise RuntimeError(f"loss: image {tuple(image.shape)} and gt {tuple(gt.shape)} must both be [C,H,W]")
+    if image.dtype != torch.float32 or gt.dtype != torch.float32:
+        raise RuntimeError("loss: FP32 images expected")
+
+
+class _L1SSIMFunction(torch.autograd.Function):
+    """(l1, ssim, loss) = f(image); loss = w_l1*l1 + w_ssim*ssim + bias.  Gradients flow to `image` only."""
+
+    @staticmethod
+    def forward(ctx, image, gt, row_mask, w_l1, w_ssim, bias):
+        _check(image, gt)
+        lib = _lib.load()
+        C_, H, W = image.shape
+        img_c, gt_c = image.contiguous(), gt.contiguous()
+        mask_c = row_mask.contiguous() if row_mask is not None else None
+        if mask_c is not None and tuple(mask_c.shape) != (C_, H):
+            raise RuntimeError(f"loss: row_mask must be [C,H] = {(C_, H)}, got {tuple(mask_c.shape)}")
+        state = torch.empty((int(lib.segs_loss_state_bytes(C_, H, W)),), dtype=torch.uint8, device=image.device)
+        out = torch.empty((3,), dtype=torch.float32, device=image.device)
+        with torch.cuda.device(image.device):
+            _lib.check(lib.segs_loss_l1_ssim_forward(C_, H, W, _ptr(img_c), _ptr(gt_c), _ptr(mask_c), w_l1, w_ssim,
+                                                     bias, _ptr(out), state.data_ptr(), _stream()))
+        ctx.save_for_backward(img_c, gt_c, mask_c if mask_c is not None else torch.empty(0, device=image.device),
+                              state)
+        ctx.w = (float(w_l1), float(w_ssim))
+        return out[0], out[1], out[2]
+
+    @staticmethod
+    def backward(ctx, g_l1, g_ssim, g_loss):
+        lib = _lib.load()
+        img_c, gt_c, mask_c, state = ctx.saved_tensors
+        C_, H, W = img_c.shape
+        w_l1, w_ssim = ctx.w
+        grad = None
+        # each output is the same kernel with different weights; the usual case is one call (g_loss only)
+        for g, (a, b) in ((g_loss, (w_l1, w_ssim)), (g_l1, (1.0, 0.0)), (g_ssim, (0.0, 1.0))):
+            if g is None:
+                continue
+            d = torch.empty_like(img_c)
+            gc = g.to(torch.float32).contiguous()
+            with torch.cuda.device(img_c.device):
+                _lib.check(lib.segs_loss_l1_ssim_backward(C_, H, W, _ptr(img_c), _ptr(gt_c), _ptr(mask_c), a, b,
+                                                          _ptr(gc), state.data_ptr(), _ptr(d), _stream()))
+            grad = d if grad is None else grad + d
+        return grad, None, None, None, None, None
+
+
+def l1_ssim_loss(image: torch.Tensor, gt: torch.Tensor, lambda_dssim: float, row_mask: torch.Tensor | None = None):
+    """(1 - lambda) * l1_loss + lambda * (1 - ssim)  (gaussian_mapper.cpp:917-921), one fused kernel each way.
+    row_mask [C,H]: the `mask_rgb` of :911-915 (see `mask_rgb`).  -> (loss, Ll1, ssim) scalars on the device."""
+    l1, ss, loss = _L1SSIMFunction.apply(image, gt, row_mask, 1.0 - lambda_dssim, -lambda_dssim, lambda_dssim)
+    return loss, l1, ss
+
+
+def l1_loss(network_output: torch.Tensor, gt: torch.Tensor) -> torch.Tensor:
+    """loss_utils::l1_loss (loss_utils.h:29-32)."""
+    return _L1SSIMFunction.apply(network_output, gt, None, 1.0, 0.0, 0.0)[0]
+
+
+def ssim(img1: torch.Tensor, img2: torch.Tensor, window_size: int = 11, size_average: bool = True) -> torch.Tensor:
+    """loss_utils::ssim (loss_utils.h:112-127) with the only configuration the reference uses."""
+    if window_size != 11 or not size_average:
+        raise RuntimeError("ssim: only window_size = 11, size_average = true (the reference's call sites) is built")
+    return _L1SSIMFunction.apply(img1, img2, None, 0.0, 1.0, 0.0)[1]
+
+
+def psnr(img1: torch.Tensor, img2: torch.Tensor) -> torch.Tensor:
+    """loss_utils::psnr (loss_utils.h:39-43); evaluation only, plain device arithmetic."""
+    _check(img1, img2)
+    mse = torch.pow(img1 - img2, 2).mean()
+    return 10.0 * torch.log10(1.0 / mse)
+
+
+def mask_rgb(gt_image: torch.Tensor) -> torch.Tensor:
+    """(gt != 0).any(-1) as float, [C,H] (gaussian_mapper.cpp:911-912); constant per keyframe."""
+    return (gt_image != 0.0).any(-1).to(torch.float32)
+
+
+class _ScalingReg(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, scaling, weight):
+        if not scaling.is_cuda:
+            raise RuntimeError("segs_slam_b200 has no CPU path: tensors must live on a CUDA device")
+        lib = _lib.load()
+        s = scaling.contiguous()
+        out = torch.zeros((), dtype=torch.float32, device=s.device)
+        with torch.cuda.device(s.device):
+            _lib.check(lib.segs_scaling_reg(s.size(0), _ptr(s), weight, None, None, _ptr(out), _stream()))
+        ctx.save_for_backward(s)
+        ctx.weight = float(weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        (s,) = ctx.saved_tensors
+        d = torch.zeros_like(s)
+        gc = g.to(torch.float32).contiguous()
+        with torch.cuda.device(s.device):
+            _lib.check(lib.segs_scaling_reg(s.size(0), _ptr(s), ctx.weight, _ptr(gc), _ptr(d), None, _stream()))
+        return d, None
+
+
+def scaling_reg(scaling: torch.Tensor, weight: float = 0.01) -> torch.Tensor:
+    """weight * scaling.prod(1).mean() (gaussian_mapper.cpp:919-921)."""
+    return _ScalingReg.apply(scaling, weight)
