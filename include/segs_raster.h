@@ -262,6 +262,84 @@ int segs_decode_backward(
     segs_alloc_fn scratch_alloc, void* scratch_user,
     void* stream);
 
+/* segs_decode_backward with options (flags, OR-ed):
+ *   SEGS_DECODE_ACCUMULATE   d_anchor / d_anchor_feat / d_offset / d_scaling are ADDED to instead of being zeroed
+ *                            and written (gradient accumulation over the keyframe batch; every anchor row is owned
+ *                            by one thread, no atomics).  *dparams is still zeroed and written.
+ *   SEGS_DECODE_LOG_SCALING  d_scaling is the gradient w.r.t. _scaling = log(scaling) (the trainable tensor,
+ *                            gaussian_model.cpp:186-189), i.e. multiplied by `scaling`. */
+#define SEGS_DECODE_ACCUMULATE  1
+#define SEGS_DECODE_LOG_SCALING 2
+int segs_decode_backward_ex(
+    int A, const unsigned char* visible_mask,
+    const float* anchor, const float* anchor_feat, const float* offset, const float* scaling,
+    const float* camera_center, const float* pose,
+    const segs_decode_params* params,
+    const char* state, int n_vis, int n_out,
+    const float* g_xyz, const float* g_color, const float* g_opacity, const float* g_scaling, const float* g_rot,
+    const float* g_neural_opacity,
+    float* d_anchor, float* d_anchor_feat, float* d_offset, float* d_scaling,
+    const segs_decode_grads* dparams,
+    segs_alloc_fn scratch_alloc, void* scratch_user,
+    int flags, void* stream);
+
+/* ---- one keyframe view of the batched mapping step (BASELINE config 4) -------------
+ *   segs_mapper_view      the body of GaussianMapper::trainForOneIteration  src/gaussian_mapper.cpp:870-950:
+ *                         prefilter_voxel (src/gaussian_renderer.cpp:131-199) -> generate_neural_gaussians
+ *                         (:214-334) -> render (:40-127) -> loss (gaussian_mapper.cpp:908-925) -> backward,
+ *                         with the parameter gradients ACCUMULATED into the caller's bucket.
+ * A workspace is a reusable device arena (grown with cudaMalloc on demand, reset per view); one workspace
+ * serves one stream at a time. */
+typedef struct segs_workspace segs_workspace;
+int    segs_workspace_create(segs_workspace** out);
+int    segs_workspace_destroy(segs_workspace* ws);
+size_t segs_workspace_bytes(const segs_workspace* ws);
+
+typedef struct segs_mapper_view_args {
+    /* replicated model (DEVICE) */
+    int A;
+    const float* anchor;            /* [A,3]    */
+    const float* anchor_feat;       /* [A,32]   */
+    const float* offset;            /* [A,10,3] */
+    const float* scaling;           /* [A,6] = exp(_scaling) (GaussianModel::get_scaling)                   */
+    int scaling_is_log;             /* != 0: grad_scaling is w.r.t. _scaling (chain through the exp)         */
+    const float* filter_scales;     /* [A,3] = get_scaling()[:, :3] contiguous (gaussian_renderer.cpp:172)  */
+    const float* filter_rotations;  /* [A,4] = get_rotation() (normalised)                                   */
+    const segs_decode_params* params;
+    /* keyframe */
+    int width, height;
+    float tan_fovx, tan_fovy;
+    const float* viewmatrix;        /* DEVICE, 16 floats, m[4*col+row] */
+    const float* projmatrix;        /* DEVICE */
+    const float* campos;            /* DEVICE, 3 floats */
+    const float* pose;              /* HOST, {t.xyz, q.wxyz} */
+    const float* background;        /* DEVICE, 3 floats */
+    const float* gt_image;          /* DEVICE [3,H,W] */
+    const float* row_mask;          /* DEVICE [3,H] or NULL (mask_rgb, gaussian_mapper.cpp:911-915) */
+    float lambda_dssim;             /* loss = (1-l) L1 + l (1-SSIM) + scaling_reg_weight * mean(prod(scaling)) */
+    float scaling_reg_weight;       /* 0.01 in the reference (gaussian_mapper.cpp:921) */
+    /* accumulated outputs (DEVICE; += ) */
+    float* grad_anchor;             /* [A,3]    */
+    float* grad_anchor_feat;        /* [A,32]   */
+    float* grad_offset;             /* [A,10,3] */
+    float* grad_scaling;            /* [A,6]    */
+    const segs_decode_grads* grad_params;   /* every live MLP tensor */
+    float* loss_accum;              /* scalar */
+    /* optional per-view outputs (DEVICE, may be NULL) */
+    float* image_out;               /* [3,H,W] rendered image */
+    float* loss_terms_out;          /* {Ll1, ssim, photometric loss} */
+    float* dL_dmean2D_out;          /* [A*10,3] capacity: screen-space gradient of the emitted Gaussians (densification) */
+    int*   radii_out;               /* [A*10] capacity */
+} segs_mapper_view_args;
+
+typedef struct segs_mapper_view_result {
+    int n_visible;                  /* anchors that passed the prefilter */
+    int n_gaussians;                /* neural Gaussians emitted by the decode */
+    int num_rendered;               /* tile instances */
+} segs_mapper_view_result;
+
+int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* args, segs_mapper_view_result* result, void* stream);
+
 /* ---- mapper loss and optimizer ---------------------------------------
  *   segs_loss_l1_ssim_*   loss_utils::l1_loss / ssim / _ssim           include/loss_utils.h:29-32, 50-127,
  *                         as combined at                                src/gaussian_mapper.cpp:917-925

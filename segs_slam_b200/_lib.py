@@ -34,6 +34,26 @@ class DecodeGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in _PARAM_NAMES]
 
 
+class MapperViewArgs(C.Structure):
+    """segs_mapper_view_args (include/segs_raster.h)."""
+    _fields_ = [("A", C.c_int), ("anchor", C.c_void_p), ("anchor_feat", C.c_void_p), ("offset", C.c_void_p),
+                ("scaling", C.c_void_p), ("scaling_is_log", C.c_int), ("filter_scales", C.c_void_p),
+                ("filter_rotations", C.c_void_p), ("params", C.POINTER(DecodeParams)),
+                ("width", C.c_int), ("height", C.c_int), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("pose", C.POINTER(C.c_float)), ("background", C.c_void_p), ("gt_image", C.c_void_p),
+                ("row_mask", C.c_void_p), ("lambda_dssim", C.c_float), ("scaling_reg_weight", C.c_float),
+                ("grad_anchor", C.c_void_p), ("grad_anchor_feat", C.c_void_p), ("grad_offset", C.c_void_p),
+                ("grad_scaling", C.c_void_p), ("grad_params", C.POINTER(DecodeGrads)), ("loss_accum", C.c_void_p),
+                ("image_out", C.c_void_p), ("loss_terms_out", C.c_void_p), ("dL_dmean2D_out", C.c_void_p),
+                ("radii_out", C.c_void_p)]
+
+
+class MapperViewResult(C.Structure):
+    """segs_mapper_view_result (include/segs_raster.h)."""
+    _fields_ = [("n_visible", C.c_int), ("n_gaussians", C.c_int), ("num_rendered", C.c_int)]
+
+
 class AdamTensor(C.Structure):
     """segs_adam_tensor (include/segs_raster.h)."""
     _fields_ = [("param", C.c_void_p), ("offset", C.c_ulonglong), ("count", C.c_ulonglong), ("lr", C.c_float),
@@ -88,6 +108,16 @@ _PROTOTYPES = {
          C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
          _f32p, _f32p, _f32p, _f32p, C.POINTER(DecodeGrads), ALLOC_FN, C.c_void_p, C.c_void_p],
     ),
+    "segs_decode_backward_ex": (
+        C.c_int,
+        [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),
+         C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+         _f32p, _f32p, _f32p, _f32p, C.POINTER(DecodeGrads), ALLOC_FN, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "segs_workspace_create": (C.c_int, [C.POINTER(C.c_void_p)]),
+    "segs_workspace_destroy": (C.c_int, [C.c_void_p]),
+    "segs_workspace_bytes": (C.c_size_t, [C.c_void_p]),
+    "segs_mapper_view": (C.c_int, [C.c_void_p, C.POINTER(MapperViewArgs), C.POINTER(MapperViewResult), C.c_void_p]),
     "segs_loss_state_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "segs_loss_l1_ssim_forward": (
         C.c_int,

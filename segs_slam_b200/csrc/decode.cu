@@ -669,10 +669,12 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
                        const float* __restrict__ g_opacity, const float* __restrict__ g_scaling,
                        const float* __restrict__ g_rot, const float* __restrict__ g_nop,
                        float* __restrict__ d_anchor, float* __restrict__ d_feat, float* __restrict__ d_offset,
-                       float* __restrict__ d_scaling, float* __restrict__ fact)
+                       float* __restrict__ d_scaling, float* __restrict__ fact, const int flags)
 {
     __shared__ __align__(16) SW sw;
     stage_weights(sw, p, pose);
+    // SEGS_DECODE_ACCUMULATE: every anchor row is owned by exactly one thread, so `+=` needs no atomics
+    const bool acc_mode = (flags & SEGS_DECODE_ACCUMULATE) != 0;
   for (size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x; ordinal < (size_t)n_vis;
        ordinal += size_t(gridDim.x) * DEC_THREADS) {
     const size_t a = st.anchor_index[ordinal];
@@ -743,7 +745,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
             if (!((m >> o) & 1u)) {
 #pragma unroll
                 for (int k = 0; k < 7; ++k) put(F_D2S + 7 * o + k, 0.f);
-                dof[0] = 0.f; dof[1] = 0.f; dof[2] = 0.f;
+                if (!acc_mode) { dof[0] = 0.f; dof[1] = 0.f; dof[2] = 0.f; }
                 continue;
             }
             float sr[7], dsr[7];
@@ -754,7 +756,8 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
                         oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
             // xyz = anchor + offset * s[:3]
             dax += gx; day += gy; daz += gz;
-            dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2];
+            if (acc_mode) { dof[0] += gx * in.s[0]; dof[1] += gy * in.s[1]; dof[2] += gz * in.s[2]; }
+            else { dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2]; }
             ds[0] = fmaf(gx, ox, ds[0]); ds[1] = fmaf(gy, oy, ds[1]); ds[2] = fmaf(gz, oz, ds[2]);
             // scaling = s[3:] * sigmoid(sr[:3])
 #pragma unroll
@@ -861,8 +864,12 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
         for (int j = 0; j < FEAT; ++j) df[j] = dx[j];
     }
 #pragma unroll
-    for (int q = 0; q < FEAT / 4; ++q)
-        reinterpret_cast<float4*>(d_feat + a * FEAT)[q] = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+    for (int q = 0; q < FEAT / 4; ++q) {
+        float4* dst = reinterpret_cast<float4*>(d_feat + a * FEAT) + q;
+        float4 v = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+        if (acc_mode) { const float4 o4 = *dst; v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w; }
+        *dst = v;
+    }
 
     // ob_view = v / |v|, ob_dist = |v|, v = anchor - camera
     {
@@ -872,9 +879,21 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
         day += (duy - uy * ud) * inv + ddist * uy;
         daz += (duz - uz * ud) * inv + ddist * uz;
     }
-    d_anchor[3 * a] = dax; d_anchor[3 * a + 1] = day; d_anchor[3 * a + 2] = daz;
+    // SEGS_DECODE_LOG_SCALING: the caller's parameter is _scaling = log(scaling) (GaussianModel::get_scaling,
+    // gaussian_model.cpp:186-189), so chain through the exp: d/d_log = d/d_scaling * scaling
+    if (flags & SEGS_DECODE_LOG_SCALING) {
 #pragma unroll
-    for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] = ds[k];
+        for (int k = 0; k < 6; ++k) ds[k] *= in.s[k];
+    }
+    if (acc_mode) {
+        d_anchor[3 * a] += dax; d_anchor[3 * a + 1] += day; d_anchor[3 * a + 2] += daz;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] += ds[k];
+    } else {
+        d_anchor[3 * a] = dax; d_anchor[3 * a + 1] = day; d_anchor[3 * a + 2] = daz;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] = ds[k];
+    }
   }
 }
 
@@ -1118,15 +1137,16 @@ extern "C" int segs_decode_forward(
     return SEGS_OK;
 }
 
-extern "C" int segs_decode_backward(
+extern "C" int segs_decode_backward_ex(
     int A, const unsigned char* visible_mask, const float* anchor, const float* anchor_feat, const float* offset,
     const float* scaling, const float* camera_center, const float* pose, const segs_decode_params* params,
     const char* state, int n_vis, int n_out, const float* g_xyz, const float* g_color, const float* g_opacity,
     const float* g_scaling, const float* g_rot, const float* g_neural_opacity, float* d_anchor, float* d_anchor_feat,
     float* d_offset, float* d_scaling, const segs_decode_grads* dp, segs_alloc_fn scratch_alloc, void* scratch_user,
-    void* stream_)
+    int flags, void* stream_)
 {
     (void)visible_mask;
+    const bool acc_mode = (flags & SEGS_DECODE_ACCUMULATE) != 0;
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (A == 0) return SEGS_OK;
     int rc = check_params(params);
@@ -1150,8 +1170,10 @@ extern "C" int segs_decode_backward(
         ZeroList z;
         int c = 0;
         auto zero = [&](float* ptr, size_t n) { if (ptr && n) { z.p[c] = ptr; z.n[c] = n; ++c; } };
-        zero(d_anchor, size_t(A) * 3); zero(d_anchor_feat, size_t(A) * FEAT);
-        zero(d_offset, size_t(A) * NOFF * 3); zero(d_scaling, size_t(A) * 6);
+        if (!acc_mode) {
+            zero(d_anchor, size_t(A) * 3); zero(d_anchor_feat, size_t(A) * FEAT);
+            zero(d_offset, size_t(A) * NOFF * 3); zero(d_scaling, size_t(A) * 6);
+        }
         zero(dp->opacity_w1, size_t(FEAT) * in_o); zero(dp->opacity_b1, FEAT);
         zero(dp->opacity_w2, NOFF * FEAT);         zero(dp->opacity_b2, NOFF);
         zero(dp->cov_w1, size_t(FEAT) * in_s);     zero(dp->cov_b1, FEAT);
@@ -1182,7 +1204,7 @@ extern "C" int segs_decode_backward(
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
     decode_backward_kernel<<<std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 3), DEC_THREADS, 0, stream>>>(
         n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
-        g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact);
+        g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
     SEGS_LAUNCH_CHECK();
 
     WJobs jobs;
@@ -1228,4 +1250,17 @@ extern "C" int segs_decode_backward(
         SEGS_LAUNCH_CHECK();
     }
     return SEGS_OK;
+}
+
+extern "C" int segs_decode_backward(
+    int A, const unsigned char* visible_mask, const float* anchor, const float* anchor_feat, const float* offset,
+    const float* scaling, const float* camera_center, const float* pose, const segs_decode_params* params,
+    const char* state, int n_vis, int n_out, const float* g_xyz, const float* g_color, const float* g_opacity,
+    const float* g_scaling, const float* g_rot, const float* g_neural_opacity, float* d_anchor, float* d_anchor_feat,
+    float* d_offset, float* d_scaling, const segs_decode_grads* dp, segs_alloc_fn scratch_alloc, void* scratch_user,
+    void* stream_)
+{
+    return segs_decode_backward_ex(A, visible_mask, anchor, anchor_feat, offset, scaling, camera_center, pose, params, state,
+                                   n_vis, n_out, g_xyz, g_color, g_opacity, g_scaling, g_rot, g_neural_opacity, d_anchor,
+                                   d_anchor_feat, d_offset, d_scaling, dp, scratch_alloc, scratch_user, 0, stream_);
 }

@@ -1,0 +1,220 @@
+// One keyframe view of the batched mapping step, issued from C++ with no interpreter in the loop
+// (BASELINE config 4): anchor prefilter -> fused decode -> rasterize -> L1+SSIM loss ->
+// rasterizer backward -> decode backward that ACCUMULATES straight into the caller's gradient bucket.
+//
+// Restates the per-iteration body of GaussianMapper::trainForOneIteration
+// (/root/reference/src/gaussian_mapper.cpp:870-950): prefilter_voxel (src/gaussian_renderer.cpp:131-199),
+// GaussianRenderer::render (:40-127, generate_neural_gaussians :214-334), the loss (:908-925) and
+// loss.backward() — as one host function over the kernels of this library.  The reference runs it as
+// ~150 ATen launches with autograd bookkeeping; here it is 27 launches, two host read-backs (the
+// decode's row count and num_rendered — both shape the next allocation, as in the reference) and no
+// temporary that outlives the view: everything is carved from a reusable workspace arena.
+#include <vector>
+#include "common.cuh"
+
+namespace segs {
+
+namespace {
+
+// Bump arena over a few large cudaMalloc'd chunks; reset per view, chunks are kept (after the first
+// views of a run no allocation happens any more).
+struct Chunk { char* base; size_t size; size_t used; };
+
+}  // namespace
+
+}  // namespace segs
+
+struct segs_workspace {
+    std::vector<segs::Chunk> chunks;
+    size_t granule = size_t(256) << 20;
+    size_t total = 0;
+    bool failed = false;
+
+    void reset() { for (auto& c : chunks) c.used = 0; failed = false; }
+    char* alloc(size_t bytes) {
+        bytes = (bytes + 255) & ~size_t(255);
+        if (bytes == 0) bytes = 256;
+        for (auto& c : chunks)
+            if (c.size - c.used >= bytes) { char* p = c.base + c.used; c.used += bytes; return p; }
+        const size_t sz = bytes > granule ? bytes : granule;
+        void* p = nullptr;
+        if (cudaMalloc(&p, sz) != cudaSuccess) { cudaGetLastError(); failed = true; return nullptr; }
+        chunks.push_back(segs::Chunk{static_cast<char*>(p), sz, bytes});
+        total += sz;
+        return static_cast<char*>(p);
+    }
+    template <typename T> T* take(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+};
+
+namespace segs {
+namespace {
+
+char* ws_alloc_cb(void* user, size_t bytes) { return static_cast<segs_workspace*>(user)->alloc(bytes); }
+
+__global__ void __launch_bounds__(256)
+radii_to_mask_kernel(int n, const int* __restrict__ radii, unsigned char* __restrict__ mask)
+{
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) mask[i] = radii[i] > 0;       // visible_mask = radii_pure > 0 (gaussian_renderer.cpp:197)
+}
+
+__global__ void add_scalar_kernel(float* __restrict__ dst, const float* __restrict__ src) { *dst += *src; }
+
+}  // namespace
+}  // namespace segs
+
+using namespace segs;
+
+extern "C" {
+
+int segs_workspace_create(segs_workspace** out)
+{
+    if (!out) { set_error("workspace: NULL output"); return SEGS_ERR_INVALID_ARG; }
+    *out = new segs_workspace();
+    return SEGS_OK;
+}
+
+int segs_workspace_destroy(segs_workspace* ws)
+{
+    if (!ws) return SEGS_OK;
+    for (auto& c : ws->chunks) cudaFree(c.base);
+    delete ws;
+    return SEGS_OK;
+}
+
+size_t segs_workspace_bytes(const segs_workspace* ws) { return ws ? ws->total : 0; }
+
+int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_mapper_view_result* res, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (!ws || !a || !res) { set_error("mapper view: NULL argument"); return SEGS_ERR_INVALID_ARG; }
+    res->n_visible = res->n_gaussians = res->num_rendered = 0;
+    const int A = a->A, W = a->width, H = a->height;
+    if (A <= 0 || W <= 0 || H <= 0) { set_error("mapper view: invalid sizes A=%d W=%d H=%d", A, W, H); return SEGS_ERR_INVALID_ARG; }
+    if (!a->anchor || !a->anchor_feat || !a->offset || !a->scaling || !a->filter_scales || !a->filter_rotations ||
+        !a->params || !a->viewmatrix || !a->projmatrix || !a->campos || !a->pose || !a->background || !a->gt_image ||
+        !a->grad_anchor || !a->grad_anchor_feat || !a->grad_offset || !a->grad_scaling || !a->grad_params || !a->loss_accum) {
+        set_error("mapper view: NULL required pointer"); return SEGS_ERR_INVALID_ARG;
+    }
+    ws->reset();
+    int rc;
+    auto oom = [&]() { set_error("mapper view: workspace allocation failed (%zu bytes held)", ws->total); return SEGS_ERR_ALLOC; };
+
+    // ---- prefilter_voxel (gaussian_renderer.cpp:131-199): radii of the anchors themselves ----
+    int* anchor_radii = ws->take<int>(A);
+    unsigned char* visible = ws->take<unsigned char>(A);
+    if (!anchor_radii || !visible) return oom();
+    if ((rc = segs_visible_filter(A, 0, W, H, a->anchor, a->filter_scales, 1.0f, a->filter_rotations, nullptr, a->viewmatrix,
+                                  a->projmatrix, a->tan_fovx, a->tan_fovy, 0, anchor_radii, stream))) return rc;
+    radii_to_mask_kernel<<<(A + 255) / 256, 256, 0, stream>>>(A, anchor_radii, visible);
+    SEGS_LAUNCH_CHECK();
+
+    // ---- generate_neural_gaussians (:214-334) ----
+    const size_t cap = size_t(A) * 10;
+    float* xyz = ws->take<float>(cap * 3);
+    float* color = ws->take<float>(cap * 3);
+    float* opacity = ws->take<float>(cap);
+    float* scaling = ws->take<float>(cap * 3);
+    float* rot = ws->take<float>(cap * 4);
+    float* neural_opacity = ws->take<float>(cap);
+    unsigned char* offset_mask = ws->take<unsigned char>(cap);
+    char* dstate = ws->alloc(segs_decode_state_bytes(A));
+    if (!xyz || !color || !opacity || !scaling || !rot || !neural_opacity || !offset_mask || !dstate) return oom();
+    int counts[2] = {0, 0};
+    if ((rc = segs_decode_forward(A, visible, a->anchor, a->anchor_feat, a->offset, a->scaling, a->campos, a->pose, a->params,
+                                  xyz, color, opacity, scaling, rot, neural_opacity, offset_mask, dstate, counts, stream)))
+        return rc;
+    const int n_vis = counts[0], P = counts[1];
+    res->n_visible = n_vis;
+    res->n_gaussians = P;
+
+    // ---- rasterize (:40-127 -> RasterizeGaussiansCUDA) ----
+    const size_t N = size_t(W) * H;
+    float* image = a->image_out ? a->image_out : ws->take<float>(3 * N);
+    int* radii = ws->take<int>(P > 0 ? P : 1);
+    if (!image || !radii) return oom();
+    // the three opaque buffers come from the arena through the same callback ABI the tensor-level API uses
+    struct Slot { segs_workspace* ws; char* ptr; };
+    Slot geom{ws, nullptr}, binning{ws, nullptr}, img{ws, nullptr};
+    auto slot_cb = [](void* u, size_t bytes) -> char* {
+        Slot* s = static_cast<Slot*>(u);
+        s->ptr = s->ws->alloc(bytes);
+        return s->ptr;
+    };
+    int R = 0;
+    if ((rc = segs_raster_forward(slot_cb, &geom, slot_cb, &binning, slot_cb, &img, P, 0, 0, a->background, W, H, xyz, nullptr,
+                                  color, opacity, scaling, 1.0f, rot, nullptr, a->viewmatrix, a->projmatrix, a->campos,
+                                  a->tan_fovx, a->tan_fovy, 0, image, radii, &R, stream))) return rc;
+    res->num_rendered = R;
+
+    // ---- loss (gaussian_mapper.cpp:908-925) and its gradient w.r.t. the image ----
+    char* lstate = ws->alloc(segs_loss_state_bytes(3, H, W));
+    float* loss3 = ws->take<float>(4);
+    float* dL_dimage = ws->take<float>(3 * N);
+    if (!lstate || !loss3 || !dL_dimage) return oom();
+    const float lam = a->lambda_dssim;
+    if ((rc = segs_loss_l1_ssim_forward(3, H, W, image, a->gt_image, a->row_mask, 1.f - lam, -lam, lam, loss3, lstate, stream))) return rc;
+    add_scalar_kernel<<<1, 1, 0, stream>>>(a->loss_accum, loss3 + 2);
+    SEGS_LAUNCH_CHECK();
+    if (a->loss_terms_out) SEGS_CUDA_CHECK(cudaMemcpyAsync(a->loss_terms_out, loss3, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    if (P == 0) return SEGS_OK;          // nothing to back-propagate into
+    if ((rc = segs_loss_l1_ssim_backward(3, H, W, image, a->gt_image, a->row_mask, 1.f - lam, -lam, nullptr, lstate, dL_dimage, stream))) return rc;
+
+    // ---- rasterizer backward (RasterizeGaussiansBackwardCUDA) ----
+    const size_t Pz = size_t(P);
+    float* dL_dmean2D = a->dL_dmean2D_out ? a->dL_dmean2D_out : ws->take<float>(Pz * 3);
+    float* dL_dconic = ws->take<float>(Pz * 4);
+    float* dL_dopacity = ws->take<float>(Pz);
+    float* dL_dcolor = ws->take<float>(Pz * 3);
+    float* dL_dmean3D = ws->take<float>(Pz * 3);
+    float* dL_dcov3D = ws->take<float>(Pz * 6);
+    float* dL_dscale = ws->take<float>(Pz * 3);
+    float* dL_drot = ws->take<float>(Pz * 4);
+    if (!dL_dmean2D || !dL_dconic || !dL_dopacity || !dL_dcolor || !dL_dmean3D || !dL_dcov3D || !dL_dscale || !dL_drot) return oom();
+    if ((rc = segs_raster_backward(P, 0, 0, R, a->background, W, H, xyz, nullptr, color, scaling, 1.0f, rot, nullptr, a->viewmatrix,
+                                   a->projmatrix, a->campos, a->tan_fovx, a->tan_fovy, radii, geom.ptr, binning.ptr, img.ptr,
+                                   dL_dimage, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, nullptr,
+                                   dL_dscale, dL_drot, stream))) return rc;
+    if (a->radii_out) SEGS_CUDA_CHECK(cudaMemcpyAsync(a->radii_out, radii, Pz * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    // 0.01 * scaling.prod(1).mean(): value into the loss, gradient on top of the rasterizer's dL_dscale
+    if (a->scaling_reg_weight != 0.f)
+        if ((rc = segs_scaling_reg(P, scaling, a->scaling_reg_weight, nullptr, dL_dscale, a->loss_accum, stream))) return rc;
+
+    // ---- decode backward, accumulating into the bucket ----
+    // MLP weight gradients of THIS view go to a small arena block first (the appearance-embedding gradient is
+    // derived from this view's colour-bias gradient), then one launch adds all of them to the bucket.
+    const segs_decode_params& p = *a->params;
+    const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
+    const int in_c = 35 + (p.add_color_dist ? 1 : 0), ld_c = in_c + p.appearance_dim;
+    const size_t wn[18] = {size_t(32) * in_o, 32, 10 * 32, 10, size_t(32) * in_s, 32, 70 * 32, 70, size_t(32) * ld_c, 32, 30 * 32, 30,
+                           size_t(p.appearance_dim) * 7, size_t(p.appearance_dim), 32 * 4, 32, 3 * 32, 3};
+    size_t wtotal = 0;
+    for (int k = 0; k < 18; ++k) wtotal += (wn[k] + 3) & ~size_t(3);
+    float* wtmp = ws->take<float>(wtotal);
+    if (!wtmp) return oom();
+    segs_decode_grads tmp;
+    float** tmp_fields = reinterpret_cast<float**>(&tmp);
+    float* const* dst_fields = reinterpret_cast<float* const*>(a->grad_params);
+    {
+        size_t off = 0;
+        for (int k = 0; k < 18; ++k) { tmp_fields[k] = wtmp + off; off += (wn[k] + 3) & ~size_t(3); }
+    }
+    if ((rc = segs_decode_backward_ex(A, visible, a->anchor, a->anchor_feat, a->offset, a->scaling, a->campos, a->pose, a->params,
+                                      dstate, n_vis, P, dL_dmean3D, dL_dcolor, dL_dopacity, dL_dscale, dL_drot, nullptr,
+                                      a->grad_anchor, a->grad_anchor_feat, a->grad_offset, a->grad_scaling, &tmp, ws_alloc_cb, ws,
+                                      SEGS_DECODE_ACCUMULATE | (a->scaling_is_log ? SEGS_DECODE_LOG_SCALING : 0), stream))) return rc;
+    {
+        float* dst[18]; const float* src[18]; unsigned long long cnt[18];
+        int n = 0;
+        for (int k = 0; k < 18; ++k) {
+            const bool live = (k < 12) || (k < 14 && p.appearance_dim > 0) || (k >= 14 && p.use_feat_bank);
+            if (!live || !wn[k]) continue;
+            if (!dst_fields[k]) { set_error("mapper view: NULL weight-gradient destination %d", k); return SEGS_ERR_INVALID_ARG; }
+            dst[n] = dst_fields[k]; src[n] = tmp_fields[k]; cnt[n] = wn[k]; ++n;
+        }
+        if ((rc = segs_accumulate(n, dst, src, cnt, stream))) return rc;
+    }
+    return SEGS_OK;
+}
+
+}  // extern "C"

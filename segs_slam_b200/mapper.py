@@ -96,15 +96,21 @@ def mapping_step(params: Sequence[torch.Tensor], render_loss: Callable[[int], to
 
 
 def make_render_loss(pc, cameras, targets, image_height: int, image_width: int, tanfovx: float, tanfovy: float,
-                     bg: torch.Tensor):
+                     bg: torch.Tensor, loss: str = "l1", lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01,
+                     row_masks=None):
     """Per-view work of the mapper on this package's kernels: anchor prefilter
     (RasterizeGaussiansfilterCUDA, gaussian_renderer.cpp:131-199) -> fused decode
-    (generate_neural_gaussians, :214-334) -> rasterize (GaussianRasterizer, :40-127) -> L1 loss against
-    the keyframe image (loss_utils::l1_loss; SSIM and the frequency terms are §8f 'next').
+    (generate_neural_gaussians, :214-334) -> rasterize (GaussianRasterizer, :40-127) -> loss against the
+    keyframe image: loss="l1" is loss_utils::l1_loss alone; loss="l1_ssim" is the mapper's
+    (1-l)*L1 + l*(1-SSIM) + 0.01*scaling.prod(1).mean() (gaussian_mapper.cpp:908-925) on the fused loss
+    kernels (loss_utils.py).  The frequency terms (:927-942, off by default) are §8f 'next'.
 
     cameras[v] carries world_view_transform_, full_proj_transform_, camera_center_, t_, R_quaternion_."""
     from . import GaussianRasterizationSettings, GaussianRasterizer, generate_neural_gaussians
     from .rasterize_points import RasterizeGaussiansfilterCUDA
+    from . import loss_utils
+    if loss not in ("l1", "l1_ssim"):
+        raise ValueError(f"unknown loss '{loss}'")
 
     def render_loss(v: int) -> torch.Tensor:
         cam = cameras[v]
@@ -126,6 +132,140 @@ def make_render_loss(pc, cameras, targets, image_height: int, image_width: int, 
         means2D = torch.zeros_like(xyz, requires_grad=True)
         image, _radii = GaussianRasterizer(settings)(xyz, means2D, opacity, False, True, True, True, False, e, color,
                                                      scaling, rots, e)
-        return (image - targets[v]).abs().mean()
+        if loss == "l1":
+            return (image - targets[v]).abs().mean()
+        photometric = loss_utils.l1_ssim_loss(image, targets[v], lambda_dssim, None if row_masks is None else row_masks[v])[0]
+        return photometric + loss_utils.scaling_reg(scaling, scaling_reg_weight)
 
     return render_loss
+
+
+class FusedMapper:
+    """The keyframe-batched mapping step with the per-view work issued from C++ (`segs_mapper_view`,
+    csrc/mapper_view.cu): prefilter -> decode -> rasterize -> L1+SSIM (+ scaling regulariser) -> backward, the
+    parameter gradients accumulated straight into the flat bucket; then ONE all-reduce and ONE fused Adam launch
+    (`segs_adam_step`) that also applies the 1/B scale and clears the bucket.
+
+    Same mathematics as `mapping_step(params, make_render_loss(..., loss="l1_ssim"), ...)` — the autograd
+    composition of the tensor-level API, which stays the reference-shaped interface and is what
+    tests/test_mapper_gpu.py checks this class against — without ~150 interpreter-issued launches per view.
+
+    `pc` carries the reference GaussianModel's members (anchor_model.AnchorModel).  Trainable tensors, in bucket
+    order: _anchor, _offset, _anchor_feat, _scaling, then the MLP weights in segs_decode_params order
+    (gaussian_model.cpp:620-872 gives each its own learning rate; `lrs` follows the same order)."""
+
+    def __init__(self, pc, image_height: int, image_width: int, tanfovx: float, tanfovy: float, bg: torch.Tensor,
+                 lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None):
+        import ctypes as C
+        from . import _lib
+        from .gaussian_renderer import _weights
+        from .optim import FusedAdam
+        self._C, self._lib_mod, self.lib = C, _lib, _lib.load()
+        self.pc, self.group = pc, group
+        self.H, self.W, self.tanfovx, self.tanfovy = int(image_height), int(image_width), float(tanfovx), float(tanfovy)
+        self.bg = bg.to(torch.float32).contiguous()
+        self.lambda_dssim, self.scaling_reg_weight = float(lambda_dssim), float(scaling_reg_weight)
+        if not pc._anchor.is_cuda:
+            raise RuntimeError("segs_slam_b200 has no CPU path: the model must live on a CUDA device")
+        self.weights = _weights(pc)                                   # 18 entries, None = absent
+        self.params = [pc._anchor, pc._offset, pc._anchor_feat, pc._scaling] + [w for w in self.weights if w is not None]
+        for p in self.params:
+            if not p.is_contiguous():
+                raise RuntimeError("FusedMapper: parameters must be contiguous")
+        self.bucket = GradBucket(self.params)
+        self.optimizer = FusedAdam(self.bucket, lrs, eps=eps)
+        v = iter(self.bucket.views[4:])
+        self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
+        self.loss_accum = torch.zeros((), dtype=torch.float32, device=pc._anchor.device)
+        ws = C.c_void_p()
+        _lib.check(self.lib.segs_workspace_create(C.byref(ws)))
+        self._ws = ws
+        self.last_result = None
+        self._dirty = False                                           # the bucket starts zeroed
+
+    def __del__(self):
+        try:
+            if getattr(self, "_ws", None):
+                self.lib.segs_workspace_destroy(self._ws)
+                self._ws = None
+        except Exception:
+            pass
+
+    def workspace_bytes(self) -> int:
+        return int(self.lib.segs_workspace_bytes(self._ws))
+
+    def _prepare(self):
+        """Per-step derived tensors (the parameters do not change between the views of one step)."""
+        pc = self.pc
+        with torch.no_grad():
+            self._scaling = torch.exp(pc._scaling)                    # get_scaling
+            self._fscales = self._scaling[:, :3].contiguous()
+            if hasattr(pc, "_rotation"):
+                self._frot = torch.nn.functional.normalize(pc._rotation).contiguous()
+            else:
+                self._frot = torch.tensor([1.0, 0.0, 0.0, 0.0], device=pc._anchor.device).repeat(pc._anchor.size(0), 1)
+        C, L = self._C, self._lib_mod
+        ptr = lambda t: None if t is None else t.data_ptr()
+        cfg = (int(getattr(pc, "appearance_dim", 0)), int(bool(getattr(pc, "use_feat_bank", False))),
+               int(bool(getattr(pc, "add_opacity_dist", False))), int(bool(getattr(pc, "add_cov_dist", False))),
+               int(bool(getattr(pc, "add_color_dist", False))))
+        self._dparams = L.DecodeParams(*[ptr(w) for w in self.weights], *cfg)
+        self._dgrads = L.DecodeGrads(*[ptr(g) for g in self._wgrad_views])
+        a = L.MapperViewArgs()
+        a.A = pc._anchor.size(0)
+        a.anchor, a.anchor_feat, a.offset = pc._anchor.data_ptr(), pc._anchor_feat.data_ptr(), pc._offset.data_ptr()
+        a.scaling, a.scaling_is_log = self._scaling.data_ptr(), 1
+        a.filter_scales, a.filter_rotations = self._fscales.data_ptr(), self._frot.data_ptr()
+        a.params = C.pointer(self._dparams)
+        a.width, a.height, a.tan_fovx, a.tan_fovy = self.W, self.H, self.tanfovx, self.tanfovy
+        a.background = self.bg.data_ptr()
+        a.lambda_dssim, a.scaling_reg_weight = self.lambda_dssim, self.scaling_reg_weight
+        v = self.bucket.views
+        a.grad_anchor, a.grad_offset, a.grad_anchor_feat, a.grad_scaling = (v[0].data_ptr(), v[1].data_ptr(),
+                                                                             v[2].data_ptr(), v[3].data_ptr())
+        a.grad_params = C.pointer(self._dgrads)
+        a.loss_accum = self.loss_accum.data_ptr()
+        self._args = a
+
+    def render_view(self, cam, target: torch.Tensor, row_mask: torch.Tensor | None = None, image_out=None,
+                    loss_terms_out=None):
+        """One view: accumulates gradients and the loss.  `_prepare()` must have run this step."""
+        C, L = self._C, self._lib_mod
+        a = self._args
+        a.viewmatrix, a.projmatrix = cam.world_view_transform_.data_ptr(), cam.full_proj_transform_.data_ptr()
+        a.campos = cam.camera_center_.data_ptr()
+        t, q = cam.t_, cam.R_quaternion_
+        pose = (C.c_float * 7)(float(t[0]), float(t[1]), float(t[2]), float(q[0]), float(q[1]), float(q[2]), float(q[3]))
+        a.pose = pose
+        a.gt_image = target.data_ptr()
+        a.row_mask = None if row_mask is None else row_mask.data_ptr()
+        a.image_out = None if image_out is None else image_out.data_ptr()
+        a.loss_terms_out = None if loss_terms_out is None else loss_terms_out.data_ptr()
+        res = L.MapperViewResult()
+        dev = self.bucket.flat.device
+        with torch.cuda.device(dev):
+            L.check(self.lib.segs_mapper_view(self._ws, C.byref(a), C.byref(res), torch.cuda.current_stream().cuda_stream))
+        self.last_result = res
+        return res
+
+    def step(self, cameras, targets, row_masks=None, n_views: int | None = None, optimize: bool = True):
+        """One batched step over `cameras` (all ranks pass the full list; each renders its partition).
+        -> mean loss over the batch (device scalar)."""
+        n_views = len(cameras) if n_views is None else n_views
+        world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
+        rank = dist.get_rank(self.group) if world > 1 else 0
+        self._prepare()
+        self.loss_accum.zero_()
+        if self._dirty:
+            self.bucket.zero_()                                      # normally cleared by the previous Adam launch
+        self._dirty = True
+        for v in partition_views(n_views, world, rank):
+            self.render_view(cameras[v], targets[v], None if row_masks is None else row_masks[v])
+        loss = self.loss_accum.clone()
+        if world > 1:
+            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+        if optimize:
+            self.optimizer.step(grad_scale=1.0 / float(n_views), zero_grad=True)
+            self._dirty = False
+        return loss / float(n_views)

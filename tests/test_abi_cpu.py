@@ -87,3 +87,22 @@ def test_libtorch_shim_exports_reference_entry_points():
     with pytest.raises(RuntimeError, match="exactly one of either scale/rotation pair"):
         shim.rasterizer_forward(16, 16, 1.0, 1.0, torch.zeros(3), 1.0, torch.eye(4), torch.eye(4), 0, torch.zeros(3),
                                 False, x, x, x[:, :1], e, x, x, e, e)
+
+
+def test_mapper_view_rejects_null_arguments():
+    """Host-side validation of the fused mapper entry points needs no GPU."""
+    import ctypes as C
+    from segs_slam_b200 import _lib
+    lib = _lib.load()
+    ws = C.c_void_p()
+    assert lib.segs_workspace_create(C.byref(ws)) == 0
+    assert lib.segs_workspace_bytes(ws) == 0
+    args, res = _lib.MapperViewArgs(), _lib.MapperViewResult()
+    assert lib.segs_mapper_view(ws, C.byref(args), C.byref(res), None) != 0
+    assert b"invalid sizes" in lib.segs_last_error()
+    args.A, args.width, args.height = 10, 16, 16
+    assert lib.segs_mapper_view(ws, C.byref(args), C.byref(res), None) != 0
+    assert b"NULL required pointer" in lib.segs_last_error()
+    assert lib.segs_workspace_destroy(ws) == 0
+    assert lib.segs_loss_state_bytes(3, 680, 1200) > 3 * 3 * 680 * 1200 * 4
+    assert lib.segs_adam_step(1, None, None, None, None, 1.0, 0, None) != 0

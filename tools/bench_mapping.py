@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--views", type=int, default=64)
 ap.add_argument("--anchors", type=int, default=200_000)
+ap.add_argument("--path", default="fused", choices=["fused", "autograd", "autograd-l1"])
 args = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
 torch.cuda.set_device(local)
@@ -31,9 +32,19 @@ g = torch.Generator(device="cpu").manual_seed(1)
 target = (torch.rand(3, H, W, generator=g) * 0.5).to(dev)
 targets = [target] * args.views
 bg = torch.zeros(3, device=dev)
-render_loss = mapper.make_render_loss(model, cams, targets, H, W, tanx, tany, bg)
-params = [p for p in model.parameters() if p.requires_grad]
-opt = torch.optim.Adam(params, lr=1e-4)
+if args.path == "fused":
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lrs=1e-4)
+    class _B:  # noqa: E701
+        flat = fm.bucket.flat
+    def one_step(bucket):
+        return fm.step(cams, targets), _B
+else:
+    render_loss = mapper.make_render_loss(model, cams, targets, H, W, tanx, tany, bg,
+                                          loss="l1" if args.path == "autograd-l1" else "l1_ssim")
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    def one_step(bucket):
+        return mapper.mapping_step(params, render_loss, args.views, opt, bucket)
 bucket = None
 
 def sync():
@@ -42,14 +53,14 @@ def sync():
         dist.barrier()
     torch.cuda.synchronize()
 
-loss, bucket = mapper.mapping_step(params, render_loss, args.views, opt, bucket)     # warm-up step
+loss, bucket = one_step(bucket)     # warm-up step
 sync()
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 t0 = time.perf_counter()
 e0.record()
 losses = []
 for _ in range(args.steps):
-    loss, bucket = mapper.mapping_step(params, render_loss, args.views, opt, bucket)
+    loss, bucket = one_step(bucket)
     losses.append(float(loss))
 e1.record()
 sync()
@@ -59,7 +70,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"metric": "mapping keyframes/s (C4: 64 keyframes, 1200x680, C3 anchor model)", "n_gpus": world,
-                      "views_per_step": args.views, "steps": args.steps, "anchors": args.anchors,
+                      "views_per_step": args.views, "path": args.path, "steps": args.steps, "anchors": args.anchors,
                       "value": round(args.views * args.steps / (float(t.item()) * 1e-3), 2), "unit": "keyframes/s",
                       "ms_per_step": round(float(t.item()) / args.steps, 2), "scaling": "strong",
                       "bucket_MB": round(bucket.flat.numel() * 4 / 1e6, 1), "losses": [round(x, 5) for x in losses]}))

@@ -15,16 +15,22 @@ model = anchor_model.synth_anchor_model(200_000, W, H, fx, fx, 1003, device=dev)
 cams = anchor_model.circle_keyframes(64, 1.5, (0.0, 0.0, 3.25), tanx, tany, dev)[:NV]
 g = torch.Generator(device="cpu").manual_seed(1)
 target = (torch.rand(3, H, W, generator=g) * 0.5).to(dev)
-kw = {} if loss_kind == "default" else {"loss": loss_kind}
-render_loss = mapper.make_render_loss(model, cams, [target] * NV, H, W, tanx, tany, torch.zeros(3, device=dev), **kw)
-params = [p for p in model.parameters() if p.requires_grad]
-opt = torch.optim.Adam(params, lr=1e-4)
-bucket = None
+if loss_kind == "fused":
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, torch.zeros(3, device=dev), lrs=1e-4)
+    step = lambda: fm.step(cams, [target] * NV)
+else:
+    kw = {} if loss_kind == "default" else {"loss": loss_kind}
+    render_loss = mapper.make_render_loss(model, cams, [target] * NV, H, W, tanx, tany, torch.zeros(3, device=dev), **kw)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4)
+    state = {"b": None}
+    def step():
+        loss, state["b"] = mapper.mapping_step(params, render_loss, NV, opt, state["b"])
 for _ in range(3):
-    loss, bucket = mapper.mapping_step(params, render_loss, NV, opt, bucket)
+    step()
 torch.cuda.synchronize()
 with profile(activities=[ProfilerActivity.CUDA, ProfilerActivity.CPU]) as prof:
-    loss, bucket = mapper.mapping_step(params, render_loss, NV, opt, bucket)
+    step()
     torch.cuda.synchronize()
 path = os.path.join(tempfile.gettempdir(), "trace_map.json")
 prof.export_chrome_trace(path)
