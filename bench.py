@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-mapping", action="store_true", help="skip the keyframe-batched mapping measurement")
+    ap.add_argument("--mapping-steps", type=int, default=3)
     return ap.parse_args()
 
 
@@ -386,6 +388,10 @@ def main():
     e2e_value = VIEWS_PER_STEP * e2e_steps * n_ranks / (float(t.item()) * 1e-3)
     clocks = sampler.stop() if rank == 0 else None
 
+    mapping = None
+    if not args.no_mapping:
+        mapping = mapping_ours(args, dev, rank, n_ranks, distributed) if args.impl == "ours" else mapping_reference(args, dev)
+
     if rank != 0:
         if distributed:
             dist.destroy_process_group()
@@ -436,6 +442,8 @@ def main():
                             "compute stream; drained inside the timed region"},
         "gpu_launches": int(launches),
     }
+    if mapping is not None:
+        line["mapping"] = mapping
     if args.impl != "ours":
         line["impl"] = "reference"
         line["gpu_launches"] = 0
@@ -451,6 +459,102 @@ def main():
     if distributed and args.impl == "ours":
         dist.destroy_process_group()
     return 0
+
+
+MAP_VIEWS, MAP_ANCHORS = 64, 200_000
+
+
+def _mapping_setup(dev):
+    """BASELINE config 4: 64 keyframes at 1200x680 on a 1.5 m circle around the C3 anchor model."""
+    import torch
+    from segs_slam_b200 import anchor_model
+    W, H, fx = 1200, 680, 600.0
+    tanx, tany = W / (2 * fx), H / (2 * fx)
+    model = anchor_model.synth_anchor_model(MAP_ANCHORS, W, H, fx, fx, 1003, device=dev)
+    cams = anchor_model.circle_keyframes(MAP_VIEWS, 1.5, (0.0, 0.0, 3.25), tanx, tany, dev)
+    g = torch.Generator(device="cpu").manual_seed(1)
+    target = (torch.rand(3, H, W, generator=g) * 0.5).to(dev)
+    return model, cams, [target] * MAP_VIEWS, (W, H, tanx, tany)
+
+
+def mapping_ours(args, dev, rank, n_ranks, distributed):
+    """Mapping keyframes/s (the second half of BASELINE.json's metric): the keyframe-batched step of
+    segs_slam_b200.mapper.FusedMapper — per view prefilter -> fused decode -> rasterize -> L1+SSIM+scaling
+    regulariser -> backward (segs_mapper_view), ONE NCCL all-reduce of the flat gradient bucket, ONE fused Adam
+    launch.  Strong scaling: the 64 views are partitioned across the ranks."""
+    import torch
+    import torch.distributed as dist
+    from segs_slam_b200 import _lib, mapper
+    model, cams, targets, (W, H, tanx, tany) = _mapping_setup(dev)
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, torch.zeros(3, device=dev), lambda_dssim=0.2, lrs=1e-4)
+
+    def barrier():
+        torch.cuda.synchronize()
+        if distributed:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(2):
+        fm.step(cams, targets)
+    barrier()
+    lib = _lib.load()
+    l0 = lib.segs_launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    losses = [fm.step(cams, targets) for _ in range(args.mapping_steps)]
+    e1.record()
+    barrier()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    t = torch.tensor([ms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    return {"metric": "mapping keyframes/s", "value": round(MAP_VIEWS * args.mapping_steps / (ms * 1e-3), 2),
+            "unit": "keyframes/s", "n_gpus": n_ranks, "views_per_step": MAP_VIEWS, "steps": args.mapping_steps,
+            "ms_per_step": round(ms / args.mapping_steps, 3), "scaling": "strong",
+            "config": {"workload": "C4: 64 keyframes 1200x680, C3 anchor model (200k anchors x 10 offsets, appearance "
+                                   "embedding + feature bank)", "loss": "0.8 L1 + 0.2 (1 - SSIM) + 0.01 scaling regulariser",
+                       "optimizer": "fused Adam, one step per 64-keyframe batch", "bucket_MB": round(fm.bucket.flat.numel() * 4 / 1e6, 1)},
+            "losses": [round(float(x), 5) for x in losses],
+            "gpu_launches_per_rank": int(lib.segs_launch_count() - l0)}
+
+
+def mapping_reference(args, dev):
+    """The reference's own mapping iteration (one keyframe, one optimizer step: gaussian_mapper.cpp:823-1032) over the
+    unmodified reference rasterizer kernels and the ATen op sequences of its LibTorch host code (tests/ref_mapper.py).
+    Single GPU (the reference has no multi-GPU mapper)."""
+    import torch
+    try:
+        import ref_mapper
+        import decode_oracle
+    except Exception as exc:                                   # oracle/_ref absent
+        return {"unavailable": f"{type(exc).__name__}: {exc}"}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    model, cams, targets, (W, H, tanx, tany) = _mapping_setup(dev)
+    # the decode oracle reads its configuration from `cfg`
+    model.cfg = decode_oracle.DecodeConfig(appearance_dim=model.appearance_dim, use_feat_bank=model.use_feat_bank)
+    params = [p for p in model.parameters() if p.requires_grad]
+    opt = torch.optim.Adam(params, lr=1e-4, eps=1e-15)
+    bg = torch.zeros(3, device=dev)
+    n = min(MAP_VIEWS, 16 * args.mapping_steps)
+    for v in range(3):
+        ref_mapper.iteration(model, cams[v], targets[v], H, W, tanx, tany, bg, opt)
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t0 = time.perf_counter()
+    e0.record()
+    losses = [ref_mapper.iteration(model, cams[v % MAP_VIEWS], targets[v % MAP_VIEWS], H, W, tanx, tany, bg, opt) for v in range(n)]
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3)
+    return {"metric": "mapping keyframes/s", "value": round(n / (ms * 1e-3), 2), "unit": "keyframes/s", "n_gpus": 1,
+            "views_per_step": 1, "steps": n, "ms_per_step": round(ms / n, 3), "scaling": "strong",
+            "config": {"workload": "C4 keyframes, C3 anchor model; the reference's iteration: one keyframe per optimizer step, "
+                                   "unmodified reference rasterizer kernels + ATen decode/loss/Adam (tests/ref_mapper.py)",
+                       "loss": "0.8 L1 + 0.2 (1 - SSIM) + 0.01 scaling regulariser"},
+            "losses": [round(float(x), 5) for x in losses[:4]]}
 
 
 def _gpu_reference_available():

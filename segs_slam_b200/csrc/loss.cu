@@ -269,9 +269,17 @@ scaling_reg_kernel(int n, const float* __restrict__ scaling, float weight, const
         }
     }
     if (reg_out) {
+        // one atomic per CTA (a single address: per-warp atomics serialise in L2)
+        __shared__ float s_p[8];
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) p += __shfl_xor_sync(0xFFFFFFFFu, p, o);
-        if ((threadIdx.x & 31) == 0 && p != 0.f) atomicAdd(reg_out, p * (weight / float(n)));
+        if ((threadIdx.x & 31) == 0) s_p[threadIdx.x >> 5] = p;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            float t = 0.f;
+            for (int w = 0; w < 8; ++w) t += s_p[w];
+            if (t != 0.f) atomicAdd(reg_out, t * (weight / float(n)));
+        }
     }
 }
 
