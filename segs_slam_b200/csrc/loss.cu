@@ -12,7 +12,8 @@
 // The reference runs 5 grouped 11x11 conv2d (121 taps each) + ~25 elementwise ATen kernels forward
 // and the same again backward, with ~12 image-sized temporaries; here the 11x11 Gaussian window
 // (sigma 1.5, zero padding 5: loss_utils.h:50-75, 85-87) is applied separably out of shared
-// memory and the only temporaries are the three derivative maps.
+// memory (horizontal pass: 4 outputs per thread sliding over 14 registers fed by LDS.128; vertical pass: two
+// rows per thread) and the only temporaries are the three derivative maps.
 //
 // SSIM algebra (per pixel, per channel; mu = G*x etc., G = the window):
 //   a = 2 mu1 mu2 + C1, b = 2 s12 + C2, c = mu1^2 + mu2^2 + C1, d = s1 + s2 + C2   (s1 = G*x^2 - mu1^2 ...)
@@ -29,11 +30,16 @@ namespace segs {
 
 namespace {
 
-constexpr int LT = 16;                 // tile side
+constexpr int TX = 32, TY = 16;        // output tile of one 256-thread CTA (two rows of one column per thread)
+constexpr int LTHREADS = 256;
 constexpr int HALO = 5;                // window 11
-constexpr int LW = LT + 2 * HALO;      // 26
+constexpr int LWX = TX + 2 * HALO;     // 42 staged columns
+constexpr int LWY = TY + 2 * HALO;     // 26 staged rows
 constexpr int WIN = 11;
-constexpr int LS = 48;                 // shared row stride: the two 16-wide half-warps of the horizontal pass hit disjoint banks
+constexpr int LS = 44;                 // shared row stride in floats: 16-byte aligned rows for LDS.128
+constexpr int RUN = 4;                 // outputs per thread in the horizontal pass (14 inputs -> 4 x LDS.128)
+constexpr int HRUNS = LWY * (TX / RUN);   // 208 row segments
+static_assert(HRUNS <= LTHREADS, "one horizontal run per thread");
 
 struct Window { float w[WIN]; };
 
@@ -78,73 +84,121 @@ __device__ __forceinline__ float masked_load(const float* __restrict__ img, cons
     return v;
 }
 
-__global__ void __launch_bounds__(LT * LT)
+// horizontal 11-tap pass of one row segment: 4 outputs from 14 staged inputs (read as 4 x float4)
+__device__ __forceinline__ void load_run(const float* row, float (&v)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const float4 t = reinterpret_cast<const float4*>(row)[q];
+        v[4 * q] = t.x; v[4 * q + 1] = t.y; v[4 * q + 2] = t.z; v[4 * q + 3] = t.w;
+    }
+}
+
+__global__ void __launch_bounds__(LTHREADS)
 ssim_l1_forward_kernel(int C, int H, int W, const float* __restrict__ image, const float* __restrict__ gt,
                        const float* __restrict__ row_mask, const Window win, float w_l1, float w_ssim, float bias,
                        LossState st, float* __restrict__ loss_out)
 {
-    __shared__ float sx[LW][LS];
-    __shared__ float sy[LW][LS];
-    __shared__ float hb[5][LW][LT];
-    __shared__ double s_red[2][LT * LT / 32];
+    __shared__ __align__(16) float sx[LWY][LS];
+    __shared__ __align__(16) float sy[LWY][LS];
+    __shared__ __align__(16) float hb[5][LWY][TX];
+    __shared__ double s_red[2][LTHREADS / 32];
     __shared__ bool s_last;
 
     const int tid = threadIdx.x;
-    const int tx = tid & (LT - 1), ty = tid >> 4;
     const int ch = blockIdx.z;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
 
-    for (int i = tid; i < LW * LW; i += LT * LT) {
-        const int r = i / LW, c = i - r * LW;
-        sx[r][c] = masked_load(image, row_mask, ch, y0 + r - HALO, x0 + c - HALO, H, W);
-        // gaussian_mapper.cpp:915: gt * mask == gt (masked rows of gt are all-zero by construction), but the
-        // product is applied anyway so arbitrary masks behave like the reference
-        sy[r][c] = masked_load(gt, row_mask, ch, y0 + r - HALO, x0 + c - HALO, H, W);
-    }
-    __syncthreads();
-    // horizontal pass: 26 rows x 16 columns x 5 quantities
-    for (int i = tid; i < LW * LT; i += LT * LT) {
-        const int r = i >> 4, c = i & (LT - 1);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f, a4 = 0.f;
+    // staging: thread = (column c of 64, row phase r0 of 4); no divisions, one pointer bump per row
+    {
+        const int c = tid & 63, r0 = tid >> 6;
+        const int gx = x0 + c - HALO;
+        const bool col_ok = c < LWX && gx >= 0 && gx < W;
+        if (c < LS) {
 #pragma unroll
-        for (int k = 0; k < WIN; ++k) {
-            const float x = sx[r][c + k], y = sy[r][c + k], w = win.w[k];
-            a0 = fmaf(w, x, a0);
-            a1 = fmaf(w, y, a1);
-            a2 = fmaf(w, x * x, a2);
-            a3 = fmaf(w, y * y, a3);
-            a4 = fmaf(w, x * y, a4);
+            for (int it = 0; it < (LWY + 3) / 4; ++it) {
+                const int r = r0 + 4 * it;
+                if (r < LWY) {
+                    const int gy = y0 + r - HALO;
+                    float vx = 0.f, vy = 0.f;
+                    if (col_ok && gy >= 0 && gy < H) {
+                        // gaussian_mapper.cpp:915: gt * mask == gt (masked rows of gt are all-zero by construction), but
+                        // the product is applied anyway so arbitrary masks behave like the reference
+                        const float m = row_mask ? __ldg(row_mask + ch * H + gy) : 1.f;
+                        const size_t o = (size_t(ch) * H + gy) * W + gx;
+                        vx = __ldg(image + o) * m;
+                        vy = __ldg(gt + o) * m;
+                    }
+                    sx[r][c] = vx;
+                    sy[r][c] = vy;
+                }
+            }
         }
-        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2; hb[3][r][c] = a3; hb[4][r][c] = a4;
     }
     __syncthreads();
-    float mu1 = 0.f, mu2 = 0.f, e11 = 0.f, e22 = 0.f, e12 = 0.f;
+    // horizontal pass: 26 rows x 8 segments of 4 outputs x 5 quantities, sliding over registers
+    if (tid < HRUNS) {
+        const int r = tid / (TX / RUN), c0 = (tid % (TX / RUN)) * RUN;
+        float x[16], y[16];
+        load_run(&sx[r][c0], x);
+        load_run(&sy[r][c0], y);
+        float a[5][RUN];
 #pragma unroll
-    for (int k = 0; k < WIN; ++k) {
-        const float w = win.w[k];
-        mu1 = fmaf(w, hb[0][ty + k][tx], mu1);
-        mu2 = fmaf(w, hb[1][ty + k][tx], mu2);
-        e11 = fmaf(w, hb[2][ty + k][tx], e11);
-        e22 = fmaf(w, hb[3][ty + k][tx], e22);
-        e12 = fmaf(w, hb[4][ty + k][tx], e12);
+        for (int o = 0; o < RUN; ++o) { a[0][o] = a[1][o] = a[2][o] = a[3][o] = a[4][o] = 0.f; }
+#pragma unroll
+        for (int k = 0; k < RUN + WIN - 1; ++k) {
+            const float xx = x[k] * x[k], yy = y[k] * y[k], xy = x[k] * y[k];
+#pragma unroll
+            for (int o = 0; o < RUN; ++o) {
+                const int tap = k - o;
+                if (tap >= 0 && tap < WIN) {
+                    const float w = win.w[tap];
+                    a[0][o] = fmaf(w, x[k], a[0][o]);
+                    a[1][o] = fmaf(w, y[k], a[1][o]);
+                    a[2][o] = fmaf(w, xx, a[2][o]);
+                    a[3][o] = fmaf(w, yy, a[3][o]);
+                    a[4][o] = fmaf(w, xy, a[4][o]);
+                }
+            }
+        }
+#pragma unroll
+        for (int q = 0; q < 5; ++q)
+            *reinterpret_cast<float4*>(&hb[q][r][c0]) = make_float4(a[q][0], a[q][1], a[q][2], a[q][3]);
     }
-    const int px = x0 + tx, py = y0 + ty;
-    const bool inside = px < W && py < H;
+    __syncthreads();
+    // vertical pass: thread = column tx, output rows 2*ty and 2*ty + 1 (12 staged rows feed both)
+    const int tx = tid & (TX - 1), ty2 = (tid >> 5) * 2;
+    float m[5][2];
+#pragma unroll
+    for (int q = 0; q < 5; ++q) {
+        float v[WIN + 1];
+#pragma unroll
+        for (int k = 0; k < WIN + 1; ++k) v[k] = hb[q][ty2 + k][tx];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) { s0 = fmaf(win.w[k], v[k], s0); s1 = fmaf(win.w[k], v[k + 1], s1); }
+        m[q][0] = s0; m[q][1] = s1;
+    }
     double l1 = 0.0, ss = 0.0;
-    if (inside) {
-        const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;          // loss_utils.h:101-102
-        const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
-        const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
-        const float a = 2.f * mu12 + C1, b = 2.f * s12 + C2;
-        const float c = mu1_sq + mu2_sq + C1, d = s1 + s2 + C2;
-        const float rcd = 1.f / (c * d);
-        const float ssim = a * b * rcd;                              // loss_utils.h:104
-        const size_t o = (size_t(ch) * H + py) * W + px;
-        st.m1[o] = 2.f * mu2 * (b - a) * rcd - 2.f * mu1 * ssim * (d - c) * rcd;
-        st.m2[o] = -ssim / d;
-        st.m3[o] = 2.f * a * rcd;
-        l1 = (double)fabsf(sx[ty + HALO][tx + HALO] - sy[ty + HALO][tx + HALO]);
-        ss = (double)ssim;
+    const int px = x0 + tx;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int py = y0 + ty2 + j;
+        if (px < W && py < H) {
+            const float mu1 = m[0][j], mu2 = m[1][j], e11 = m[2][j], e22 = m[3][j], e12 = m[4][j];
+            const float C1 = 0.01f * 0.01f, C2 = 0.03f * 0.03f;          // loss_utils.h:101-102
+            const float mu1_sq = mu1 * mu1, mu2_sq = mu2 * mu2, mu12 = mu1 * mu2;
+            const float s1 = e11 - mu1_sq, s2 = e22 - mu2_sq, s12 = e12 - mu12;
+            const float a = 2.f * mu12 + C1, b = 2.f * s12 + C2;
+            const float c = mu1_sq + mu2_sq + C1, d = s1 + s2 + C2;
+            const float rcd = 1.f / (c * d);
+            const float ssim = a * b * rcd;                              // loss_utils.h:104
+            const size_t o = (size_t(ch) * H + py) * W + px;
+            st.m1[o] = 2.f * mu2 * (b - a) * rcd - 2.f * mu1 * ssim * (d - c) * rcd;
+            st.m2[o] = -ssim / d;
+            st.m3[o] = 2.f * a * rcd;
+            l1 += (double)fabsf(sx[ty2 + j + HALO][tx + HALO] - sy[ty2 + j + HALO][tx + HALO]);
+            ss += (double)ssim;
+        }
     }
     // deterministic reduction: lanes -> warps -> CTA partial -> (last CTA) fixed-order total
 #pragma unroll
@@ -158,7 +212,7 @@ ssim_l1_forward_kernel(int C, int H, int W, const float* __restrict__ image, con
     const unsigned bid = (blockIdx.z * gridDim.y + blockIdx.y) * gridDim.x + blockIdx.x;
     if (tid == 0) {
         double t1 = 0.0, t2 = 0.0;
-        for (int w = 0; w < LT * LT / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+        for (int w = 0; w < LTHREADS / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
         st.partial[2 * bid] = t1;
         st.partial[2 * bid + 1] = t2;
         __threadfence();
@@ -168,7 +222,7 @@ ssim_l1_forward_kernel(int C, int H, int W, const float* __restrict__ image, con
     if (!s_last) return;
     __threadfence();
     double t1 = 0.0, t2 = 0.0;
-    for (unsigned i = tid; i < blocks; i += LT * LT) {
+    for (unsigned i = tid; i < blocks; i += LTHREADS) {
         t1 += __ldcg(st.partial + 2 * i);
         t2 += __ldcg(st.partial + 2 * i + 1);
     }
@@ -182,7 +236,7 @@ ssim_l1_forward_kernel(int C, int H, int W, const float* __restrict__ image, con
     __syncthreads();
     if (tid == 0) {
         t1 = 0.0; t2 = 0.0;
-        for (int w = 0; w < LT * LT / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
+        for (int w = 0; w < LTHREADS / 32; ++w) { t1 += s_red[0][w]; t2 += s_red[1][w]; }
         const double n = double(C) * H * W;
         const float l1_mean = float(t1 / n), ssim_mean = float(t2 / n);
         loss_out[0] = l1_mean;
@@ -196,59 +250,85 @@ __device__ __forceinline__ float map_load(const float* __restrict__ m, int ch, i
     return __ldg(m + (size_t(ch) * H + y) * W + x);
 }
 
-__global__ void __launch_bounds__(LT * LT)
+__global__ void __launch_bounds__(LTHREADS)
 ssim_l1_backward_kernel(int C, int H, int W, const float* __restrict__ image, const float* __restrict__ gt,
                         const float* __restrict__ row_mask, const Window win, float w_l1, float w_ssim,
                         const float* __restrict__ dL_dloss, LossState st, float* __restrict__ dL_dimage)
 {
-    __shared__ float sm[3][LW][LS];
-    __shared__ float hb[3][LW][LT];
+    __shared__ __align__(16) float sm[3][LWY][LS];
+    __shared__ __align__(16) float hb[3][LWY][TX];
 
     const int tid = threadIdx.x;
-    const int tx = tid & (LT - 1), ty = tid >> 4;
     const int ch = blockIdx.z;
-    const int x0 = blockIdx.x * LT, y0 = blockIdx.y * LT;
+    const int x0 = blockIdx.x * TX, y0 = blockIdx.y * TY;
 
-    for (int i = tid; i < LW * LW; i += LT * LT) {
-        const int r = i / LW, c = i - r * LW;
-        const int gy = y0 + r - HALO, gx = x0 + c - HALO;
-        sm[0][r][c] = map_load(st.m1, ch, gy, gx, H, W);
-        sm[1][r][c] = map_load(st.m2, ch, gy, gx, H, W);
-        sm[2][r][c] = map_load(st.m3, ch, gy, gx, H, W);
-    }
-    __syncthreads();
-    for (int i = tid; i < LW * LT; i += LT * LT) {
-        const int r = i >> 4, c = i & (LT - 1);
-        float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+    {
+        const int c = tid & 63, r0 = tid >> 6;
+        const int gx = x0 + c - HALO;
+        const bool col_ok = c < LWX && gx >= 0 && gx < W;
+        if (c < LS) {
 #pragma unroll
-        for (int k = 0; k < WIN; ++k) {
-            const float w = win.w[k];
-            a0 = fmaf(w, sm[0][r][c + k], a0);
-            a1 = fmaf(w, sm[1][r][c + k], a1);
-            a2 = fmaf(w, sm[2][r][c + k], a2);
+            for (int it = 0; it < (LWY + 3) / 4; ++it) {
+                const int r = r0 + 4 * it;
+                if (r < LWY) {
+                    const int gy = y0 + r - HALO;
+                    float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+                    if (col_ok && gy >= 0 && gy < H) {
+                        const size_t o = (size_t(ch) * H + gy) * W + gx;
+                        v0 = __ldg(st.m1 + o); v1 = __ldg(st.m2 + o); v2 = __ldg(st.m3 + o);
+                    }
+                    sm[0][r][c] = v0; sm[1][r][c] = v1; sm[2][r][c] = v2;
+                }
+            }
         }
-        hb[0][r][c] = a0; hb[1][r][c] = a1; hb[2][r][c] = a2;
     }
     __syncthreads();
-    const int px = x0 + tx, py = y0 + ty;
-    if (px >= W || py >= H) return;
-    float c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    if (tid < HRUNS) {
+        const int r = tid / (TX / RUN), c0 = (tid % (TX / RUN)) * RUN;
 #pragma unroll
-    for (int k = 0; k < WIN; ++k) {
-        const float w = win.w[k];
-        c1 = fmaf(w, hb[0][ty + k][tx], c1);
-        c2 = fmaf(w, hb[1][ty + k][tx], c2);
-        c3 = fmaf(w, hb[2][ty + k][tx], c3);
+        for (int q = 0; q < 3; ++q) {
+            float v[16];
+            load_run(&sm[q][r][c0], v);
+            float a[RUN] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+            for (int k = 0; k < RUN + WIN - 1; ++k) {
+#pragma unroll
+                for (int o = 0; o < RUN; ++o) {
+                    const int tap = k - o;
+                    if (tap >= 0 && tap < WIN) a[o] = fmaf(win.w[tap], v[k], a[o]);
+                }
+            }
+            *reinterpret_cast<float4*>(&hb[q][r][c0]) = make_float4(a[0], a[1], a[2], a[3]);
+        }
+    }
+    __syncthreads();
+    const int tx = tid & (TX - 1), ty2 = (tid >> 5) * 2;
+    float cq[3][2];
+#pragma unroll
+    for (int q = 0; q < 3; ++q) {
+        float v[WIN + 1];
+#pragma unroll
+        for (int k = 0; k < WIN + 1; ++k) v[k] = hb[q][ty2 + k][tx];
+        float s0 = 0.f, s1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < WIN; ++k) { s0 = fmaf(win.w[k], v[k], s0); s1 = fmaf(win.w[k], v[k + 1], s1); }
+        cq[q][0] = s0; cq[q][1] = s1;
     }
     const float up = dL_dloss ? __ldg(dL_dloss) : 1.f;
     const float inv_n = 1.f / (float(C) * float(H) * float(W));
-    const size_t o = (size_t(ch) * H + py) * W + px;
-    const float m = row_mask ? __ldg(row_mask + ch * H + py) : 1.f;
-    const float x = __ldg(image + o) * m, y = __ldg(gt + o) * m;
-    const float diff = x - y;
-    const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);   // abs backward: sign(0) = 0
-    const float g = (w_ssim * inv_n) * (c1 + 2.f * x * c2 + y * c3) + (w_l1 * inv_n) * sgn;
-    dL_dimage[o] = up * m * g;
+    const int px = x0 + tx;
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+        const int py = y0 + ty2 + j;
+        if (px >= W || py >= H) continue;
+        const size_t o = (size_t(ch) * H + py) * W + px;
+        const float m = row_mask ? __ldg(row_mask + ch * H + py) : 1.f;
+        const float x = __ldg(image + o) * m, y = __ldg(gt + o) * m;
+        const float diff = x - y;
+        const float sgn = diff > 0.f ? 1.f : (diff < 0.f ? -1.f : 0.f);   // abs backward: sign(0) = 0
+        const float g = (w_ssim * inv_n) * (cq[0][j] + 2.f * x * cq[1][j] + y * cq[2][j]) + (w_l1 * inv_n) * sgn;
+        dL_dimage[o] = up * m * g;
+    }
 }
 
 // 0.01 * scaling.prod(1).mean() of gaussian_mapper.cpp:922-925, forward value + gradient added in place
@@ -295,7 +375,7 @@ size_t segs_loss_state_bytes(int C, int H, int W)
 {
     if (C <= 0 || H <= 0 || W <= 0) return 0;
     size_t bytes = 0;
-    const size_t blocks = size_t((W + LT - 1) / LT) * ((H + LT - 1) / LT) * C;
+    const size_t blocks = size_t((W + TX - 1) / TX) * ((H + TY - 1) / TY) * C;
     LossState::carve(nullptr, size_t(C) * H * W, blocks, &bytes);
     return bytes;
 }
@@ -306,13 +386,13 @@ int segs_loss_l1_ssim_forward(int C, int H, int W, const float* image, const flo
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (C <= 0 || H <= 0 || W <= 0 || C > 65535) { set_error("loss: invalid sizes C=%d H=%d W=%d", C, H, W); return SEGS_ERR_INVALID_ARG; }
     if (!image || !gt || !loss_out || !state) { set_error("loss: NULL required pointer"); return SEGS_ERR_INVALID_ARG; }
-    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    const dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, C);
     if (grid.y > 65535) { set_error("loss: image too tall"); return SEGS_ERR_INVALID_ARG; }
     const size_t blocks = size_t(grid.x) * grid.y * grid.z;
     LossState st = LossState::carve(state, size_t(C) * H * W, blocks, nullptr);
     SEGS_CUDA_CHECK(cudaMemsetAsync(st.ticket, 0, sizeof(uint32_t), stream));
     static const Window win = make_window();
-    ssim_l1_forward_kernel<<<grid, LT * LT, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, bias, st, loss_out);
+    ssim_l1_forward_kernel<<<grid, LTHREADS, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, bias, st, loss_out);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
@@ -324,12 +404,12 @@ int segs_loss_l1_ssim_backward(int C, int H, int W, const float* image, const fl
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (C <= 0 || H <= 0 || W <= 0 || C > 65535) { set_error("loss: invalid sizes C=%d H=%d W=%d", C, H, W); return SEGS_ERR_INVALID_ARG; }
     if (!image || !gt || !dL_dimage || !state) { set_error("loss: NULL required pointer"); return SEGS_ERR_INVALID_ARG; }
-    const dim3 grid((W + LT - 1) / LT, (H + LT - 1) / LT, C);
+    const dim3 grid((W + TX - 1) / TX, (H + TY - 1) / TY, C);
     if (grid.y > 65535) { set_error("loss: image too tall"); return SEGS_ERR_INVALID_ARG; }
     const size_t blocks = size_t(grid.x) * grid.y * grid.z;
     LossState st = LossState::carve(state, size_t(C) * H * W, blocks, nullptr);
     static const Window win = make_window();
-    ssim_l1_backward_kernel<<<grid, LT * LT, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, dL_dloss, st, dL_dimage);
+    ssim_l1_backward_kernel<<<grid, LTHREADS, 0, stream>>>(C, H, W, image, gt, row_mask, win, w_l1, w_ssim, dL_dloss, st, dL_dimage);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
