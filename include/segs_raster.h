@@ -267,9 +267,12 @@ int segs_decode_backward(
  *                            and written (gradient accumulation over the keyframe batch; every anchor row is owned
  *                            by one thread, no atomics).  *dparams is still zeroed and written.
  *   SEGS_DECODE_LOG_SCALING  d_scaling is the gradient w.r.t. _scaling = log(scaling) (the trainable tensor,
- *                            gaussian_model.cpp:186-189), i.e. multiplied by `scaling`. */
+ *                            gaussian_model.cpp:186-189), i.e. multiplied by `scaling`.
+ *   SEGS_DECODE_ATOMIC       with ACCUMULATE: add with RED.ADD.F32 (several views accumulate into the same arrays
+ *                            from concurrent streams; the summation order then varies from run to run). */
 #define SEGS_DECODE_ACCUMULATE  1
 #define SEGS_DECODE_LOG_SCALING 2
+#define SEGS_DECODE_ATOMIC      4
 int segs_decode_backward_ex(
     int A, const unsigned char* visible_mask,
     const float* anchor, const float* anchor_feat, const float* offset, const float* scaling,
@@ -340,6 +343,15 @@ typedef struct segs_mapper_view_result {
 
 int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* args, segs_mapper_view_result* result, void* stream);
 
+/* A batch of views on `n_lanes` concurrent lanes (lane l = workspace ws[l] + stream streams[l] + one persistent host
+ * thread owned by the workspace; lane 0 runs on the calling thread): lane l issues views l, l + n_lanes, ...  The
+ * latency-bound stages of one view (sorts, decode, the two host read-backs) overlap the issue-bound blend kernels of
+ * another.  With n_lanes > 1 the accumulated outputs are updated with RED.ADD.F32.  Every lane stream first waits for
+ * the work already queued on `main_stream`, and `main_stream` waits for every lane before the call returns (the host
+ * does not wait for the GPU beyond the read-backs).  args: HOST array [n_views]; results: HOST array [n_views]. */
+int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mapper_view_result* results,
+                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream);
+
 /* ---- mapper loss and optimizer ---------------------------------------
  *   segs_loss_l1_ssim_*   loss_utils::l1_loss / ssim / _ssim           include/loss_utils.h:29-32, 50-127,
  *                         as combined at                                src/gaussian_mapper.cpp:917-925
@@ -385,9 +397,10 @@ typedef struct segs_adam_tensor {
 int segs_adam_step(int n_tensors, const segs_adam_tensor* tensors, float* grad_flat, float* exp_avg_flat,
                    float* exp_avg_sq_flat, float grad_scale, int zero_grad, void* stream);
 
-/* dst[k][i] += src[k][i], i < counts[k], for all k in one launch (HOST arrays of DEVICE pointers). */
+/* dst[k][i] += src[k][i], i < counts[k], for all k in one launch (HOST arrays of DEVICE pointers);
+ * atomic != 0: with RED.ADD.F32 (concurrent accumulators). */
 int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, const unsigned long long* counts,
-                    void* stream);
+                    int atomic, void* stream);
 
 /* ---- per-stage device timing (bench.py roofline) -------------------------------------- */
 /* When enabled (per host thread), segs_raster_forward / segs_raster_backward bracket their
@@ -397,7 +410,7 @@ int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, co
  *   ms[3] blend forward   ms[4] blend backward   ms[5] preprocess backward
  * (a stage that did not run since the last read reports 0). */
 #define SEGS_PROFILE_STAGES 6
-/* Number of kernels this library has launched from the calling host thread so far. */
+/* Number of kernels this library has launched in this process so far (all host threads). */
 unsigned long long segs_launch_count(void);
 int segs_profile_enable(int on);
 int segs_profile_read(float* ms /* [SEGS_PROFILE_STAGES] */);

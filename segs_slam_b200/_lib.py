@@ -118,6 +118,11 @@ _PROTOTYPES = {
     "segs_workspace_destroy": (C.c_int, [C.c_void_p]),
     "segs_workspace_bytes": (C.c_size_t, [C.c_void_p]),
     "segs_mapper_view": (C.c_int, [C.c_void_p, C.POINTER(MapperViewArgs), C.POINTER(MapperViewResult), C.c_void_p]),
+    "segs_mapper_views": (
+        C.c_int,
+        [C.c_int, C.POINTER(MapperViewArgs), C.POINTER(MapperViewResult), C.c_int, C.POINTER(C.c_void_p),
+         C.POINTER(C.c_void_p), C.c_void_p],
+    ),
     "segs_loss_state_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),
     "segs_loss_l1_ssim_forward": (
         C.c_int,
@@ -134,7 +139,7 @@ _PROTOTYPES = {
     ),
     "segs_accumulate": (
         C.c_int,
-        [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong), C.c_void_p],
+        [C.c_int, C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_ulonglong), C.c_int, C.c_void_p],
     ),
     "segs_launch_count": (C.c_ulonglong, []),
     "segs_profile_enable": (C.c_int, [C.c_int]),

@@ -5,6 +5,7 @@
 // 397-490,494-585).  Unlike the reference, every launch goes to the caller's stream, every
 // CUDA call is checked, and nothing is allocated here: all device memory comes from the
 // three allocation callbacks.
+#include <atomic>
 #include <cstdarg>
 #include <cstring>
 #include <string>
@@ -22,8 +23,8 @@ void set_error(const char* fmt, ...) {
     va_end(ap);
 }
 
-static thread_local unsigned long long g_launches = 0;
-void count_launch() { ++g_launches; }
+static std::atomic<unsigned long long> g_launches{0};      // process-wide: lanes launch from their own host threads
+void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
 // ---- layouts --------------------------------------------------------------------------
 GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
@@ -150,7 +151,7 @@ extern "C" {
 
 int segs_version(void) { return SEGS_ABI_VERSION; }
 
-unsigned long long segs_launch_count(void) { return g_launches; }
+unsigned long long segs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
 
 int segs_profile_enable(int on) { g_prof.on = on != 0; return SEGS_OK; }
 

@@ -675,6 +675,9 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     stage_weights(sw, p, pose);
     // SEGS_DECODE_ACCUMULATE: every anchor row is owned by exactly one thread, so `+=` needs no atomics
     const bool acc_mode = (flags & SEGS_DECODE_ACCUMULATE) != 0;
+    // SEGS_DECODE_ATOMIC: several views accumulate into the same arrays from concurrent streams
+    const bool atomic_mode = (flags & SEGS_DECODE_ATOMIC) != 0;
+    auto accum = [&](float* dst, float v) { if (atomic_mode) atomicAdd(dst, v); else *dst += v; };
   for (size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x; ordinal < (size_t)n_vis;
        ordinal += size_t(gridDim.x) * DEC_THREADS) {
     const size_t a = st.anchor_index[ordinal];
@@ -756,7 +759,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
                         oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
             // xyz = anchor + offset * s[:3]
             dax += gx; day += gy; daz += gz;
-            if (acc_mode) { dof[0] += gx * in.s[0]; dof[1] += gy * in.s[1]; dof[2] += gz * in.s[2]; }
+            if (acc_mode) { accum(dof, gx * in.s[0]); accum(dof + 1, gy * in.s[1]); accum(dof + 2, gz * in.s[2]); }
             else { dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2]; }
             ds[0] = fmaf(gx, ox, ds[0]); ds[1] = fmaf(gy, oy, ds[1]); ds[2] = fmaf(gz, oz, ds[2]);
             // scaling = s[3:] * sigmoid(sr[:3])
@@ -867,6 +870,11 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     for (int q = 0; q < FEAT / 4; ++q) {
         float4* dst = reinterpret_cast<float4*>(d_feat + a * FEAT) + q;
         float4 v = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
+        if (acc_mode && atomic_mode) {
+            float* d1 = reinterpret_cast<float*>(dst);
+            atomicAdd(d1, v.x); atomicAdd(d1 + 1, v.y); atomicAdd(d1 + 2, v.z); atomicAdd(d1 + 3, v.w);
+            continue;
+        }
         if (acc_mode) { const float4 o4 = *dst; v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w; }
         *dst = v;
     }
@@ -886,9 +894,9 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
         for (int k = 0; k < 6; ++k) ds[k] *= in.s[k];
     }
     if (acc_mode) {
-        d_anchor[3 * a] += dax; d_anchor[3 * a + 1] += day; d_anchor[3 * a + 2] += daz;
+        accum(d_anchor + 3 * a, dax); accum(d_anchor + 3 * a + 1, day); accum(d_anchor + 3 * a + 2, daz);
 #pragma unroll
-        for (int k = 0; k < 6; ++k) d_scaling[6 * a + k] += ds[k];
+        for (int k = 0; k < 6; ++k) accum(d_scaling + 6 * a + k, ds[k]);
     } else {
         d_anchor[3 * a] = dax; d_anchor[3 * a + 1] = day; d_anchor[3 * a + 2] = daz;
 #pragma unroll

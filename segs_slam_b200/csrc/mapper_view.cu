@@ -9,6 +9,11 @@
 // ~150 ATen launches with autograd bookkeeping; here it is 27 launches, two host read-backs (the
 // decode's row count and num_rendered — both shape the next allocation, as in the reference) and no
 // temporary that outlives the view: everything is carved from a reusable workspace arena.
+#include <condition_variable>
+#include <functional>
+#include <mutex>
+#include <string>
+#include <thread>
 #include <vector>
 #include "common.cuh"
 
@@ -29,6 +34,61 @@ struct segs_workspace {
     size_t granule = size_t(256) << 20;
     size_t total = 0;
     bool failed = false;
+
+    // lane thread (segs_mapper_views): persistent, so the per-thread pinned read-back words and events of the
+    // library are created once, not once per step
+    std::thread worker;
+    std::mutex mu;
+    std::condition_variable cv;
+    std::function<void()> job;
+    bool has_job = false, job_done = false, quit = false;
+    int job_status = 0;
+    std::string job_error;
+
+    void start_worker() {
+        if (worker.joinable()) return;
+        worker = std::thread([this] {
+            for (;;) {
+                std::function<void()> j;
+                {
+                    std::unique_lock<std::mutex> lk(mu);
+                    cv.wait(lk, [this] { return has_job || quit; });
+                    if (quit) return;
+                    j = std::move(job);
+                    has_job = false;
+                }
+                j();
+                {
+                    std::lock_guard<std::mutex> lk(mu);
+                    job_done = true;
+                }
+                cv.notify_all();
+            }
+        });
+    }
+    void submit(std::function<void()> j) {
+        start_worker();
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            job = std::move(j);
+            has_job = true;
+            job_done = false;
+        }
+        cv.notify_all();
+    }
+    void wait_job() {
+        std::unique_lock<std::mutex> lk(mu);
+        cv.wait(lk, [this] { return job_done; });
+    }
+    void stop_worker() {
+        if (!worker.joinable()) return;
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            quit = true;
+        }
+        cv.notify_all();
+        worker.join();
+    }
 
     void reset() { for (auto& c : chunks) c.used = 0; failed = false; }
     char* alloc(size_t bytes) {
@@ -58,7 +118,7 @@ radii_to_mask_kernel(int n, const int* __restrict__ radii, unsigned char* __rest
     if (i < n) mask[i] = radii[i] > 0;       // visible_mask = radii_pure > 0 (gaussian_renderer.cpp:197)
 }
 
-__global__ void add_scalar_kernel(float* __restrict__ dst, const float* __restrict__ src) { *dst += *src; }
+__global__ void add_scalar_kernel(float* __restrict__ dst, const float* __restrict__ src) { atomicAdd(dst, *src); }
 
 }  // namespace
 }  // namespace segs
@@ -77,6 +137,7 @@ int segs_workspace_create(segs_workspace** out)
 int segs_workspace_destroy(segs_workspace* ws)
 {
     if (!ws) return SEGS_OK;
+    ws->stop_worker();
     for (auto& c : ws->chunks) cudaFree(c.base);
     delete ws;
     return SEGS_OK;
@@ -84,9 +145,9 @@ int segs_workspace_destroy(segs_workspace* ws)
 
 size_t segs_workspace_bytes(const segs_workspace* ws) { return ws ? ws->total : 0; }
 
-int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_mapper_view_result* res, void* stream_)
+static int mapper_view_impl(segs_workspace* ws, const segs_mapper_view_args* a, segs_mapper_view_result* res,
+                            bool concurrent, cudaStream_t stream)
 {
-    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (!ws || !a || !res) { set_error("mapper view: NULL argument"); return SEGS_ERR_INVALID_ARG; }
     res->n_visible = res->n_gaussians = res->num_rendered = 0;
     const int A = a->A, W = a->width, H = a->height;
@@ -202,7 +263,8 @@ int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_ma
     if ((rc = segs_decode_backward_ex(A, visible, a->anchor, a->anchor_feat, a->offset, a->scaling, a->campos, a->pose, a->params,
                                       dstate, n_vis, P, dL_dmean3D, dL_dcolor, dL_dopacity, dL_dscale, dL_drot, nullptr,
                                       a->grad_anchor, a->grad_anchor_feat, a->grad_offset, a->grad_scaling, &tmp, ws_alloc_cb, ws,
-                                      SEGS_DECODE_ACCUMULATE | (a->scaling_is_log ? SEGS_DECODE_LOG_SCALING : 0), stream))) return rc;
+                                      SEGS_DECODE_ACCUMULATE | (a->scaling_is_log ? SEGS_DECODE_LOG_SCALING : 0) |
+                                          (concurrent ? SEGS_DECODE_ATOMIC : 0), stream))) return rc;
     {
         float* dst[18]; const float* src[18]; unsigned long long cnt[18];
         int n = 0;
@@ -212,9 +274,68 @@ int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_ma
             if (!dst_fields[k]) { set_error("mapper view: NULL weight-gradient destination %d", k); return SEGS_ERR_INVALID_ARG; }
             dst[n] = dst_fields[k]; src[n] = tmp_fields[k]; cnt[n] = wn[k]; ++n;
         }
-        if ((rc = segs_accumulate(n, dst, src, cnt, stream))) return rc;
+        if ((rc = segs_accumulate(n, dst, src, cnt, concurrent ? 1 : 0, stream))) return rc;
     }
     return SEGS_OK;
+}
+
+int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_mapper_view_result* res, void* stream)
+{
+    return mapper_view_impl(ws, a, res, false, static_cast<cudaStream_t>(stream));
+}
+
+int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mapper_view_result* results,
+                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream_)
+{
+    cudaStream_t main_stream = static_cast<cudaStream_t>(main_stream_);
+    if (n_views < 0 || n_lanes < 1 || n_lanes > 8 || (n_views > 0 && (!args || !results)) || !ws || !streams) {
+        set_error("mapper views: invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    for (int l = 0; l < n_lanes; ++l)
+        if (!ws[l]) { set_error("mapper views: NULL workspace %d", l); return SEGS_ERR_INVALID_ARG; }
+    if (n_views == 0) return SEGS_OK;
+    if (n_lanes > n_views) n_lanes = n_views;
+    int device = 0;
+    SEGS_CUDA_CHECK(cudaGetDevice(&device));
+    const bool concurrent = n_lanes > 1;
+
+    cudaEvent_t start = nullptr;
+    SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
+    SEGS_CUDA_CHECK(cudaEventRecord(start, main_stream));
+    std::vector<cudaEvent_t> done(n_lanes, nullptr);
+    for (int l = 0; l < n_lanes; ++l) SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming));
+
+    auto run_lane = [&](int l) -> int {
+        cudaStream_t st = static_cast<cudaStream_t>(streams[l]);
+        cudaError_t e = cudaStreamWaitEvent(st, start, 0);
+        if (e != cudaSuccess) { set_error("mapper views: cudaStreamWaitEvent: %s", cudaGetErrorString(e)); return SEGS_ERR_CUDA; }
+        int rc = SEGS_OK;
+        for (int v = l; v < n_views && rc == SEGS_OK; v += n_lanes) rc = mapper_view_impl(ws[l], args + v, results + v, concurrent, st);
+        cudaEventRecord(done[l], st);
+        return rc;
+    };
+    for (int l = 1; l < n_lanes; ++l) {
+        segs_workspace* w = ws[l];
+        w->submit([w, l, device, &run_lane] {
+            cudaSetDevice(device);
+            w->job_status = run_lane(l);
+            w->job_error = w->job_status ? segs_last_error() : "";
+        });
+    }
+    int rc = run_lane(0);
+    for (int l = 1; l < n_lanes; ++l) {
+        ws[l]->wait_job();
+        if (rc == SEGS_OK && ws[l]->job_status) {
+            rc = ws[l]->job_status;
+            set_error("lane %d: %s", l, ws[l]->job_error.c_str());
+        }
+    }
+    for (int l = 0; l < n_lanes; ++l) {
+        cudaStreamWaitEvent(main_stream, done[l], 0);
+        cudaEventDestroy(done[l]);
+    }
+    cudaEventDestroy(start);
+    return rc;
 }
 
 }  // extern "C"

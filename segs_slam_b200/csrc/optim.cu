@@ -60,7 +60,7 @@ adam_step_kernel(const AdamTable t, float* __restrict__ grad, float* __restrict_
 
 // dst[i] += src[i] over up to 24 (dst, src, n) triples in one launch (gradient accumulation of one view
 // into the bucket when the producing kernel cannot accumulate in place)
-struct AddList { float* dst[24]; const float* src[24]; unsigned long long n[24]; int count; };
+struct AddList { float* dst[24]; const float* src[24]; unsigned long long n[24]; int count; int atomic; };
 __global__ void __launch_bounds__(256)
 add_many_kernel(const AddList z)
 {
@@ -69,7 +69,7 @@ add_many_kernel(const AddList z)
         const float* s = z.src[a];
         const unsigned long long n = z.n[a];
         for (unsigned long long i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
-            d[i] += s[i];
+            if (z.atomic) atomicAdd(d + i, s[i]); else d[i] += s[i];
     }
 }
 
@@ -119,13 +119,14 @@ int segs_adam_step(int n_tensors, const segs_adam_tensor* tensors, float* grad_f
 }
 
 int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, const unsigned long long* counts,
-                    void* stream_)
+                    int atomic, void* stream_)
 {
     cudaStream_t stream = static_cast<cudaStream_t>(stream_);
     if (n_arrays < 0 || (n_arrays > 0 && (!dst || !src || !counts))) { set_error("accumulate: invalid argument"); return SEGS_ERR_INVALID_ARG; }
     for (int first = 0; first < n_arrays; first += 24) {
         AddList z;
         z.count = 0;
+        z.atomic = atomic;
         unsigned long long largest = 0;
         for (int k = first; k < n_arrays && k < first + 24; ++k) {
             if (!counts[k]) continue;

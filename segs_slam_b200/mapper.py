@@ -155,7 +155,8 @@ class FusedMapper:
     (gaussian_model.cpp:620-872 gives each its own learning rate; `lrs` follows the same order)."""
 
     def __init__(self, pc, image_height: int, image_width: int, tanfovx: float, tanfovy: float, bg: torch.Tensor,
-                 lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None):
+                 lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None,
+                 lanes: int = 2):
         import ctypes as C
         from . import _lib
         from .gaussian_renderer import _weights
@@ -177,22 +178,30 @@ class FusedMapper:
         v = iter(self.bucket.views[4:])
         self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
         self.loss_accum = torch.zeros((), dtype=torch.float32, device=pc._anchor.device)
-        ws = C.c_void_p()
-        _lib.check(self.lib.segs_workspace_create(C.byref(ws)))
-        self._ws = ws
+        # lanes: concurrent views per rank (segs_mapper_views): lane = workspace + stream + persistent host thread.
+        # The sorts / decode / read-backs of one view overlap the issue-bound blend kernels of another; gradients
+        # are then accumulated with RED.ADD (one more order-dependent sum on top of the rasterizer backward's own).
+        self.lanes = max(1, int(lanes))
+        self._wss = []
+        for _ in range(self.lanes):
+            ws = C.c_void_p()
+            _lib.check(self.lib.segs_workspace_create(C.byref(ws)))
+            self._wss.append(ws)
+        self._ws = self._wss[0]
+        self._streams = [torch.cuda.Stream(device=pc._anchor.device) for _ in range(self.lanes)] if self.lanes > 1 else []
         self.last_result = None
         self._dirty = False                                           # the bucket starts zeroed
 
     def __del__(self):
         try:
-            if getattr(self, "_ws", None):
-                self.lib.segs_workspace_destroy(self._ws)
-                self._ws = None
+            for ws in getattr(self, "_wss", []):
+                self.lib.segs_workspace_destroy(ws)
+            self._wss, self._ws = [], None
         except Exception:
             pass
 
     def workspace_bytes(self) -> int:
-        return int(self.lib.segs_workspace_bytes(self._ws))
+        return sum(int(self.lib.segs_workspace_bytes(ws)) for ws in self._wss)
 
     def _prepare(self):
         """Per-step derived tensors (the parameters do not change between the views of one step)."""
@@ -227,6 +236,37 @@ class FusedMapper:
         a.loss_accum = self.loss_accum.data_ptr()
         self._args = a
 
+    def _fill(self, a, cam, target, row_mask, keep):
+        C = self._C
+        C.memmove(C.byref(a), C.byref(self._args), C.sizeof(self._args))
+        a.viewmatrix, a.projmatrix = cam.world_view_transform_.data_ptr(), cam.full_proj_transform_.data_ptr()
+        a.campos = cam.camera_center_.data_ptr()
+        t, q = cam.t_, cam.R_quaternion_
+        pose = (C.c_float * 7)(float(t[0]), float(t[1]), float(t[2]), float(q[0]), float(q[1]), float(q[2]), float(q[3]))
+        keep.append(pose)
+        a.pose = pose
+        a.gt_image = target.data_ptr()
+        a.row_mask = None if row_mask is None else row_mask.data_ptr()
+
+    def render_views(self, cams, targets, row_masks=None):
+        """A batch of views on `self.lanes` concurrent lanes: accumulates gradients and the loss."""
+        C, L = self._C, self._lib_mod
+        n = len(cams)
+        if n == 0:
+            return []
+        arr, res, keep = (L.MapperViewArgs * n)(), (L.MapperViewResult * n)(), []
+        for i in range(n):
+            self._fill(arr[i], cams[i], targets[i], None if row_masks is None else row_masks[i], keep)
+        dev = self.bucket.flat.device
+        with torch.cuda.device(dev):
+            main = torch.cuda.current_stream().cuda_stream
+            lanes = min(self.lanes, n)
+            wss = (C.c_void_p * lanes)(*[w.value for w in self._wss[:lanes]])
+            sts = (C.c_void_p * lanes)(*([main] if lanes == 1 else [s.cuda_stream for s in self._streams[:lanes]]))
+            L.check(self.lib.segs_mapper_views(n, arr, res, lanes, wss, sts, main))
+        self.last_result = res[n - 1]
+        return list(res)
+
     def render_view(self, cam, target: torch.Tensor, row_mask: torch.Tensor | None = None, image_out=None,
                     loss_terms_out=None):
         """One view: accumulates gradients and the loss.  `_prepare()` must have run this step."""
@@ -259,8 +299,9 @@ class FusedMapper:
         if self._dirty:
             self.bucket.zero_()                                      # normally cleared by the previous Adam launch
         self._dirty = True
-        for v in partition_views(n_views, world, rank):
-            self.render_view(cameras[v], targets[v], None if row_masks is None else row_masks[v])
+        mine = partition_views(n_views, world, rank)
+        self.render_views([cameras[v] for v in mine], [targets[v] for v in mine],
+                          None if row_masks is None else [row_masks[v] for v in mine])
         loss = self.loss_accum.clone()
         if world > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)

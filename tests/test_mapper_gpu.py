@@ -65,14 +65,15 @@ def _small_setup(device, A=4000, n_views=3):
     return model, cams, targets, (W, H, tanx, tany)
 
 
-def test_fused_view_matches_autograd_composition(device):
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_fused_view_matches_autograd_composition(device, lanes):
     """segs_mapper_view (C++-issued view, gradients accumulated in place) == the autograd composition of the
     tensor-level API (prefilter, decode, rasterize, fused loss, scaling regulariser) on the same views."""
     from segs_slam_b200 import loss_utils
     model, cams, targets, (W, H, tanx, tany) = _small_setup(device)
     bg = torch.tensor([0.1, 0.0, 0.2], device=device)
     masks = [loss_utils.mask_rgb(t) for t in targets]
-    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01)
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01, lanes=lanes)
     loss_f = fm.step(cams, targets, masks, optimize=False)
     grads_f = [v.clone() / len(cams) for v in fm.bucket.views]
     res = fm.last_result
@@ -114,3 +115,4 @@ def test_fused_mapper_optimises_like_torch_adam(device):
         # gradient differences (atomic order) can flip nothing but can shift m/sqrt(v) slightly
         assert float((pa - pb).abs().max()) < 2e-4 * 2e-3 * 50 + 1e-6, float((pa - pb).abs().max())
     assert fm.workspace_bytes() > 0
+

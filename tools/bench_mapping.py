@@ -17,6 +17,7 @@ ap = argparse.ArgumentParser()
 ap.add_argument("--steps", type=int, default=3)
 ap.add_argument("--views", type=int, default=64)
 ap.add_argument("--anchors", type=int, default=200_000)
+ap.add_argument("--lanes", type=int, default=2)
 ap.add_argument("--path", default="fused", choices=["fused", "autograd", "autograd-l1"])
 args = ap.parse_args()
 rank, local, world = (int(os.environ.get(k, d)) for k, d in (("RANK", 0), ("LOCAL_RANK", 0), ("WORLD_SIZE", 1)))
@@ -33,7 +34,7 @@ target = (torch.rand(3, H, W, generator=g) * 0.5).to(dev)
 targets = [target] * args.views
 bg = torch.zeros(3, device=dev)
 if args.path == "fused":
-    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lrs=1e-4)
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lrs=1e-4, lanes=args.lanes)
     class _B:  # noqa: E701
         flat = fm.bucket.flat
     def one_step(bucket):
@@ -70,7 +71,7 @@ if world > 1:
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
 if rank == 0:
     print(json.dumps({"metric": "mapping keyframes/s (C4: 64 keyframes, 1200x680, C3 anchor model)", "n_gpus": world,
-                      "views_per_step": args.views, "path": args.path, "steps": args.steps, "anchors": args.anchors,
+                      "views_per_step": args.views, "path": args.path, "lanes": args.lanes, "steps": args.steps, "anchors": args.anchors,
                       "value": round(args.views * args.steps / (float(t.item()) * 1e-3), 2), "unit": "keyframes/s",
                       "ms_per_step": round(float(t.item()) / args.steps, 2), "scaling": "strong",
                       "bucket_MB": round(bucket.flat.numel() * 4 / 1e6, 1), "losses": [round(x, 5) for x in losses]}))
