@@ -352,6 +352,39 @@ int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* args, segs
 int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mapper_view_result* results,
                       int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream);
 
+/* One view of a keyframe batch over EXPLICIT Gaussians (precomputed colours, scale + quaternion — the
+ * GaussianRasterizer call of src/gaussian_renderer.cpp:86-127 followed by its backward, src/gaussian_rasterizer.cpp:
+ * 88-154): forward into image_out, and, when dL_dout is not NULL, backward with the parameter gradients ADDED to the
+ * grad_* accumulators (NULL = not wanted).  All pointers DEVICE. */
+typedef struct segs_raster_view_args {
+    int P;
+    const float* means3D;           /* [P,3] */
+    const float* colors_precomp;    /* [P,3] */
+    const float* opacities;         /* [P,1] */
+    const float* scales;            /* [P,3] */
+    const float* rotations;         /* [P,4] */
+    const float* background;        /* [3]   */
+    int width, height;
+    float tan_fovx, tan_fovy;
+    const float* viewmatrix;        /* 16 floats, m[4*col+row] */
+    const float* projmatrix;
+    const float* campos;            /* [3] */
+    const float* dL_dout;           /* [3,H,W] or NULL (forward only) */
+    float* image_out;               /* [3,H,W] */
+    int*   radii_out;               /* [P] or NULL */
+    float* grad_means3D;            /* [P,3] += */
+    float* grad_means2D;            /* [P,3] += (screen-space gradient; drives densification, gaussian_model.cpp:1488-1499) */
+    float* grad_colors;             /* [P,3] += */
+    float* grad_opacity;            /* [P,1] += */
+    float* grad_scales;             /* [P,3] += */
+    float* grad_rotations;          /* [P,4] += */
+} segs_raster_view_args;
+
+/* A batch of such views on n_lanes concurrent lanes; lanes, streams and ordering exactly as segs_mapper_views.
+ * results[v].num_rendered is filled (n_visible is unused). */
+int segs_raster_views(int n_views, const segs_raster_view_args* args, segs_mapper_view_result* results,
+                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream);
+
 /* ---- mapper loss and optimizer ---------------------------------------
  *   segs_loss_l1_ssim_*   loss_utils::l1_loss / ssim / _ssim           include/loss_utils.h:29-32, 50-127,
  *                         as combined at                                src/gaussian_mapper.cpp:917-925

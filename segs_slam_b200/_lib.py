@@ -49,6 +49,17 @@ class MapperViewArgs(C.Structure):
                 ("radii_out", C.c_void_p)]
 
 
+class RasterViewArgs(C.Structure):
+    """segs_raster_view_args (include/segs_raster.h)."""
+    _fields_ = [("P", C.c_int), ("means3D", C.c_void_p), ("colors_precomp", C.c_void_p), ("opacities", C.c_void_p),
+                ("scales", C.c_void_p), ("rotations", C.c_void_p), ("background", C.c_void_p),
+                ("width", C.c_int), ("height", C.c_int), ("tan_fovx", C.c_float), ("tan_fovy", C.c_float),
+                ("viewmatrix", C.c_void_p), ("projmatrix", C.c_void_p), ("campos", C.c_void_p),
+                ("dL_dout", C.c_void_p), ("image_out", C.c_void_p), ("radii_out", C.c_void_p),
+                ("grad_means3D", C.c_void_p), ("grad_means2D", C.c_void_p), ("grad_colors", C.c_void_p),
+                ("grad_opacity", C.c_void_p), ("grad_scales", C.c_void_p), ("grad_rotations", C.c_void_p)]
+
+
 class MapperViewResult(C.Structure):
     """segs_mapper_view_result (include/segs_raster.h)."""
     _fields_ = [("n_visible", C.c_int), ("n_gaussians", C.c_int), ("num_rendered", C.c_int)]
@@ -121,6 +132,11 @@ _PROTOTYPES = {
     "segs_mapper_views": (
         C.c_int,
         [C.c_int, C.POINTER(MapperViewArgs), C.POINTER(MapperViewResult), C.c_int, C.POINTER(C.c_void_p),
+         C.POINTER(C.c_void_p), C.c_void_p],
+    ),
+    "segs_raster_views": (
+        C.c_int,
+        [C.c_int, C.POINTER(RasterViewArgs), C.POINTER(MapperViewResult), C.c_int, C.POINTER(C.c_void_p),
          C.POINTER(C.c_void_p), C.c_void_p],
     ),
     "segs_loss_state_bytes": (C.c_size_t, [C.c_int, C.c_int, C.c_int]),

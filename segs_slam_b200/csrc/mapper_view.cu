@@ -284,16 +284,11 @@ int segs_mapper_view(segs_workspace* ws, const segs_mapper_view_args* a, segs_ma
     return mapper_view_impl(ws, a, res, false, static_cast<cudaStream_t>(stream));
 }
 
-int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mapper_view_result* results,
-                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream_)
+// run fn(view index, lane workspace, lane stream, concurrent) over n_views on n_lanes lanes (see segs_mapper_views)
+extern "C++" {
+template <class F>
+static int run_lanes(int n_views, int n_lanes, segs_workspace* const* ws, void* const* streams, cudaStream_t main_stream, F fn)
 {
-    cudaStream_t main_stream = static_cast<cudaStream_t>(main_stream_);
-    if (n_views < 0 || n_lanes < 1 || n_lanes > 8 || (n_views > 0 && (!args || !results)) || !ws || !streams) {
-        set_error("mapper views: invalid argument"); return SEGS_ERR_INVALID_ARG;
-    }
-    for (int l = 0; l < n_lanes; ++l)
-        if (!ws[l]) { set_error("mapper views: NULL workspace %d", l); return SEGS_ERR_INVALID_ARG; }
-    if (n_views == 0) return SEGS_OK;
     if (n_lanes > n_views) n_lanes = n_views;
     int device = 0;
     SEGS_CUDA_CHECK(cudaGetDevice(&device));
@@ -308,9 +303,9 @@ int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mappe
     auto run_lane = [&](int l) -> int {
         cudaStream_t st = static_cast<cudaStream_t>(streams[l]);
         cudaError_t e = cudaStreamWaitEvent(st, start, 0);
-        if (e != cudaSuccess) { set_error("mapper views: cudaStreamWaitEvent: %s", cudaGetErrorString(e)); return SEGS_ERR_CUDA; }
+        if (e != cudaSuccess) { set_error("lanes: cudaStreamWaitEvent: %s", cudaGetErrorString(e)); return SEGS_ERR_CUDA; }
         int rc = SEGS_OK;
-        for (int v = l; v < n_views && rc == SEGS_OK; v += n_lanes) rc = mapper_view_impl(ws[l], args + v, results + v, concurrent, st);
+        for (int v = l; v < n_views && rc == SEGS_OK; v += n_lanes) rc = fn(v, ws[l], st, concurrent);
         cudaEventRecord(done[l], st);
         return rc;
     };
@@ -336,6 +331,95 @@ int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mappe
     }
     cudaEventDestroy(start);
     return rc;
+}
+}  // extern "C++"
+
+static int check_lanes(int n_views, const void* args, const void* results, int n_lanes, segs_workspace* const* ws, void* const* streams)
+{
+    if (n_views < 0 || n_lanes < 1 || n_lanes > 8 || (n_views > 0 && (!args || !results)) || !ws || !streams) {
+        set_error("views: invalid argument"); return SEGS_ERR_INVALID_ARG;
+    }
+    for (int l = 0; l < n_lanes; ++l)
+        if (!ws[l]) { set_error("views: NULL workspace %d", l); return SEGS_ERR_INVALID_ARG; }
+    return SEGS_OK;
+}
+
+int segs_mapper_views(int n_views, const segs_mapper_view_args* args, segs_mapper_view_result* results,
+                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream)
+{
+    int rc = check_lanes(n_views, args, results, n_lanes, ws, streams);
+    if (rc || n_views == 0) return rc;
+    return run_lanes(n_views, n_lanes, ws, streams, static_cast<cudaStream_t>(main_stream),
+                     [&](int v, segs_workspace* w, cudaStream_t st, bool concurrent) {
+                         return mapper_view_impl(w, args + v, results + v, concurrent, st);
+                     });
+}
+
+// rasterize + back-propagate one view of explicit Gaussians, gradients accumulated (see segs_raster_views)
+static int raster_view_impl(segs_workspace* ws, const segs_raster_view_args* a, segs_mapper_view_result* res,
+                            bool concurrent, cudaStream_t stream)
+{
+    res->n_visible = res->n_gaussians = res->num_rendered = 0;
+    const int P = a->P, W = a->width, H = a->height;
+    if (P < 0 || W <= 0 || H <= 0) { set_error("raster view: invalid sizes P=%d W=%d H=%d", P, W, H); return SEGS_ERR_INVALID_ARG; }
+    if (!a->background || !a->viewmatrix || !a->projmatrix || !a->campos || !a->image_out ||
+        (P > 0 && (!a->means3D || !a->colors_precomp || !a->opacities || !a->scales || !a->rotations))) {
+        set_error("raster view: NULL required pointer"); return SEGS_ERR_INVALID_ARG;
+    }
+    ws->reset();
+    int rc;
+    auto oom = [&]() { set_error("raster view: workspace allocation failed (%zu bytes held)", ws->total); return SEGS_ERR_ALLOC; };
+    struct Slot { segs_workspace* ws; char* ptr; };
+    Slot geom{ws, nullptr}, binning{ws, nullptr}, img{ws, nullptr};
+    auto slot_cb = [](void* u, size_t bytes) -> char* {
+        Slot* s = static_cast<Slot*>(u);
+        s->ptr = s->ws->alloc(bytes);
+        return s->ptr;
+    };
+    int* radii = a->radii_out ? a->radii_out : ws->take<int>(P > 0 ? P : 1);
+    if (!radii) return oom();
+    int R = 0;
+    if ((rc = segs_raster_forward(slot_cb, &geom, slot_cb, &binning, slot_cb, &img, P, 0, 0, a->background, W, H, a->means3D,
+                                  nullptr, a->colors_precomp, a->opacities, a->scales, 1.0f, a->rotations, nullptr,
+                                  a->viewmatrix, a->projmatrix, a->campos, a->tan_fovx, a->tan_fovy, 0, a->image_out, radii,
+                                  &R, stream))) return rc;
+    res->n_gaussians = P;
+    res->num_rendered = R;
+    if (!a->dL_dout || P == 0) return SEGS_OK;            // forward only
+    const size_t Pz = size_t(P);
+    float* g2D = ws->take<float>(Pz * 3);
+    float* gconic = ws->take<float>(Pz * 4);
+    float* gop = ws->take<float>(Pz);
+    float* gcol = ws->take<float>(Pz * 3);
+    float* g3D = ws->take<float>(Pz * 3);
+    float* gcov = ws->take<float>(Pz * 6);
+    float* gsc = ws->take<float>(Pz * 3);
+    float* grot = ws->take<float>(Pz * 4);
+    if (!g2D || !gconic || !gop || !gcol || !g3D || !gcov || !gsc || !grot) return oom();
+    if ((rc = segs_raster_backward(P, 0, 0, R, a->background, W, H, a->means3D, nullptr, a->colors_precomp, a->scales, 1.0f,
+                                   a->rotations, nullptr, a->viewmatrix, a->projmatrix, a->campos, a->tan_fovx, a->tan_fovy,
+                                   radii, geom.ptr, binning.ptr, img.ptr, a->dL_dout, g2D, gconic, gop, gcol, g3D, gcov, nullptr,
+                                   gsc, grot, stream))) return rc;
+    float* dst[6] = {a->grad_means3D, a->grad_means2D, a->grad_colors, a->grad_opacity, a->grad_scales, a->grad_rotations};
+    const float* src[6] = {g3D, g2D, gcol, gop, gsc, grot};
+    const unsigned long long w6[6] = {3, 3, 3, 1, 3, 4};
+    float* d2[6]; const float* s2[6]; unsigned long long c2[6];
+    int n = 0;
+    for (int k = 0; k < 6; ++k)
+        if (dst[k]) { d2[n] = dst[k]; s2[n] = src[k]; c2[n] = w6[k] * Pz; ++n; }
+    if (n) return segs_accumulate(n, d2, s2, c2, concurrent ? 1 : 0, stream);
+    return SEGS_OK;
+}
+
+int segs_raster_views(int n_views, const segs_raster_view_args* args, segs_mapper_view_result* results,
+                      int n_lanes, segs_workspace* const* ws, void* const* streams, void* main_stream)
+{
+    int rc = check_lanes(n_views, args, results, n_lanes, ws, streams);
+    if (rc || n_views == 0) return rc;
+    return run_lanes(n_views, n_lanes, ws, streams, static_cast<cudaStream_t>(main_stream),
+                     [&](int v, segs_workspace* w, cudaStream_t st, bool concurrent) {
+                         return raster_view_impl(w, args + v, results + v, concurrent, st);
+                     });
 }
 
 }  // extern "C"

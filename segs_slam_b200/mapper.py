@@ -310,3 +310,69 @@ class FusedMapper:
             self.optimizer.step(grad_scale=1.0 / float(n_views), zero_grad=True)
             self._dirty = False
         return loss / float(n_views)
+
+
+class RasterBatch:
+    """A keyframe batch over EXPLICIT Gaussians (precomputed colours, scale + quaternion) on concurrent lanes
+    (`segs_raster_views`, csrc/mapper_view.cu): per view the GaussianRasterizer forward
+    (/root/reference/src/gaussian_renderer.cpp:86-127) and, when a dL_dout is given, its backward
+    (src/gaussian_rasterizer.cpp:88-154), the parameter gradients ADDED to caller-owned accumulators — the
+    rasterizer-only sibling of FusedMapper, and what bench.py times on BASELINE config 2."""
+
+    def __init__(self, device, lanes: int = 2):
+        import ctypes as C
+        from . import _lib
+        self._C, self._L, self.lib = C, _lib, _lib.load()
+        self.device = torch.device(device)
+        if self.device.type != "cuda":
+            raise RuntimeError("segs_slam_b200 has no CPU path: RasterBatch needs a CUDA device")
+        self.lanes = max(1, int(lanes))
+        self._wss = []
+        for _ in range(self.lanes):
+            ws = C.c_void_p()
+            _lib.check(self.lib.segs_workspace_create(C.byref(ws)))
+            self._wss.append(ws)
+        self._streams = [torch.cuda.Stream(device=self.device) for _ in range(self.lanes)] if self.lanes > 1 else []
+
+    def __del__(self):
+        try:
+            for ws in getattr(self, "_wss", []):
+                self.lib.segs_workspace_destroy(ws)
+            self._wss = []
+        except Exception:
+            pass
+
+    def run(self, means3D, colors, opacities, scales, rotations, bg, cameras, image_height, image_width, tanfovx, tanfovy,
+            images_out, dL_douts=None, grads=None, lanes: int | None = None):
+        """cameras: objects/dicts with viewmatrix, projmatrix, campos (DEVICE tensors, kernel memory order).
+        images_out[v]: [3,H,W] tensors written.  dL_douts[v] (optional): [3,H,W].  grads: 6 accumulators in the order
+        (means3D [P,3], means2D [P,3], colors [P,3], opacity [P,1], scales [P,3], rotations [P,4]), entries may be None.
+        -> list of num_rendered."""
+        C, L = self._C, self._L
+        n = len(cameras)
+        if n == 0:
+            return []
+        for t in (means3D, colors, opacities, scales, rotations, bg):
+            if not t.is_cuda or t.dtype != torch.float32 or not t.is_contiguous():
+                raise RuntimeError("RasterBatch: contiguous FP32 CUDA tensors expected (no CPU path)")
+        get = (lambda c, k: c[k]) if isinstance(cameras[0], dict) else getattr
+        arr, res = (L.RasterViewArgs * n)(), (L.MapperViewResult * n)()
+        g = [None] * 6 if grads is None else [None if t is None else t.data_ptr() for t in grads]
+        for v in range(n):
+            a = arr[v]
+            a.P = means3D.size(0)
+            a.means3D, a.colors_precomp, a.opacities = means3D.data_ptr(), colors.data_ptr(), opacities.data_ptr()
+            a.scales, a.rotations, a.background = scales.data_ptr(), rotations.data_ptr(), bg.data_ptr()
+            a.width, a.height, a.tan_fovx, a.tan_fovy = int(image_width), int(image_height), float(tanfovx), float(tanfovy)
+            a.viewmatrix, a.projmatrix = get(cameras[v], "viewmatrix").data_ptr(), get(cameras[v], "projmatrix").data_ptr()
+            a.campos = get(cameras[v], "campos").data_ptr()
+            a.dL_dout = None if dL_douts is None else dL_douts[v].data_ptr()
+            a.image_out = images_out[v].data_ptr()
+            (a.grad_means3D, a.grad_means2D, a.grad_colors, a.grad_opacity, a.grad_scales, a.grad_rotations) = g
+        nl = min(self.lanes if lanes is None else max(1, min(int(lanes), self.lanes)), n)
+        with torch.cuda.device(self.device):
+            main = torch.cuda.current_stream().cuda_stream
+            wss = (C.c_void_p * nl)(*[w.value for w in self._wss[:nl]])
+            sts = (C.c_void_p * nl)(*([main] if nl == 1 else [s.cuda_stream for s in self._streams[:nl]]))
+            L.check(self.lib.segs_raster_views(n, arr, res, nl, wss, sts, main))
+        return [int(r.num_rendered) for r in res]

@@ -116,3 +116,51 @@ def test_fused_mapper_optimises_like_torch_adam(device):
         assert float((pa - pb).abs().max()) < 2e-4 * 2e-3 * 50 + 1e-6, float((pa - pb).abs().max())
     assert fm.workspace_bytes() > 0
 
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_raster_views_match_the_tensor_level_api(device, lanes):
+    """segs_raster_views (batched views on lanes, accumulated gradients) == per-view RasterizeGaussiansCUDA /
+    RasterizeGaussiansBackwardCUDA summed over the views: images and num_rendered bit-exact, gradients 1e-4."""
+    import common
+    from segs_slam_b200 import rasterize_points as rp
+    scene = synth.config("small")
+    t = scene.to_torch(device)
+    P, W, H = scene.P, scene.W, scene.H
+    views = [synth.with_camera(scene, np.eye(3, dtype=np.float32), np.array([0.03 * v, -0.02 * v, 0.0], np.float32))
+             for v in range(3)]
+    cams = [{k: torch.from_numpy(np.ascontiguousarray(getattr(s, k))).to(device) for k in ("viewmatrix", "projmatrix", "campos")}
+            for s in views]
+    g = torch.Generator(device="cpu").manual_seed(2)
+    dLs = [torch.randn(3, H, W, generator=g).to(device) for _ in cams]
+    e = common.empty(device)
+    ref_imgs, ref_R, ref_sum = [], [], None
+    for cam, dL in zip(cams, dLs):
+        R, color, radii, gb_, bb_, ib_ = rp.RasterizeGaussiansCUDA(t["bg"], t["means3D"], t["colors"], t["opacities"], t["scales"],
+                                                                   t["rotations"], 1.0, e, cam["viewmatrix"], cam["projmatrix"],
+                                                                   scene.tanfovx, scene.tanfovy, H, W, e, 0, cam["campos"], False)
+        gr = rp.RasterizeGaussiansBackwardCUDA(t["bg"], t["means3D"], radii, t["colors"], t["scales"], t["rotations"], 1.0, e,
+                                               cam["viewmatrix"], cam["projmatrix"], scene.tanfovx, scene.tanfovy, dL, e, 0,
+                                               cam["campos"], gb_, R, bb_, ib_)
+        six = [gr[3], gr[0], gr[1], gr[2], gr[6], gr[7]]
+        ref_sum = [x.clone() for x in six] if ref_sum is None else [a + b for a, b in zip(ref_sum, six)]
+        ref_imgs.append(color)
+        ref_R.append(R)
+    rb = mapper.RasterBatch(device, lanes=lanes)
+    imgs = [torch.empty(3, H, W, device=device) for _ in cams]
+    acc = [torch.zeros(P, w, device=device) for w in (3, 3, 3, 1, 3, 4)]
+    Rs = rb.run(t["means3D"], t["colors"], t["opacities"], t["scales"], t["rotations"], t["bg"], cams, H, W, scene.tanfovx,
+                scene.tanfovy, imgs, dLs, acc)
+    torch.cuda.synchronize()
+    assert Rs == ref_R
+    for a, b in zip(imgs, ref_imgs):
+        assert torch.equal(a, b)
+    for a, b in zip(acc, ref_sum):
+        ok, why = common.grad_close(a.reshape(b.shape), b, None, rel=1e-4)
+        assert ok, why
+    # forward only: no dL_dout, no accumulators
+    imgs2 = [torch.empty(3, H, W, device=device) for _ in cams]
+    rb.run(t["means3D"], t["colors"], t["opacities"], t["scales"], t["rotations"], t["bg"], cams, H, W, scene.tanfovx,
+           scene.tanfovy, imgs2)
+    torch.cuda.synchronize()
+    assert all(torch.equal(a, b) for a, b in zip(imgs2, ref_imgs))
