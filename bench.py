@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--lanes", type=int, default=2, help="views in flight per GPU (concurrent lanes of the batch API)")
     ap.add_argument("--no-mapping", action="store_true", help="skip the keyframe-batched mapping measurement")
     ap.add_argument("--mapping-steps", type=int, default=3)
     return ap.parse_args()
@@ -207,15 +208,33 @@ def main():
         b.accumulate([grads[gi].view(P, w) for gi, w in zip(GRAD_IDX, widths)])
 
     R_seen = []
+    LANES = args.lanes if args.impl == "ours" else 1
+    if args.impl == "ours":
+        # The step goes through the batch API (mapper.RasterBatch -> segs_raster_views): the views of the keyframe
+        # batch are issued from C++ on LANES concurrent lanes (stream + host thread each), so the latency-bound
+        # stages of one view (sorts, binning, the num_rendered read-back) overlap the issue-bound blend kernels of
+        # another; gradients are accumulated straight into the flat bucket.
+        rb = mapper.RasterBatch(dev, lanes=LANES)
+        step_images = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in cams]
+        dLs_same = [dL] * len(cams)
 
-    def step():
-        for v, cam in enumerate(cams):
-            R, color, grads = fwd_bwd(cam, dL)
-            accumulate(grads, v == 0)
-            R_seen.append(R)
-        if distributed and args.impl == "ours":
-            dist.all_reduce(bucket)
-        return color
+        def run_batch(pr, dLs, imgs, bkt, lanes=None):
+            bkt.zero_()
+            return rb.run(pr["means3D"], pr["colors"], pr["opacities"], pr["scales"], pr["rotations"], base["bg"], cams,
+                          H, W, scene0.tanfovx, scene0.tanfovy, imgs, dLs, bkt.views, lanes=lanes)
+
+        def step(lanes=None):
+            R_seen.extend(run_batch(base, dLs_same, step_images, gb, lanes))
+            if distributed:
+                dist.all_reduce(bucket)
+            return step_images[-1]
+    else:
+        def step(lanes=None):
+            for v, cam in enumerate(cams):
+                R, color, grads = fwd_bwd(cam, dL)
+                accumulate(grads, v == 0)
+                R_seen.append(R)
+            return color
 
     def barrier():
         torch.cuda.synchronize()
@@ -260,12 +279,13 @@ def main():
     ev0.record()
     n_prof = 0
     for s in range(args.steps):
-        # per-stage CUDA events (12 event records per view) are only armed on every 5th step so
-        # that they do not perturb the step time they are part of
-        prof = lib is not None and s % 5 == 0
+        # per-stage CUDA events are armed on every 10th step only; that step runs its views on ONE lane so that
+        # each stage is timed on its own (under two lanes the stages of different views overlap); it stays inside
+        # the timed region and costs it a few percent
+        prof = lib is not None and s % 10 == 0
         if prof:
             lib.segs_profile_enable(1)
-        step()
+        step(lanes=1 if prof else None)
         if prof:
             lib.segs_profile_enable(0)
             ms = (C.c_float * len(STAGES))()
@@ -364,6 +384,52 @@ def main():
             ev_grads_done[p].record(s_out)
         ev_grads_done[p ^ 1].synchronize()            # the host owns the previous step's results
 
+    if args.impl == "ours":
+        # batch API: the step's inputs (parameters + every view's dL_dout) are uploaded while the previous step
+        # computes, its outputs (every view's image + the accumulated gradients) are downloaded while the next one
+        # computes; same bytes per step as the per-view harness of the reference arm
+        nv = len(cams)
+        dev_dLs = [[torch.empty_like(dL) for _ in range(nv)] for _ in range(2)]
+        dev_imgs = [[torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(nv)] for _ in range(2)]
+        host_imgs = [[torch.empty((3, H, W), dtype=torch.float32).pin_memory() for _ in range(nv)] for _ in range(2)]
+        ev_in_ready, ev_in_free, ev_out_done = [Ev(), Ev()], [Ev(), Ev()], [Ev(), Ev()]
+        for e_ in ev_in_free + ev_out_done:
+            e_.record(cur)
+
+        def upload_step(slot):
+            with torch.cuda.stream(s_in):
+                s_in.wait_event(ev_in_free[slot])
+                for k in PKEYS:
+                    dev_params[slot][k].copy_(host_in[k], non_blocking=True)
+                for v in range(nv):
+                    dev_dLs[slot][v].copy_(host_dL, non_blocking=True)
+                ev_in_ready[slot].record(s_in)
+
+        def e2e_step(i, last):                      # noqa: F811  (replaces the per-view variant above)
+            p = i & 1
+            if i == 0:
+                upload_step(0)
+            if not last:
+                upload_step(p ^ 1)                    # next step's inputs ride behind this step's kernels
+            cur.wait_event(ev_in_ready[p])
+            cur.wait_event(ev_out_done[p])            # slot p's images / bucket were downloaded two steps ago
+            run_batch(dev_params[p], dev_dLs[p], dev_imgs[p], buckets[p])
+            ev_in_free[p].record(cur)
+            if distributed:
+                dist.all_reduce(buckets[p].flat)
+            done = Ev()
+            done.record(cur)
+            with torch.cuda.stream(s_out):
+                s_out.wait_event(done)
+                for v in range(nv):
+                    host_imgs[p][v].copy_(dev_imgs[p][v], non_blocking=True)
+                host_grads[p].copy_(buckets[p].flat, non_blocking=True)
+                ev_out_done[p].record(s_out)
+            ev_out_done[p ^ 1].synchronize()          # the host owns the previous step's results
+            state["views"] += nv
+
+        ev_grads_done = ev_out_done                   # what e2e_run drains
+
     def e2e_run(n):
         state["views"] = 0
         for i in range(n):
@@ -432,14 +498,15 @@ def main():
         "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{args.config}: synth({P},{W},{H}) single-view rasterizer forward+backward "
                                f"(BASELINE.md section 3), colours precomputed, scale+quaternion",
-                   "views_per_step_per_gpu": VIEWS_PER_STEP, "P": P, "W": W, "H": H,
+                   "views_per_step_per_gpu": VIEWS_PER_STEP, "views_in_flight_per_gpu": LANES, "P": P, "W": W, "H": H,
                    "num_rendered_mean": round(R_mean), "parallelism": f"dp{n_ranks} (keyframe views)",
                    "l2": "working set per view (~0.45 GB state + gradients) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
                 "d2h_bytes_per_step": int(d2h), "steps": e2e_steps,
                 "pipeline": "pinned host buffers; H2D and D2H on two copy streams, double-buffered against the "
-                            "compute stream; drained inside the timed region"},
+                            "compute stream; drained inside the timed region" +
+                            ("; batch API (mapper.RasterBatch), step-level double buffering" if args.impl == "ours" else "")},
         "gpu_launches": int(launches),
     }
     if mapping is not None:
