@@ -9,12 +9,13 @@ Restates, in PyTorch FP32 on the CPU (same ATen ops in the same order as the ref
   * loss_utils::create_window      :67-76   (outer product, expanded to [C,1,11,11])
   * loss_utils::_ssim / ssim       :78-127  (5 grouped conv2d with zero padding 5, C1 = 0.01^2, C2 = 0.03^2)
   * loss_utils::psnr               :39-43
+  * loss_utils::high_frequency_loss / low_freq_loss / multi_scale_loss   :129-237 (torch.fft, op for op)
   * the call site                  /root/reference/src/gaussian_mapper.cpp:908-925
       mask_rgb = (gt != 0).any(-1) ; loss = (1-l)*L1 + l*(1-ssim) + 0.01*scaling.prod(1).mean()
   * torch::optim::Adam::step       LibTorch torch/csrc/api/src/optim/adam.cpp (amsgrad off), the optimizer the
                                    reference builds at src/gaussian_model.cpp:620-872 (eps = 1e-15, :634)
 
-Pinned: tests/golden/loss_*.npz and adam_*.npz were produced by the reference's own loss_utils.h and by
+Pinned: tests/golden/loss_*.npz, freq_*.npz and adam_*.npz were produced by the reference's own loss_utils.h and by
 torch::optim::Adam (oracle/_ref/libloss_ref.so via tests/golden/make_loss_golden.py);
 tests/test_loss_cpu.py holds this file to them.
 """
@@ -107,3 +108,44 @@ def adam(param: np.ndarray, grads: np.ndarray, lr: float, beta1: float = 0.9, be
         denom = np.sqrt(v) / f(math.sqrt(bc2)) + f(eps)
         p = p - f(lr / bc1) * (m / denom)
     return p, m, v
+
+
+# ---- frequency-domain terms (loss_utils.h:129-237), op for op -----------------------------------------------------
+# NOTE (reference behaviour, reproduced on purpose): the images are [C,H,W] but the masks are indexed with
+# index_put_({Slice(crow-r, crow+r), Slice(ccol-r, ccol+r)}, v), i.e. on dims 0 and 1 — the CHANNEL and ROW dims.  With
+# C = 3 the first slice is empty, so the high-pass mask stays all ones (the "high frequency" loss is the mean
+# magnitude difference over the FULL spectrum) and the low-pass mask stays all zeros (low_freq_loss has zero gradient;
+# its value is pi/(HWC) times the number of spectrum bins whose signed zeros differ in angle).  fftshift() without
+# dims also rolls the channel dim; neither loss depends on the bin order.
+def _filtered_fft(img: torch.Tensor, cutoff_ratio: float, high: bool) -> torch.Tensor:
+    f = torch.fft.fftshift(torch.fft.fft2(img))
+    H, W = img.shape[1], img.shape[2]
+    crow, ccol = H // 2, W // 2
+    mask = torch.ones_like(f) if high else torch.zeros_like(f)
+    r = int(cutoff_ratio * min(H, W) / 2)
+    mask[crow - r:crow + r, ccol - r:ccol + r] = 0 if high else 1
+    return f * mask
+
+
+def high_frequency_loss(img1: torch.Tensor, img2: torch.Tensor, cutoff_ratio: float = 0.4) -> torch.Tensor:
+    a, b = _filtered_fft(img1, cutoff_ratio, True), _filtered_fft(img2, cutoff_ratio, True)
+    return torch.mean(torch.abs(torch.abs(a) - torch.abs(b)))
+
+
+def low_freq_loss(img1: torch.Tensor, img2: torch.Tensor, cutoff_ratio: float = 0.2) -> torch.Tensor:
+    norm = float(img1.shape[0] * img1.shape[1] * img1.shape[2])
+    a, b = _filtered_fft(img1, cutoff_ratio, False), _filtered_fft(img2, cutoff_ratio, False)
+    la = torch.sum(torch.abs(torch.abs(a) - torch.abs(b))) / norm
+    lp = torch.sum(torch.abs(torch.angle(a) - torch.angle(b))) / norm
+    return la + lp
+
+
+def multi_scale_loss(gen: torch.Tensor, target: torch.Tensor, scales) -> torch.Tensor:
+    loss = torch.zeros((), device=gen.device)
+    for s in scales:
+        g = F.interpolate(gen.unsqueeze(0), scale_factor=(float(s), float(s)), mode="bilinear", align_corners=False,
+                          recompute_scale_factor=True)
+        t = F.interpolate(target.unsqueeze(0), scale_factor=(float(s), float(s)), mode="bilinear", align_corners=False,
+                          recompute_scale_factor=True)
+        loss = loss + s * high_frequency_loss(g.squeeze(0), t.squeeze(0))
+    return loss

@@ -57,6 +57,29 @@ float ref_psnr(int C, int H, int W, const float* a, const float* b)
     return loss_utils::psnr(x, y).item<float>();
 }
 
+// the frequency-domain terms (loss_utils.h:129-237) with their gradients w.r.t. img1:
+// out3 = { high_frequency_loss(cutoff 0.4), low_freq_loss(cutoff 0.2), multi_scale_loss(scales {1.0, 0.5}) }
+int ref_frequency_losses(int C, int H, int W, const float* a, const float* b, float* out3, float* d_high, float* d_multi)
+{
+    auto opts = torch::TensorOptions().dtype(torch::kFloat32);
+    torch::Tensor y = torch::from_blob(const_cast<float*>(b), {C, H, W}, opts).clone();
+    {
+        torch::Tensor x = torch::from_blob(const_cast<float*>(a), {C, H, W}, opts).clone().requires_grad_(true);
+        auto l = loss_utils::high_frequency_loss(x, y, 0.4f, torch::kCPU);
+        l.backward();
+        out3[0] = l.item<float>();
+        std::memcpy(d_high, x.grad().contiguous().data_ptr<float>(), sizeof(float) * C * H * W);
+    }
+    {
+        torch::Tensor x = torch::from_blob(const_cast<float*>(a), {C, H, W}, opts).clone();
+        out3[1] = loss_utils::low_freq_loss(x, y, 0.2f, torch::kCPU).item<float>();
+    }
+    // multi_scale_loss (:204-235) calls high_frequency_loss with its DEFAULT device (kCUDA), so the reference's own
+    // code cannot produce it on the CPU: out3[2] / d_multi stay 0 here and the oracle restates it from the two pieces.
+    (void)d_multi; out3[2] = 0.f;
+    return 0;
+}
+
 // `steps` Adam steps on one tensor of n floats; grads [steps, n]; param updated in place
 int ref_adam(int n, float* param, const float* grads, int steps, double lr, double beta1, double beta2, double eps,
              double weight_decay)

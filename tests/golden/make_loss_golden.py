@@ -25,6 +25,10 @@ lib.ref_adam.argtypes = [C.c_int, fp, fp, C.c_int, C.c_double, C.c_double, C.c_d
 lib.ref_adam.restype = C.c_int
 
 
+lib.ref_frequency_losses.argtypes = [C.c_int, C.c_int, C.c_int, fp, fp, fp, fp, fp]
+lib.ref_frequency_losses.restype = C.c_int
+
+
 def p(a):
     return a.ctypes.data_as(fp)
 
@@ -61,6 +65,16 @@ def loss_case(name, C_, H, W, seed, lam, apply_mask, n_scaling):
     print(name, out3)
 
 
+def freq_case(name, C_, H, W, seed):
+    img, gt = images(C_, H, W, seed)
+    out3 = np.zeros(3, np.float32)
+    dh, dm = np.zeros_like(img), np.zeros_like(img)
+    assert lib.ref_frequency_losses(C_, H, W, p(img), p(gt), p(out3), p(dh), p(dm)) == 0
+    np.savez_compressed(os.path.join(HERE, f"freq_{name}.npz"), image=img, gt=gt, high=out3[0], low=out3[1], multi=out3[2],
+                        d_high=dh, d_multi=dm)
+    print(name, out3)
+
+
 def adam_case(name, n, steps, seed, lr, b1, b2, eps, wd):
     rng = np.random.default_rng(seed)
     p0 = rng.normal(0, 1, n).astype(np.float32)
@@ -78,6 +92,8 @@ if __name__ == "__main__":
     loss_case("masked_48x64", 3, 48, 64, 12, 0.2, True, 500)          # mask_rgb rows + scaling regulariser
     loss_case("ssim_only_20x9", 3, 20, 9, 13, 1.0, False, 0)          # narrower than the window
     loss_case("l1_only_33x40", 1, 33, 40, 14, 0.0, False, 0)
+    freq_case("rgb_40x50", 3, 40, 50, 15)                             # even sizes (bilinear 0.5x -> 20x25)
+    freq_case("rgb_33x47", 3, 33, 47, 16)                             # odd sizes
     adam_case("default", 1000, 5, 21, 1e-3, 0.9, 0.999, 1e-8, 0.0)
     adam_case("segs", 777, 4, 22, 0.0075, 0.9, 0.999, 1e-15, 0.0)     # eps of gaussian_model.cpp:634
     adam_case("decay", 300, 3, 23, 2e-3, 0.8, 0.99, 1e-8, 0.01)

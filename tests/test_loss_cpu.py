@@ -48,3 +48,21 @@ def test_adam_oracle_matches_torch_optim_adam(path):
     np.testing.assert_allclose(d_mine, d_ref, rtol=2e-5, atol=2.0 * ulp)
     if float(g["weight_decay"]) == 0.0:
         assert np.array_equal(p[:7], g["param0"][:7])      # zero gradient, zero moments: untouched
+
+
+FREQ = sorted(glob.glob(os.path.join(GOLD, "freq_*.npz")))
+
+
+@pytest.mark.parametrize("path", FREQ, ids=[os.path.basename(p) for p in FREQ])
+def test_frequency_loss_oracle_matches_reference(path):
+    """high_frequency_loss / low_freq_loss of the reference's own header (incl. its mask-indexing quirk)."""
+    import torch
+    g = np.load(path)
+    x = torch.from_numpy(g["image"]).clone().requires_grad_(True)
+    y = torch.from_numpy(g["gt"])
+    hi = loss_oracle.high_frequency_loss(x, y)
+    hi.backward()
+    np.testing.assert_allclose(float(hi), float(g["high"]), rtol=1e-5)
+    np.testing.assert_allclose(x.grad.numpy(), g["d_high"], rtol=1e-4, atol=1e-5 * float(np.abs(g["d_high"]).max()))
+    np.testing.assert_allclose(float(loss_oracle.low_freq_loss(x.detach(), y)), float(g["low"]), rtol=1e-5)
+    assert len(FREQ) >= 2
