@@ -4,6 +4,7 @@
 #include <torch/extension.h>
 
 #include "gaussian_rasterizer.h"
+#include "loss_utils.h"
 #include "rasterize_points.h"
 
 namespace {
@@ -29,6 +30,18 @@ torch::Tensor mark_visible(torch::Tensor means3D, torch::Tensor viewmatrix, torc
     return markVisible(means3D, viewmatrix, projmatrix);
 }
 
+torch::Tensor lu_l1_loss(torch::Tensor a, torch::Tensor b) { return loss_utils::l1_loss(a, b); }
+torch::Tensor lu_ssim(torch::Tensor a, torch::Tensor b) { return loss_utils::ssim(a, b); }
+torch::Tensor lu_psnr(torch::Tensor a, torch::Tensor b) { return loss_utils::psnr(a, b); }
+torch::Tensor lu_l1_ssim(torch::Tensor image, torch::Tensor gt, double lambda_dssim, torch::Tensor row_mask) {
+    return loss_utils::l1_ssim(image, gt, lambda_dssim, row_mask);
+}
+void lu_adam_step(std::vector<torch::Tensor> params, std::vector<double> lrs, torch::Tensor grad, torch::Tensor m,
+                  torch::Tensor v, int64_t step, double beta1, double beta2, double eps, double weight_decay,
+                  double grad_scale, bool zero_grad) {
+    loss_utils::adam_step(params, lrs, grad, m, v, step, beta1, beta2, eps, weight_decay, grad_scale, zero_grad);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_segs_torch, m) {
@@ -39,4 +52,9 @@ PYBIND11_MODULE(_segs_torch, m) {
     m.def("RasterizeGaussiansprojectCUDA", &RasterizeGaussiansprojectCUDA);
     m.def("distCUDA2", &distCUDA2);
     m.def("rasterizer_forward", &rasterizer_forward);
+    m.def("l1_loss", &lu_l1_loss);
+    m.def("ssim", &lu_ssim);
+    m.def("psnr", &lu_psnr);
+    m.def("l1_ssim", &lu_l1_ssim);
+    m.def("adam_step", &lu_adam_step);
 }

@@ -61,7 +61,8 @@ def _small_setup(device, A=4000, n_views=3):
     cams = anchor_model.circle_keyframes(8, 1.5, (0.0, 0.0, 3.25), tanx, tany, device)[:n_views]
     g = torch.Generator(device="cpu").manual_seed(1)
     targets = [(torch.rand(3, H, W, generator=g) * 0.5).to(device) for _ in cams]
-    targets[1][:, 7:9, :] = 0.0                                      # rows the mapper's mask_rgb removes
+    if len(targets) > 1:
+        targets[1][:, 7:9, :] = 0.0                                  # rows the mapper's mask_rgb removes
     return model, cams, targets, (W, H, tanx, tany)
 
 
@@ -164,3 +165,29 @@ def test_raster_views_match_the_tensor_level_api(device, lanes):
            scene.tanfovy, imgs2)
     torch.cuda.synchronize()
     assert all(torch.equal(a, b) for a, b in zip(imgs2, ref_imgs))
+
+
+def test_mapper_view_edge_cases(device):
+    """No visible anchor (camera looking away): the view contributes the loss of the background image and no
+    gradient; an empty Gaussian set through segs_raster_views leaves a zero image like RasterizeGaussiansCUDA."""
+    from segs_slam_b200 import anchor_model, loss_utils
+    model, cams, targets, (W, H, tanx, tany) = _small_setup(device, A=2000, n_views=1)
+    R = np.diag([-1.0, 1.0, -1.0])                                   # look along -z: every anchor is behind the camera
+    away = anchor_model.Keyframe(R, np.zeros(3), tanx, tany, device)
+    bg = torch.tensor([0.2, 0.4, 0.6], device=device)
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, lanes=1)
+    loss = fm.step([away], targets, optimize=False)
+    res = fm.last_result
+    assert res.n_visible == 0 and res.n_gaussians == 0 and res.num_rendered == 0
+    assert float(fm.bucket.flat.abs().max()) == 0.0
+    expected = loss_utils.l1_ssim_loss(torch.zeros(3, H, W, device=device), targets[0], 0.2)[0]
+    # RasterizeGaussiansCUDA with P == 0 leaves the image ZERO, not background (rasterize_points.cu:81)
+    np.testing.assert_allclose(float(loss), float(expected), rtol=1e-6)
+
+    rb = mapper.RasterBatch(device, lanes=2)
+    e3, e1, e4 = torch.empty(0, 3, device=device), torch.empty(0, 1, device=device), torch.empty(0, 4, device=device)
+    cam = {"viewmatrix": away.world_view_transform_, "projmatrix": away.full_proj_transform_, "campos": away.camera_center_}
+    imgs = [torch.full((3, H, W), 7.0, device=device) for _ in range(2)]
+    Rs = rb.run(e3, e3, e1, e3, e4, bg, [cam, cam], H, W, tanx, tany, imgs)
+    torch.cuda.synchronize()
+    assert Rs == [0, 0] and all(float(i.abs().max()) == 0.0 for i in imgs)

@@ -120,3 +120,57 @@ def test_cpp_empty_and_errors(device, shim):
     with pytest.raises(RuntimeError, match="means3D must have dimensions"):
         shim.RasterizeGaussiansCUDA(bg, torch.zeros((5, 4), device=device), e, e, e, e, 1.0, e, eye, eye, 1.0, 1.0,
                                     16, 16, e, 0, bg, False)
+
+
+# ---- loss_utils drop-in (torch_shim/loss_utils.{h,cpp}) against the goldens of the reference's own header ----------
+import glob  # noqa: E402
+import os  # noqa: E402
+
+import numpy as np  # noqa: E402
+
+_GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+_LOSS = sorted(glob.glob(os.path.join(_GOLD, "loss_*.npz")))
+_ADAM = sorted(glob.glob(os.path.join(_GOLD, "adam_*.npz")))
+
+
+@pytest.mark.parametrize("path", _LOSS, ids=[os.path.basename(p) for p in _LOSS])
+def test_cpp_loss_utils_match_reference_golden(device, shim, path):
+    g = np.load(path)
+    x = torch.from_numpy(g["image"]).to(device).requires_grad_(True)
+    y = torch.from_numpy(g["gt"]).to(device)
+    lam = float(g["lambda_dssim"])
+    mask = (y != 0).any(-1).float() if bool(g["apply_mask"]) else torch.empty(0, device=device)
+    loss = shim.l1_ssim(x, y, lam, mask)
+    if "scaling" in g.files:
+        sc = torch.from_numpy(g["scaling"]).to(device)
+        loss = loss + 0.01 * sc.prod(1).mean()
+    loss.backward()
+    np.testing.assert_allclose(loss.item(), float(g["loss"]), rtol=1e-5)
+    ref = g["dL_dimage"]
+    np.testing.assert_allclose(x.grad.cpu().numpy(), ref, rtol=1e-4, atol=1e-4 * float(np.abs(ref).max()))
+    if not bool(g["apply_mask"]):
+        np.testing.assert_allclose(shim.l1_loss(x.detach(), y).item(), float(g["l1"]), rtol=1e-5)
+        np.testing.assert_allclose(shim.ssim(x.detach(), y).item(), float(g["ssim"]), rtol=1e-5)
+        np.testing.assert_allclose(shim.psnr(x.detach(), y).item(), float(g["psnr"]), rtol=1e-5)
+
+
+@pytest.mark.parametrize("path", _ADAM, ids=[os.path.basename(p) for p in _ADAM])
+def test_cpp_adam_step_matches_torch_optim_adam_golden(device, shim, path):
+    g = np.load(path)
+    n = g["param0"].size
+    cuts = [0, n // 2, n]
+    params = [torch.from_numpy(g["param0"][a:b].copy()).to(device) for a, b in zip(cuts[:-1], cuts[1:])]
+    grad, m, v = (torch.zeros(n, device=device) for _ in range(3))
+    for step, gr in enumerate(g["grads"], start=1):
+        grad.copy_(torch.from_numpy(gr).to(device))
+        shim.adam_step(params, [float(g["lr"])] * 2, grad, m, v, step, float(g["beta1"]), float(g["beta2"]), float(g["eps"]),
+                       float(g["weight_decay"]), 1.0, True)
+        assert float(grad.abs().max()) == 0.0
+    mine = torch.cat(params).cpu().numpy()
+    ulp = float(np.spacing(np.float32(np.abs(g["param0"]).max())))
+    np.testing.assert_allclose(mine - g["param0"], g["param"] - g["param0"], rtol=2e-5, atol=2.0 * ulp)
+
+
+def test_cpp_loss_rejects_cpu_tensors(shim):
+    with pytest.raises(RuntimeError, match="no CPU path"):
+        shim.l1_loss(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8))
