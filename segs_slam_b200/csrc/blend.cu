@@ -179,18 +179,20 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     // pixels that are done / miss the reference's tests simply do not commit.
                     const float4 g0 = s_rec[buf][0][slot];
                     const float4 g1 = s_rec[buf][1][slot];
-                    const float4 g2 = s_rec[buf][2][slot];
                     const float dx = __fsub_rn(g0.x, pixfx);
                     const float dy0 = __fsub_rn(g0.y, pixfy0), dy1 = __fsub_rn(g0.y, pixfy1);
                     const float power0 = gauss_power(dx, dy0, g1.x, g1.y, g1.z);
                     const float power1 = gauss_power(dx, dy1, g1.x, g1.y, g1.z);
                     const float alpha0 = fminf(0.99f, __fmul_rn(g1.w, expf(power0)));
                     const float alpha1 = fminf(0.99f, __fmul_rn(g1.w, expf(power1)));
-                    const float test_T0 = __fmul_rn(T0, __fsub_rn(1.f, alpha0));
-                    const float test_T1 = __fmul_rn(T1, __fsub_rn(1.f, alpha1));
                     // forward.cu:414-429: power > 0 / alpha < 1/255 skip; T < 1e-4 stops the pixel
                     const bool contrib0 = !done0 && !(power0 > 0.0f) && !(alpha0 < 1.0f / 255.0f);
                     const bool contrib1 = !done1 && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f);
+                    // the extent test is a bounding box: a fifth of the hits reach no pixel of the sub-tile at all
+                    if (!__any_sync(FULL, contrib0 || contrib1)) continue;
+                    const float4 g2 = s_rec[buf][2][slot];
+                    const float test_T0 = __fmul_rn(T0, __fsub_rn(1.f, alpha0));
+                    const float test_T1 = __fmul_rn(T1, __fsub_rn(1.f, alpha1));
                     const bool stop0 = contrib0 && (test_T0 < 0.0001f), stop1 = contrib1 && (test_T1 < 0.0001f);
                     done0 = done0 || stop0;
                     done1 = done1 || stop1;
