@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--blocking-sync", type=int, default=-1, help="-1 auto, 0 spin, 1 sleep in the read-back waits")
     ap.add_argument("--lanes", type=int, default=2, help="views in flight per GPU (concurrent lanes of the batch API)")
     ap.add_argument("--no-mapping", action="store_true", help="skip the keyframe-batched mapping measurement")
     ap.add_argument("--mapping-steps", type=int, default=3)
@@ -162,6 +163,9 @@ def main():
     if args.impl == "ours":
         from segs_slam_b200 import _lib, rasterize_points as rp
         lib = _lib.load()
+        # more waiting host threads (ranks x lanes) than cores: sleep in the read-back waits instead of spinning
+        blocking = args.blocking_sync if args.blocking_sync >= 0 else int(world * args.lanes * 2 > (os.cpu_count() or 1))
+        lib.segs_set_blocking_sync(blocking)
 
         def fwd_bwd(cam, dL_dout, pr=None):
             pr = pr or base

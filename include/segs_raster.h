@@ -446,6 +446,10 @@ int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, co
 /* Number of kernels this library has launched in this process so far (all host threads). */
 unsigned long long segs_launch_count(void);
 int segs_profile_enable(int on);
+/* Host threads waiting for the library's small read-backs (num_rendered, decode counts) spin by default; on != 0
+ * makes every host thread that has not waited yet sleep instead (cudaEventBlockingSync) — for boxes that run more
+ * waiting threads (ranks x lanes) than they have cores.  Call before the first forward. */
+int segs_set_blocking_sync(int on);
 int segs_profile_read(float* ms /* [SEGS_PROFILE_STAGES] */);
 
 /* ---- inspection of the opaque buffers (parity tests, debugging) --------------------- */

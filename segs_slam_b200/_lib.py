@@ -159,6 +159,7 @@ _PROTOTYPES = {
     ),
     "segs_launch_count": (C.c_ulonglong, []),
     "segs_profile_enable": (C.c_int, [C.c_int]),
+    "segs_set_blocking_sync": (C.c_int, [C.c_int]),
     "segs_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
     "segs_buffer_section": (
         C.c_int,

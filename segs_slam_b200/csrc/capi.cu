@@ -26,6 +26,13 @@ void set_error(const char* fmt, ...) {
 static std::atomic<unsigned long long> g_launches{0};      // process-wide: lanes launch from their own host threads
 void count_launch() { g_launches.fetch_add(1, std::memory_order_relaxed); }
 
+// Host waits for the two small read-backs (num_rendered, decode counts) spin by default; with more waiting host
+// threads than cores (8 ranks x lanes on one box) they should sleep instead: cudaEventBlockingSync.
+static std::atomic<int> g_blocking_sync{0};
+unsigned readback_event_flags() {
+    return cudaEventDisableTiming | (g_blocking_sync.load(std::memory_order_relaxed) ? cudaEventBlockingSync : 0u);
+}
+
 // ---- layouts --------------------------------------------------------------------------
 GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
     Carver c(base);
@@ -116,7 +123,7 @@ static HostWords pinned_words() {
 // One event per host thread marking "num_rendered has landed in pinned memory".
 static cudaEvent_t readback_event() {
     static thread_local cudaEvent_t ev = nullptr;
-    if (!ev && cudaEventCreateWithFlags(&ev, cudaEventDisableTiming) != cudaSuccess) ev = nullptr;
+    if (!ev && cudaEventCreateWithFlags(&ev, readback_event_flags()) != cudaSuccess) ev = nullptr;
     return ev;
 }
 
@@ -152,6 +159,8 @@ extern "C" {
 int segs_version(void) { return SEGS_ABI_VERSION; }
 
 unsigned long long segs_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+int segs_set_blocking_sync(int on) { g_blocking_sync.store(on != 0); return SEGS_OK; }
 
 int segs_profile_enable(int on) { g_prof.on = on != 0; return SEGS_OK; }
 

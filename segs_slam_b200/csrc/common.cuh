@@ -27,6 +27,7 @@ void set_error(const char* fmt, ...);
         }                                                                                \
     } while (0)
 void count_launch();
+unsigned readback_event_flags();      // flags of the events the host read-backs wait on (segs_set_blocking_sync)
 #define SEGS_LAUNCH_CHECK()                  \
     do {                                     \
         ::segs::count_launch();              \

@@ -1078,7 +1078,7 @@ HostCounts decode_host_counts()
         void *hp = nullptr, *dp = nullptr;
         if (cudaHostAlloc(&hp, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
             cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h.ev, cudaEventDisableTiming) == cudaSuccess) {
+            cudaEventCreateWithFlags(&h.ev, readback_event_flags()) == cudaSuccess) {
             h.host = static_cast<uint32_t*>(hp);
             h.dev = static_cast<uint32_t*>(dp);
         }
