@@ -484,9 +484,11 @@ def main():
                                 "GBps": round(ab[name] / (m * 1e-3) / 1e9, 1) if m > 0 else None}
         top = STAGES[int(np.argmax(ms))]
         achieved = ab[top] / (float(ms[STAGES.index(top)]) * 1e-3) / 1e9
-        traffic = None
+        traffic, issue_pct = None, None
         try:
-            traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(top)
+            tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+            traffic = tj.get(top)
+            issue_pct = tj.get("_issue_active_pct", {}).get(top)
         except Exception:
             pass
         roofline = {"kernel": top, "bound": "hbm", "achieved": round(achieved, 1), "peak": peak_gbs,
@@ -494,7 +496,7 @@ def main():
                     "peak_source": peak_src, "ms_per_launch": round(float(ms[STAGES.index(top)]), 4),
                     "note": "blend kernels are FP32-ALU/MUFU bound, not HBM bound (SURVEY 8d); "
                             "frac is algorithmic bytes / time / copy peak as the contract asks",
-                    "stages": stages_out, "step_share": round(float(ms[STAGES.index(top)] / ms.sum()), 3)}
+                    "issue_active_pct_ncu": issue_pct, "stages": stages_out, "step_share": round(float(ms[STAGES.index(top)] / ms.sum()), 3)}
 
     line = {
         "metric": METRIC, "value": round(value, 2), "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
