@@ -13,8 +13,12 @@ function with world_size 1: sequential rendering of all B views with gradient ac
 Single-view rendering does not shard (sort -> ranges -> blend of one image is one dependency
 chain): replicas only.
 
-Only host-side orchestration lives here; `render_loss` is the per-view work (prefilter -> decode ->
-rasterize -> loss, all on the GPU kernels of this package — `make_render_loss` below builds it).
+Only host-side orchestration lives here.  Two ways to do the per-view work:
+  * `mapping_step` + `make_render_loss`: the autograd composition of the tensor-level API (prefilter -> decode ->
+    rasterize -> loss), reference-shaped, one interpreter-issued launch sequence per view;
+  * `FusedMapper` (anchor model) / `RasterBatch` (explicit Gaussians): the same views issued from C++
+    (`segs_mapper_views` / `segs_raster_views`, csrc/mapper_view.cu) on concurrent lanes, gradients accumulated straight
+    into the flat bucket, one fused Adam launch per step — what bench.py measures.
 """
 from __future__ import annotations
 
