@@ -286,6 +286,15 @@ int segs_decode_backward_ex(
     segs_alloc_fn scratch_alloc, void* scratch_user,
     int flags, void* stream);
 
+/* Densification statistics of one view (GaussianModel::training_statis, src/gaussian_model.cpp:1459-1503), from the
+ * state segs_decode_forward left: for every visible anchor a, opacity_accum[a] += sum over its 10 offsets of
+ * max(neural_opacity, 0) and anchor_demon[a] += 1; for every emitted offset o whose Gaussian was rendered (radii > 0),
+ * offset_gradient_accum[a*10+o] += |dL_dmean2D.xy| and offset_denom[a*10+o] += 1.  radii [n_out], dL_dmean2D [n_out,3]
+ * are the rasterizer's outputs for the decoded Gaussians.  atomic != 0: RED.ADD (concurrent views). */
+int segs_training_statis(int A, const char* decode_state, int n_vis, const float* neural_opacity, const int* radii,
+                         const float* dL_dmean2D, float* opacity_accum, float* anchor_demon,
+                         float* offset_gradient_accum, float* offset_denom, int atomic, void* stream);
+
 /* ---- one keyframe view of the batched mapping step (BASELINE config 4) -------------
  *   segs_mapper_view      the body of GaussianMapper::trainForOneIteration  src/gaussian_mapper.cpp:870-950:
  *                         prefilter_voxel (src/gaussian_renderer.cpp:131-199) -> generate_neural_gaussians
@@ -333,6 +342,11 @@ typedef struct segs_mapper_view_args {
     float* loss_terms_out;          /* {Ll1, ssim, photometric loss} */
     float* dL_dmean2D_out;          /* [A*10,3] capacity: screen-space gradient of the emitted Gaussians (densification) */
     int*   radii_out;               /* [A*10] capacity */
+    /* optional densification statistics (segs_training_statis), all four or none; += */
+    float* stat_opacity_accum;          /* [A]    */
+    float* stat_anchor_demon;           /* [A]    */
+    float* stat_offset_gradient_accum;  /* [A*10] */
+    float* stat_offset_denom;           /* [A*10] */
 } segs_mapper_view_args;
 
 typedef struct segs_mapper_view_result {

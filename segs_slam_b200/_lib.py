@@ -46,7 +46,8 @@ class MapperViewArgs(C.Structure):
                 ("grad_anchor", C.c_void_p), ("grad_anchor_feat", C.c_void_p), ("grad_offset", C.c_void_p),
                 ("grad_scaling", C.c_void_p), ("grad_params", C.POINTER(DecodeGrads)), ("loss_accum", C.c_void_p),
                 ("image_out", C.c_void_p), ("loss_terms_out", C.c_void_p), ("dL_dmean2D_out", C.c_void_p),
-                ("radii_out", C.c_void_p)]
+                ("radii_out", C.c_void_p), ("stat_opacity_accum", C.c_void_p), ("stat_anchor_demon", C.c_void_p),
+                ("stat_offset_gradient_accum", C.c_void_p), ("stat_offset_denom", C.c_void_p)]
 
 
 class RasterViewArgs(C.Structure):
@@ -124,6 +125,10 @@ _PROTOTYPES = {
         [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),
          C.c_void_p, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
          _f32p, _f32p, _f32p, _f32p, C.POINTER(DecodeGrads), ALLOC_FN, C.c_void_p, C.c_int, C.c_void_p],
+    ),
+    "segs_training_statis": (
+        C.c_int,
+        [C.c_int, C.c_void_p, C.c_int, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p],
     ),
     "segs_workspace_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "segs_workspace_destroy": (C.c_int, [C.c_void_p]),

@@ -1260,6 +1260,63 @@ extern "C" int segs_decode_backward_ex(
     return SEGS_OK;
 }
 
+// =======================================================================================
+// densification statistics of one view (GaussianModel::training_statis, gaussian_model.cpp:1459-1503)
+// =======================================================================================
+namespace segs {
+namespace {
+// thread = visible anchor.  opacity_accum[a] += sum_o max(neural_opacity, 0); anchor_demon[a] += 1; for every emitted
+// offset whose Gaussian was rendered (radii > 0): offset_gradient_accum[a,o] += |dL_dmean2D.xy|, offset_denom[a,o] += 1.
+__global__ void __launch_bounds__(256)
+training_statis_kernel(int n_vis, DecodeState st, const float* __restrict__ neural_opacity, const int* __restrict__ radii,
+                       const float* __restrict__ dL_dmean2D, float* __restrict__ opacity_accum,
+                       float* __restrict__ anchor_demon, float* __restrict__ offset_gradient_accum,
+                       float* __restrict__ offset_denom, const int atomic)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= n_vis) return;
+    auto add = [&](float* dst, float v) { if (atomic) atomicAdd(dst, v); else *dst += v; };
+    const size_t a = st.anchor_index[k];
+    const uint32_t m = st.mask_bits[k];
+    size_t r = st.row_start[k];
+    float sum = 0.f;
+#pragma unroll
+    for (int o = 0; o < NOFF; ++o) {
+        const float v = __ldg(neural_opacity + size_t(k) * NOFF + o);
+        sum += v < 0.f ? 0.f : v;                       // torch::where(temp_opacity < 0, 0, temp_opacity)
+    }
+    add(opacity_accum + a, sum);
+    add(anchor_demon + a, 1.f);
+#pragma unroll 1
+    for (int o = 0; o < NOFF; ++o) {
+        if (!((m >> o) & 1u)) continue;
+        if (__ldg(radii + r) > 0) {
+            const float gx = __ldg(dL_dmean2D + 3 * r), gy = __ldg(dL_dmean2D + 3 * r + 1);
+            add(offset_gradient_accum + a * NOFF + o, sqrtf(gx * gx + gy * gy));
+            add(offset_denom + a * NOFF + o, 1.f);
+        }
+        ++r;
+    }
+}
+}  // namespace
+}  // namespace segs
+
+extern "C" int segs_training_statis(int A, const char* decode_state, int n_vis, const float* neural_opacity, const int* radii,
+                                    const float* dL_dmean2D, float* opacity_accum, float* anchor_demon,
+                                    float* offset_gradient_accum, float* offset_denom, int atomic, void* stream_)
+{
+    cudaStream_t stream = static_cast<cudaStream_t>(stream_);
+    if (A < 0 || n_vis < 0 || n_vis > A) { set_error("training_statis: invalid sizes"); return SEGS_ERR_INVALID_ARG; }
+    if (n_vis == 0) return SEGS_OK;
+    if (!decode_state || !neural_opacity || !radii || !dL_dmean2D || !opacity_accum || !anchor_demon || !offset_gradient_accum ||
+        !offset_denom) { set_error("training_statis: NULL pointer"); return SEGS_ERR_INVALID_ARG; }
+    DecodeState st = DecodeState::carve(const_cast<char*>(decode_state), A, nullptr);
+    training_statis_kernel<<<(n_vis + 255) / 256, 256, 0, stream>>>(n_vis, st, neural_opacity, radii, dL_dmean2D, opacity_accum,
+                                                                     anchor_demon, offset_gradient_accum, offset_denom, atomic);
+    SEGS_LAUNCH_CHECK();
+    return SEGS_OK;
+}
+
 extern "C" int segs_decode_backward(
     int A, const unsigned char* visible_mask, const float* anchor, const float* anchor_feat, const float* offset,
     const float* scaling, const float* camera_center, const float* pose, const segs_decode_params* params,

@@ -218,7 +218,13 @@ static int mapper_view_impl(segs_workspace* ws, const segs_mapper_view_args* a, 
     add_scalar_kernel<<<1, 1, 0, stream>>>(a->loss_accum, loss3 + 2);
     SEGS_LAUNCH_CHECK();
     if (a->loss_terms_out) SEGS_CUDA_CHECK(cudaMemcpyAsync(a->loss_terms_out, loss3, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
-    if (P == 0) return SEGS_OK;          // nothing to back-propagate into
+    if (P == 0) {                        // nothing to back-propagate into; visible anchors still count in the statistics
+        if (n_vis > 0 && (a->stat_opacity_accum || a->stat_anchor_demon || a->stat_offset_gradient_accum || a->stat_offset_denom))
+            return segs_training_statis(A, dstate, n_vis, neural_opacity, anchor_radii /* not read: no offset survived */, xyz,
+                                        a->stat_opacity_accum, a->stat_anchor_demon, a->stat_offset_gradient_accum,
+                                        a->stat_offset_denom, concurrent ? 1 : 0, stream);
+        return SEGS_OK;
+    }
     if ((rc = segs_loss_l1_ssim_backward(3, H, W, image, a->gt_image, a->row_mask, 1.f - lam, -lam, nullptr, lstate, dL_dimage, stream))) return rc;
 
     // ---- rasterizer backward (RasterizeGaussiansBackwardCUDA) ----
@@ -237,6 +243,11 @@ static int mapper_view_impl(segs_workspace* ws, const segs_mapper_view_args* a, 
                                    dL_dimage, dL_dmean2D, dL_dconic, dL_dopacity, dL_dcolor, dL_dmean3D, dL_dcov3D, nullptr,
                                    dL_dscale, dL_drot, stream))) return rc;
     if (a->radii_out) SEGS_CUDA_CHECK(cudaMemcpyAsync(a->radii_out, radii, Pz * sizeof(int), cudaMemcpyDeviceToDevice, stream));
+    // training_statis (gaussian_mapper.cpp:963): this view's contribution to the densification statistics
+    if (a->stat_opacity_accum || a->stat_anchor_demon || a->stat_offset_gradient_accum || a->stat_offset_denom)
+        if ((rc = segs_training_statis(A, dstate, n_vis, neural_opacity, radii, dL_dmean2D, a->stat_opacity_accum,
+                                       a->stat_anchor_demon, a->stat_offset_gradient_accum, a->stat_offset_denom,
+                                       concurrent ? 1 : 0, stream))) return rc;
     // 0.01 * scaling.prod(1).mean(): value into the loss, gradient on top of the rasterizer's dL_dscale
     if (a->scaling_reg_weight != 0.f)
         if ((rc = segs_scaling_reg(P, scaling, a->scaling_reg_weight, nullptr, dL_dscale, a->loss_accum, stream))) return rc;

@@ -160,7 +160,7 @@ class FusedMapper:
 
     def __init__(self, pc, image_height: int, image_width: int, tanfovx: float, tanfovy: float, bg: torch.Tensor,
                  lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None,
-                 lanes: int = 2):
+                 lanes: int = 2, statistics: bool = False):
         import ctypes as C
         from . import _lib
         from .gaussian_renderer import _weights
@@ -182,6 +182,18 @@ class FusedMapper:
         v = iter(self.bucket.views[4:])
         self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
         self.loss_accum = torch.zeros((), dtype=torch.float32, device=pc._anchor.device)
+        # densification statistics (GaussianModel::training_statis, gaussian_model.cpp:1459-1503): running accumulators
+        # opacity_accum [A,1], anchor_demon [A,1], offset_gradient_accum [A*10,1], offset_denom [A*10,1] and the per-step
+        # delta the views add to; the delta is all-reduced (the second, small all-reduce of SURVEY §8e) so that the
+        # replicas' statistics — and therefore their densification decisions — stay identical
+        self.statistics = bool(statistics)
+        if self.statistics:
+            A_ = pc._anchor.size(0)
+            self.stats = torch.zeros(22 * A_, dtype=torch.float32, device=pc._anchor.device)
+            self.stats_delta = torch.zeros_like(self.stats)
+            cut = lambda t: (t[:A_].view(A_, 1), t[A_:2 * A_].view(A_, 1), t[2 * A_:12 * A_].view(10 * A_, 1), t[12 * A_:].view(10 * A_, 1))
+            self.opacity_accum, self.anchor_demon, self.offset_gradient_accum, self.offset_denom = cut(self.stats)
+            self._stat_delta_views = cut(self.stats_delta)
         # lanes: concurrent views per rank (segs_mapper_views): lane = workspace + stream + persistent host thread.
         # The sorts / decode / read-backs of one view overlap the issue-bound blend kernels of another; gradients
         # are then accumulated with RED.ADD (one more order-dependent sum on top of the rasterizer backward's own).
@@ -238,6 +250,9 @@ class FusedMapper:
                                                                              v[2].data_ptr(), v[3].data_ptr())
         a.grad_params = C.pointer(self._dgrads)
         a.loss_accum = self.loss_accum.data_ptr()
+        if self.statistics:
+            (a.stat_opacity_accum, a.stat_anchor_demon, a.stat_offset_gradient_accum,
+             a.stat_offset_denom) = [t.data_ptr() for t in self._stat_delta_views]
         self._args = a
 
     def _fill(self, a, cam, target, row_mask, keep):
@@ -303,6 +318,8 @@ class FusedMapper:
         if self._dirty:
             self.bucket.zero_()                                      # normally cleared by the previous Adam launch
         self._dirty = True
+        if self.statistics:
+            self.stats_delta.zero_()
         mine = partition_views(n_views, world, rank)
         self.render_views([cameras[v] for v in mine], [targets[v] for v in mine],
                           None if row_masks is None else [row_masks[v] for v in mine])
@@ -310,6 +327,10 @@ class FusedMapper:
         if world > 1:
             dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
             dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
+            if self.statistics:
+                dist.all_reduce(self.stats_delta, op=dist.ReduceOp.SUM, group=self.group)
+        if self.statistics:
+            self.stats.add_(self.stats_delta)
         if optimize:
             self.optimizer.step(grad_scale=1.0 / float(n_views), zero_grad=True)
             self._dirty = False

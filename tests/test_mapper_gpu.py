@@ -191,3 +191,44 @@ def test_mapper_view_edge_cases(device):
     Rs = rb.run(e3, e3, e1, e3, e4, bg, [cam, cam], H, W, tanx, tany, imgs)
     torch.cuda.synchronize()
     assert Rs == [0, 0] and all(float(i.abs().max()) == 0.0 for i in imgs)
+
+
+@pytest.mark.parametrize("lanes", [1, 2])
+def test_fused_mapper_training_statistics(device, lanes):
+    """The densification statistics the fused view accumulates (segs_training_statis) against the restatement of
+    GaussianModel::training_statis (oracle/statis_oracle.py) fed by the autograd composition of the same views."""
+    import statis_oracle
+    from segs_slam_b200 import GaussianRasterizationSettings, GaussianRasterizer, generate_neural_gaussians, loss_utils
+    from segs_slam_b200.rasterize_points import RasterizeGaussiansfilterCUDA
+    model, cams, targets, (W, H, tanx, tany) = _small_setup(device, A=4000, n_views=3)
+    bg = torch.zeros(3, device=device)
+    A = model._anchor.size(0)
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lanes=lanes, statistics=True)
+    fm.step(cams, targets, optimize=False)
+    fm.step(cams, targets, optimize=False)                          # running accumulators: two steps = twice the views
+
+    z = lambda n: torch.zeros(n, 1, device=device)
+    ref = dict(opacity_accum=z(A), anchor_demon=z(A), offset_gradient_accum=z(10 * A), offset_denom=z(10 * A))
+    e = torch.empty(0, device=device)
+    for cam, tgt in zip(cams, targets):
+        with torch.no_grad():
+            radii_a = RasterizeGaussiansfilterCUDA(model.get_anchor(), model.get_scaling()[:, :3].contiguous(),
+                                                   torch.nn.functional.normalize(model._rotation), 1.0, e,
+                                                   cam.world_view_transform_, cam.full_proj_transform_, tanx, tany, H, W, False)
+            visible = radii_a > 0
+        xyz, color, opacity, scaling, rots, nop, mask = generate_neural_gaussians(cam, model, visible)
+        settings = GaussianRasterizationSettings(H, W, tanx, tany, bg, 1.0, cam.world_view_transform_, cam.full_proj_transform_,
+                                                 0, cam.camera_center_, False)
+        means2D = torch.zeros_like(xyz, requires_grad=True)
+        image, radii = GaussianRasterizer(settings)(xyz, means2D, opacity, False, True, True, True, False, e, color, scaling,
+                                                    rots, e)
+        loss = loss_utils.l1_ssim_loss(image, tgt, 0.2)[0] + loss_utils.scaling_reg(scaling, 0.01)
+        loss.backward()
+        for _ in range(2):
+            statis_oracle.training_statis(ref, means2D.grad, nop.detach(), radii > 0, mask, visible)
+    assert torch.equal(fm.anchor_demon, ref["anchor_demon"])
+    assert torch.equal(fm.offset_denom, ref["offset_denom"])
+    torch.testing.assert_close(fm.opacity_accum, ref["opacity_accum"], rtol=1e-5, atol=1e-6)
+    scale = float(ref["offset_gradient_accum"].max())
+    assert scale > 0
+    torch.testing.assert_close(fm.offset_gradient_accum, ref["offset_gradient_accum"], rtol=1e-4, atol=1e-4 * scale)
