@@ -52,3 +52,23 @@ class FusedAdam:
         with torch.cuda.device(b.flat.device):
             _lib.check(lib.segs_adam_step(len(b.params), arr, b.flat.data_ptr(), self.exp_avg.data_ptr(),
                                           self.exp_avg_sq.data_ptr(), float(grad_scale), int(zero_grad), _stream()))
+
+
+def get_expon_lr_func(step: int, lr_init: float, lr_final: float, lr_delay_mult: float = 1.0, max_steps: int = 1000000,
+                      lr_delay_steps: int = 0) -> float:
+    """GaussianModel::getExponLrFunc / exponLrFunc (/root/reference/src/gaussian_model.cpp:1368-1407): log-linear
+    interpolation from lr_init to lr_final over max_steps with an optional sine warm-up; FP32 arithmetic like the
+    reference.  Host scalar code (the per-group learning rates the mapper sets every iteration, :874-960)."""
+    import math
+
+    import numpy as np
+    f = np.float32
+    if step < 0 or (lr_init == 0.0 and lr_final == 0.0):
+        return 0.0
+    if lr_delay_steps > 0:
+        delay_rate = f(lr_delay_mult) + (f(1.0) - f(lr_delay_mult)) * f(math.sin(f(math.pi / 2) * f(np.clip(f(step) / f(lr_delay_steps), 0.0, 1.0))))
+    else:
+        delay_rate = f(1.0)
+    t = f(np.clip(f(step) / f(max_steps), 0.0, 1.0))
+    log_lerp = f(math.exp(f(math.log(f(lr_init))) * (f(1.0) - t) + f(math.log(f(lr_final))) * t))
+    return float(f(delay_rate) * log_lerp)

@@ -106,3 +106,18 @@ def test_mapper_view_rejects_null_arguments():
     assert lib.segs_workspace_destroy(ws) == 0
     assert lib.segs_loss_state_bytes(3, 680, 1200) > 3 * 3 * 680 * 1200 * 4
     assert lib.segs_adam_step(1, None, None, None, None, 1.0, 0, None) != 0
+
+
+def test_expon_lr_schedule_matches_reference_formula():
+    """getExponLrFunc (gaussian_model.cpp:1390-1407): end points, geometric midpoint, clamping, the zero shortcut."""
+    import math
+    from segs_slam_b200.optim import get_expon_lr_func as lr
+    assert lr(-1, 1e-2, 1e-4) == 0.0 and lr(10, 0.0, 0.0) == 0.0
+    assert abs(lr(0, 1e-2, 1e-4, max_steps=1000) - 1e-2) < 1e-8
+    assert abs(lr(1000, 1e-2, 1e-4, max_steps=1000) - 1e-4) < 1e-10
+    assert abs(lr(5000, 1e-2, 1e-4, max_steps=1000) - 1e-4) < 1e-10                      # clamped
+    assert abs(lr(500, 1e-2, 1e-4, max_steps=1000) - 1e-3) < 1e-8                        # log-linear: geometric mean
+    # sine warm-up: delay_mult at step 0, 1 at lr_delay_steps
+    assert abs(lr(0, 1e-2, 1e-4, 0.01, 1000, lr_delay_steps=100) - 1e-4) < 1e-9
+    mid = lr(50, 1e-2, 1e-2, 0.01, 1000, lr_delay_steps=100)
+    assert abs(mid - 1e-2 * (0.01 + 0.99 * math.sin(math.pi / 4))) < 1e-7
