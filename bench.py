@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--blocking-sync", type=int, default=-1, help="-1 auto, 0 spin, 1 sleep in the read-back waits")
-    ap.add_argument("--lanes", type=int, default=2, help="views in flight per GPU (concurrent lanes of the batch API)")
+    ap.add_argument("--lanes", type=int, default=4, help="views in flight per GPU (concurrent lanes of the batch API)")
     ap.add_argument("--no-mapping", action="store_true", help="skip the keyframe-batched mapping measurement")
     ap.add_argument("--mapping-steps", type=int, default=3)
     return ap.parse_args()

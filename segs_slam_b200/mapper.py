@@ -160,7 +160,7 @@ class FusedMapper:
 
     def __init__(self, pc, image_height: int, image_width: int, tanfovx: float, tanfovy: float, bg: torch.Tensor,
                  lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None,
-                 lanes: int = 2, statistics: bool = False):
+                 lanes: int = 4, statistics: bool = False):
         import ctypes as C
         from . import _lib
         from .gaussian_renderer import _weights
@@ -344,7 +344,7 @@ class RasterBatch:
     (src/gaussian_rasterizer.cpp:88-154), the parameter gradients ADDED to caller-owned accumulators — the
     rasterizer-only sibling of FusedMapper, and what bench.py times on BASELINE config 2."""
 
-    def __init__(self, device, lanes: int = 2):
+    def __init__(self, device, lanes: int = 4):
         import ctypes as C
         from . import _lib
         self._C, self._L, self.lib = C, _lib, _lib.load()
