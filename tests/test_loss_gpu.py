@@ -175,3 +175,17 @@ def test_frequency_losses_match_reference_golden(path, device):
     ms = loss_utils.multi_scale_loss(x, y, [1.0, 0.5])
     r = loss_oracle.multi_scale_loss(torch.from_numpy(g["image"]), torch.from_numpy(g["gt"]), [1.0, 0.5])
     np.testing.assert_allclose(ms.item(), float(r), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape", [(3, 1, 1), (3, 7, 300), (1, 17, 31), (3, 16, 32), (3, 33, 65), (2, 200, 45), (3, 5, 5)])
+def test_loss_ragged_sizes_against_oracle(device, shape):
+    """Tile edges of the 32x16 CTA tiles, images smaller than the 11x11 window, single pixels, non-RGB channel counts."""
+    C_, H, W = shape
+    rng = np.random.default_rng(H * 1000 + W)
+    gt = rng.uniform(0, 1, shape).astype(np.float32)
+    img = np.clip(gt + rng.normal(0, 0.15, shape), 0, 1).astype(np.float32)
+    o = _run(img, gt, 0.2, False, None, device)
+    r = loss_oracle.mapper_loss(img, gt, 0.2, False)
+    for k in ("l1", "ssim", "loss"):
+        np.testing.assert_allclose(o[k], float(r[k]), rtol=2e-5)
+    _grad_close(o["dL_dimage"], r["dL_dimage"])
