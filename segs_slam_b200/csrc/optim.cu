@@ -64,12 +64,14 @@ struct AddList { float* dst[24]; const float* src[24]; unsigned long long n[24];
 __global__ void __launch_bounds__(256)
 add_many_kernel(const AddList z)
 {
-    for (int a = 0; a < z.count; ++a) {
-        float* d = z.dst[a];
-        const float* s = z.src[a];
-        const unsigned long long n = z.n[a];
-        for (unsigned long long i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x)
-            if (z.atomic) atomicAdd(d + i, s[i]); else d[i] += s[i];
+    // blockIdx.y = array: the arrays proceed side by side (18 tiny MLP tensors would otherwise be 18 dependent
+    // load-add-store round trips)
+    const int a = blockIdx.y;
+    float* d = z.dst[a];
+    const float* s = z.src[a];
+    const unsigned long long n = z.n[a];
+    for (unsigned long long i = size_t(blockIdx.x) * blockDim.x + threadIdx.x; i < n; i += size_t(gridDim.x) * blockDim.x) {
+        if (z.atomic) atomicAdd(d + i, s[i]); else d[i] += s[i];
     }
 }
 
@@ -137,7 +139,7 @@ int segs_accumulate(int n_arrays, float* const* dst, const float* const* src, co
         if (!z.count) continue;
         const unsigned long long want = (largest + 255) / 256;
         const int grid = (int)(want < (unsigned long long)(SM_COUNT * 8) ? want : (unsigned long long)(SM_COUNT * 8));
-        add_many_kernel<<<grid, 256, 0, stream>>>(z);
+        add_many_kernel<<<dim3(grid, z.count), 256, 0, stream>>>(z);
         SEGS_LAUNCH_CHECK();
     }
     return SEGS_OK;
