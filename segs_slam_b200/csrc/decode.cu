@@ -661,7 +661,7 @@ constexpr int F_DLOG = F_DPREB + FEAT;     // bank logit gradients [3]
 constexpr int F_CAT = F_DLOG + 3;          // bank input [view, dist] [4]
 constexpr int FACT_ROWS = F_CAT + 4;       // 409
 
-__global__ void __launch_bounds__(DEC_THREADS, 3)
+__global__ void __launch_bounds__(DEC_THREADS, 4)
 decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float* __restrict__ anchor_feat,
                        const float* __restrict__ offset, const float* __restrict__ scaling,
                        const float* __restrict__ cam, const Pose7 pose, const segs_decode_params p, DecodeState st,
@@ -1210,7 +1210,7 @@ extern "C" int segs_decode_backward_ex(
     DecodeState st = DecodeState::carve(const_cast<char*>(state), A, nullptr);
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
-    decode_backward_kernel<<<std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 3), DEC_THREADS, 0, stream>>>(
+    decode_backward_kernel<<<std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 4), DEC_THREADS, 0, stream>>>(
         n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
         g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
     SEGS_LAUNCH_CHECK();
