@@ -605,6 +605,7 @@ def mapping_reference(args, dev):
         return {"unavailable": f"{type(exc).__name__}: {exc}"}
     torch.backends.cuda.matmul.allow_tf32 = False
     torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True          # the reference arm at its best: cuDNN times its conv2d algorithms once
     model, cams, targets, (W, H, tanx, tany) = _mapping_setup(dev)
     # the decode oracle reads its configuration from `cfg`
     model.cfg = decode_oracle.DecodeConfig(appearance_dim=model.appearance_dim, use_feat_bank=model.use_feat_bank)
