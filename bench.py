@@ -46,6 +46,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference", "reference-cpu"])
     ap.add_argument("--config", default="C2")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-numa-bind", action="store_true", help="multi-rank runs: do not pin each rank to its GPU's NUMA node")
     ap.add_argument("--blocking-sync", type=int, default=-1, help="-1 auto, 0 spin, 1 sleep in the read-back waits")
     ap.add_argument("--lanes", type=int, default=4, help="views in flight per GPU (concurrent lanes of the batch API)")
     ap.add_argument("--no-mapping", action="store_true", help="skip the keyframe-batched mapping measurement")
@@ -141,6 +142,7 @@ def main():
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device (there is no CPU fallback for the product path)")
+    numa = _bind_to_gpu_numa_node(local_rank) if (distributed and not args.no_numa_bind) else None
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if distributed and args.impl == "ours":
@@ -506,6 +508,7 @@ def main():
                                f"(BASELINE.md section 3), colours precomputed, scale+quaternion",
                    "views_per_step_per_gpu": VIEWS_PER_STEP, "views_in_flight_per_gpu": LANES, "P": P, "W": W, "H": H,
                    "num_rendered_mean": round(R_mean), "parallelism": f"dp{n_ranks} (keyframe views)",
+                   "numa_node_rank0": numa,
                    "l2": "working set per view (~0.45 GB state + gradients) exceeds the 126 MB L2; no flush"},
         "clocks": clocks,
         "e2e": {"value": round(e2e_value, 2), "unit": UNIT, "h2d_bytes_per_step": int(h2d),
@@ -629,6 +632,31 @@ def mapping_reference(args, dev):
                                    "unmodified reference rasterizer kernels + ATen decode/loss/Adam (tests/ref_mapper.py)",
                        "loss": "0.8 L1 + 0.2 (1 - SSIM) + 0.01 scaling regulariser"},
             "losses": [round(float(x), 5) for x in losses[:4]]}
+
+
+def _bind_to_gpu_numa_node(local_rank):
+    """Multi-rank runs: pin this rank's host threads (and therefore its pinned staging buffers, first-touch) to the
+    NUMA node its GPU hangs off, like `numactl --cpunodebind --membind` per rank.  The end-to-end pipeline moves
+    280 MB per step and rank over PCIe; with 8 ranks allocating on whatever node they start on, half of that crosses
+    the socket interconnect.  Returns the node, or None when the platform does not expose one."""
+    try:
+        import torch
+        pr = torch.cuda.get_device_properties(local_rank)
+        bdf = "%04x:%02x:%02x.0" % (pr.pci_domain_id, pr.pci_bus_id, pr.pci_device_id)
+        node = int(open(f"/sys/bus/pci/devices/{bdf}/numa_node").read().strip())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            a, _, b = part.partition("-")
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:
+        return None
 
 
 def _gpu_reference_available():
