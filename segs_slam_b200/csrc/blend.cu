@@ -13,9 +13,9 @@
 //    ids prefetched one batch further ahead, so the gather latency of batch b+1 hides behind
 //    the blending of batch b.  Colours ride in the record: the reference's per-blended-pair
 //    global colour loads (forward.cu:433) are gone.
-//  * Per 32 staged Gaussians each lane tests ONE Gaussian's conservative extent against the
-//    warp's sub-tile; a ballot turns that into a bitmask and the warp only runs the per-pixel
-//    maths for the set bits.  Culled Gaussians cannot pass the reference's alpha >= 1/255
+//  * Every staged Gaussian's conservative extent is tested ONCE per CTA against the tile's four
+//    sub-tiles (a 4-bit mask in shared memory); per 32 staged Gaussians a warp ballots its own bit
+//    and only runs the per-pixel maths for the set bits.  Culled Gaussians cannot pass the reference's alpha >= 1/255
 //    test for any pixel of the sub-tile, so the blended result, final_T and n_contrib are
 //    unchanged (n_contrib counts list positions, which are tracked arithmetically).
 //  * Early termination is per warp (all 32 pixels saturated) on top of the reference's
@@ -92,6 +92,24 @@ __device__ __forceinline__ SubTile make_subtile(int tile, int grid_x) {
     return s;
 }
 
+// 4-bit mask of the tile's 8x8 sub-tiles (bit = warp index: x half | y half << 1) the conservative extent of one
+// staged Gaussian reaches; computed ONCE per CTA and record (each warp used to run its own test on every record).
+// Written so that NaNs never cull.
+__device__ __forceinline__ uint32_t subtile_mask(float4 g0, float tx0, float ty0) {
+    const float xlo = g0.x - g0.z, xhi = g0.x + g0.z, ylo = g0.y - g0.w, yhi = g0.y + g0.w;
+    const bool c0 = !(xhi < tx0 || xlo > tx0 + 7.f), c1 = !(xhi < tx0 + 8.f || xlo > tx0 + 15.f);
+    const bool r0 = !(yhi < ty0 || ylo > ty0 + 7.f), r1 = !(yhi < ty0 + 8.f || ylo > ty0 + 15.f);
+    return (uint32_t)(c0 && r0) | ((uint32_t)(c1 && r0) << 1) | ((uint32_t)(c0 && r1) << 2) | ((uint32_t)(c1 && r1) << 3);
+}
+
+__device__ __forceinline__ void compute_masks(uint8_t* dst, const float4* g0s, int n, float tx0, float ty0) {
+#pragma unroll
+    for (int k = 0; k < PER_THREAD; ++k) {
+        const int s = k * BLEND_THREADS + threadIdx.x;
+        if (s < n) dst[s] = (uint8_t)subtile_mask(g0s[s], tx0, ty0);
+    }
+}
+
 // gather `n` records (list positions first .. first + n - 1 of `list`) into one shared-memory stage
 __device__ __forceinline__ void stage_records(float4 (*dst)[BATCH], uint32_t* dst_id, const float4* __restrict__ rec,
                                               const uint32_t (&ids)[PER_THREAD], int n) {
@@ -126,12 +144,14 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                      uint32_t* __restrict__ n_contrib, float* __restrict__ out_color)
 {
     __shared__ float4 s_rec[2][3][BATCH];
+    __shared__ uint8_t s_mask[BATCH];
 
     const int tile = blockIdx.x;
     const SubTile st = make_subtile(tile, grid_x);
     const bool inside0 = st.px < W && st.py0 < H, inside1 = st.px < W && st.py1 < H;
     const float pixfx = (float)st.px, pixfy0 = (float)st.py0, pixfy1 = (float)st.py1;
-    const int lane = threadIdx.x & 31;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const float tile_x0 = (float)((tile % grid_x) * TILE_X), tile_y0 = (float)((tile / grid_x) * TILE_Y);
 
     const uint2 range = ranges[tile];
     const int len = (int)(range.y - range.x);
@@ -162,14 +182,15 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         }
         // batch b visible to all; also the CTA-wide "everyone is done" vote of forward.cu:387
         if (__syncthreads_and(done0 && done1)) break;
+        const int n_in = min(BATCH, len - b * BATCH);
+        compute_masks(s_mask, s_rec[buf][0], n_in, tile_x0, tile_y0);
+        __syncthreads();
 
         if (!__all_sync(FULL, done0 && done1)) {
-            const int n_in = min(BATCH, len - b * BATCH);
             const int base = b * BATCH;
             for (int c = 0; c * 32 < n_in; ++c) {
                 const int slot_l = c * 32 + lane;
-                bool hit = false;
-                if (slot_l < n_in) hit = extent_hits(s_rec[buf][0][slot_l], st.wx0, st.wx1, st.wy0, st.wy1);
+                const bool hit = slot_l < n_in && ((s_mask[slot_l] >> warp) & 1u);
                 unsigned mask = __ballot_sync(FULL, hit);
                 while (mask) {
                     const int j = __ffs(mask) - 1;
@@ -286,12 +307,14 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 {
     __shared__ float4 s_rec[2][3][BATCH];
     __shared__ uint32_t s_id[2][BATCH];
+    __shared__ uint8_t s_mask[BATCH];
     __shared__ int s_bmax;
 
     const int tile = blockIdx.x;
     const SubTile st = make_subtile(tile, grid_x);
     const float pixfx = (float)st.px, pixfy0 = (float)st.py0, pixfy1 = (float)st.py1;
-    const int tid = threadIdx.x, lane = tid & 31;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const float tile_x0 = (float)((tile % grid_x) * TILE_X), tile_y0 = (float)((tile / grid_x) * TILE_Y);
 
     const uint2 range = ranges[tile];
     const uint32_t* list = point_list + range.x;
@@ -350,13 +373,13 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
             cp_async_wait<0>();
         }
         __syncthreads();
+        compute_masks(s_mask, s_rec[buf][0], n_in, tile_x0, tile_y0);
+        __syncthreads();
 
         if (lo < wmax) {
             for (int c = (n_in - 1) >> 5; c >= 0; --c) {
                 const int slot_l = c * 32 + lane;
-                bool hit = false;
-                if (slot_l < n_in && lo + slot_l < wmax)
-                    hit = extent_hits(s_rec[buf][0][slot_l], st.wx0, st.wx1, st.wy0, st.wy1);
+                const bool hit = slot_l < n_in && lo + slot_l < wmax && ((s_mask[slot_l] >> warp) & 1u);
                 unsigned mask = __ballot_sync(FULL, hit);
                 while (mask) {
                     const int j = 31 - __clz(mask);
