@@ -144,6 +144,24 @@ def make_render_loss(pc, cameras, targets, image_height: int, image_width: int, 
     return render_loss
 
 
+def exchange_step(grad_flat: torch.Tensor, loss_accum: torch.Tensor, stats_delta: torch.Tensor | None = None,
+                  stats: torch.Tensor | None = None, group=None) -> torch.Tensor:
+    """The exchange of one batched step between the ranks: ONE all-reduce(sum) of the flat gradient
+    bucket, the loss sum, and — when densification statistics are kept — the second, small all-reduce of this step's
+    statistics delta, which is then added to the running accumulators on every rank (so every replica holds the
+    statistics of ALL views and takes the same densification decisions).  Device-agnostic host logic (NCCL on the GPU
+    box, gloo in tests/test_mapper_cpu.py).  -> loss sum over all ranks (a new tensor)."""
+    loss = loss_accum.clone()
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+        dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
+        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+        if stats_delta is not None:
+            dist.all_reduce(stats_delta, op=dist.ReduceOp.SUM, group=group)
+    if stats_delta is not None and stats is not None:
+        stats.add_(stats_delta)
+    return loss
+
+
 class FusedMapper:
     """The keyframe-batched mapping step with the per-view work issued from C++ (`segs_mapper_view`,
     csrc/mapper_view.cu): prefilter -> decode -> rasterize -> L1+SSIM (+ scaling regulariser) -> backward, the
@@ -323,14 +341,8 @@ class FusedMapper:
         mine = partition_views(n_views, world, rank)
         self.render_views([cameras[v] for v in mine], [targets[v] for v in mine],
                           None if row_masks is None else [row_masks[v] for v in mine])
-        loss = self.loss_accum.clone()
-        if world > 1:
-            dist.all_reduce(self.bucket.flat, op=dist.ReduceOp.SUM, group=self.group)
-            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=self.group)
-            if self.statistics:
-                dist.all_reduce(self.stats_delta, op=dist.ReduceOp.SUM, group=self.group)
-        if self.statistics:
-            self.stats.add_(self.stats_delta)
+        loss = exchange_step(self.bucket.flat, self.loss_accum, self.stats_delta if self.statistics else None,
+                             self.stats if self.statistics else None, self.group)
         if optimize:
             self.optimizer.step(grad_scale=1.0 / float(n_views), zero_grad=True)
             self._dirty = False

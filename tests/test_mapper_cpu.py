@@ -81,3 +81,35 @@ def test_two_rank_step_matches_single_process():
         assert torch.allclose(a, b.detach(), rtol=1e-5, atol=1e-6)    # == sequential accumulation (sum order differs)
     assert l0 == l1
     assert all(abs(x - y) < 1e-5 for x, y in zip(l0, ref_losses))
+
+
+def _exchange_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # every rank holds the gradients / loss / statistics of ITS views only (rank r: views r, r + 2, ...)
+    views = mapper.partition_views(6, world, rank)
+    grad = torch.zeros(10)
+    loss = torch.zeros(())
+    delta, stats = torch.zeros(4), torch.full((4,), 100.0)
+    for v in views:
+        grad += torch.arange(10, dtype=torch.float32) * (v + 1)
+        loss += 0.5 * (v + 1)
+        delta += torch.tensor([1.0, float(v), 0.0, 2.0])
+    total = mapper.exchange_step(grad, loss, delta, stats)
+    out[rank] = (grad.clone(), float(total), stats.clone(), float(loss))
+    dist.destroy_process_group()
+
+
+def test_exchange_step_sums_gradients_loss_and_statistics_over_ranks():
+    """FusedMapper's rank exchange (gradient bucket, loss, densification-statistics delta) on gloo, world size 2."""
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_exchange_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    (g0, l0, s0, own0), (g1, l1, s1, own1) = out[0], out[1]
+    assert torch.equal(g0, g1) and torch.equal(g0, torch.arange(10, dtype=torch.float32) * 21)     # 1 + ... + 6
+    assert l0 == l1 == 0.5 * 21 and own0 != own1                    # the local accumulators are left alone
+    assert torch.equal(s0, s1) and torch.equal(s0, torch.tensor([106.0, 115.0, 100.0, 112.0]))
+    # single process: no collective, statistics still accumulate
+    stats = torch.zeros(2)
+    total = mapper.exchange_step(torch.ones(3), torch.tensor(2.0), torch.tensor([1.0, 2.0]), stats)
+    assert float(total) == 2.0 and torch.equal(stats, torch.tensor([1.0, 2.0]))
