@@ -422,22 +422,6 @@ int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, Bin
     fine_write_kernel<<<nst * SSIDE, FINE_THREADS, 0, stream>>>(pl.sgrid_x, vp.grid_x, vp.grid_y, b.st_begin, b.st_end,
                                                                   keys, vals, img.ranges, b.point_list);
     SEGS_LAUNCH_CHECK();
-    if (getenv("SEGS_DEBUG_BINNING")) {
-        cudaStreamSynchronize(stream);
-        std::vector<uint32_t> hk(Rc), hb(nst), he(nst), tc(T);
-        cudaMemcpy(hk.data(), keys, Rc * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(hb.data(), b.st_begin, nst * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(he.data(), b.st_end, nst * 4, cudaMemcpyDeviceToHost);
-        cudaMemcpy(tc.data(), b.tile_counts, T * 4, cudaMemcpyDeviceToHost);
-        fprintf(stderr, "DEBUG P=%d R=%d Rc=%d nst=%d passes=%d\n", P, R, Rc, nst, pl.sort_passes);
-        for (int i = 0; i < nst && i < 8; ++i) fprintf(stderr, "  st %d: [%u, %u)\n", i, hb[i], he[i]);
-        int unsorted = 0; for (int i = 1; i < Rc; ++i) if ((hk[i] & 0xFFFF) < (hk[i-1] & 0xFFFF)) ++unsorted;
-        fprintf(stderr, "  unsorted pairs %d; keys[0..3] %08x %08x %08x last %08x\n", unsorted, hk[0], hk[1], hk[2], hk[Rc-1]);
-        unsigned long long sum = 0; for (int i = 0; i < T; ++i) sum += tc[i];
-        fprintf(stderr, "  sum tile_counts %llu\n", sum);
-        for (int i = 0; i < T && i < 24; ++i) fprintf(stderr, " %u", tc[i]);
-        fprintf(stderr, "\n");
-    }
     return SEGS_OK;
 }
 
