@@ -26,8 +26,6 @@
 //      exactly the reference's sorted order, bit for bit.  point_list is the only R-sized
 //      array ever written (4 B/instance).
 #include "common.cuh"
-#include <vector>
-#include <cstdlib>
 
 namespace segs {
 
