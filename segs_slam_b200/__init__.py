@@ -11,6 +11,7 @@ Layout:
   optim.py             FusedAdam: one launch per step over the flat gradient bucket
   mapper.py            the keyframe-batched data-parallel mapping step: mapping_step (autograd composition),
                        FusedMapper (segs_mapper_views: views issued from C++ on concurrent lanes), RasterBatch
+  checkpoint.py        the reference's anchor checkpoint format: tinyply-compatible PLY + MLP text files
   anchor_model.py      container with the reference GaussianModel's member names + the C3 / C4 synthetic configs
   synth.py             the synthetic scenes of BASELINE.md §3
 """

@@ -43,6 +43,7 @@ class AnchorModel(nn.Module):
         self._anchor_feat = nn.Parameter(torch.zeros(A, FEAT_DIM))
         self._scaling = nn.Parameter(torch.zeros(A, 6))
         self._rotation = nn.Parameter(torch.zeros(A, 4), requires_grad=False)     # gaussian_model.cpp:372
+        self._opacity = nn.Parameter(torch.zeros(A, 1), requires_grad=False)      # :373 (carried by the checkpoint only)
 
     def get_anchor(self):
         return self._anchor
