@@ -18,7 +18,6 @@ import os
 import numpy as np
 import torch
 
-_PLY_GROUPS = (("x", "y", "z"), ("nx", "ny", "nz"))
 
 
 def _property_names(feat_dim: int, n_offsets: int, scaffold_names: bool) -> list[str]:

@@ -7,7 +7,6 @@ by ONE kernel launch that also applies the 1/B scale of the batch-mean gradient 
 """
 from __future__ import annotations
 
-import ctypes as C
 from typing import Sequence
 
 import torch
