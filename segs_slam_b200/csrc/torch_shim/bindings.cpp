@@ -3,6 +3,7 @@
 // C++ autograd function (gaussian_rasterizer.h).  Built in-tree as segs_slam_b200/_segs_torch.so.
 #include <torch/extension.h>
 
+#include "fused_mapper.h"
 #include "gaussian_rasterizer.h"
 #include "loss_utils.h"
 #include "rasterize_points.h"
@@ -42,6 +43,23 @@ void lu_adam_step(std::vector<torch::Tensor> params, std::vector<double> lrs, to
     loss_utils::adam_step(params, lrs, grad, m, v, step, beta1, beta2, eps, weight_decay, grad_scale, zero_grad);
 }
 
+// views: list of (world_view_transform, full_proj_transform, camera_center, pose[7], gt_image, row_mask-or-empty)
+torch::Tensor fm_render_views(FusedMapper& fm, const std::vector<std::tuple<torch::Tensor, torch::Tensor, torch::Tensor,
+                                                                             std::vector<double>, torch::Tensor, torch::Tensor>>& views) {
+    std::vector<KeyframeView> kv(views.size());
+    for (size_t i = 0; i < views.size(); ++i) {
+        kv[i].world_view_transform = std::get<0>(views[i]);
+        kv[i].full_proj_transform = std::get<1>(views[i]);
+        kv[i].camera_center = std::get<2>(views[i]);
+        const auto& p = std::get<3>(views[i]);
+        TORCH_CHECK(p.size() == 7, "pose = {t.xyz, q.wxyz}");
+        for (int k = 0; k < 7; ++k) kv[i].pose[k] = static_cast<float>(p[k]);
+        kv[i].gt_image = std::get<4>(views[i]);
+        if (std::get<5>(views[i]).numel()) kv[i].row_mask = std::get<5>(views[i]);
+    }
+    return fm.render_views(kv);
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_segs_torch, m) {
@@ -57,4 +75,20 @@ PYBIND11_MODULE(_segs_torch, m) {
     m.def("psnr", &lu_psnr);
     m.def("l1_ssim", &lu_l1_ssim);
     m.def("adam_step", &lu_adam_step);
+    py::class_<FusedMapper>(m, "FusedMapper")
+        .def(py::init([](std::vector<torch::Tensor> model, std::vector<c10::optional<torch::Tensor>> weights, std::vector<int> cfg,
+                         int H, int W, double tanx, double tany, torch::Tensor bg, double lambda_dssim, double reg_w,
+                         std::vector<double> lrs, double eps, int lanes) {
+            TORCH_CHECK(cfg.size() == 5, "cfg = {appearance_dim, use_feat_bank, add_opacity_dist, add_cov_dist, add_color_dist}");
+            std::vector<torch::Tensor> w;
+            for (auto& o : weights) w.push_back(o.has_value() ? *o : torch::Tensor());
+            return new FusedMapper(std::move(model), std::move(w), {cfg[0], cfg[1], cfg[2], cfg[3], cfg[4]}, H, W,
+                                   static_cast<float>(tanx), static_cast<float>(tany), bg, lambda_dssim, reg_w, std::move(lrs),
+                                   eps, lanes);
+        }))
+        .def("render_views", &fm_render_views)
+        .def("grad_flat", &FusedMapper::grad_flat)
+        .def("params", &FusedMapper::params)
+        .def("adam_step", &FusedMapper::adam_step)
+        .def("workspace_bytes", &FusedMapper::workspace_bytes);
 }

@@ -174,3 +174,44 @@ def test_cpp_adam_step_matches_torch_optim_adam_golden(device, shim, path):
 def test_cpp_loss_rejects_cpu_tensors(shim):
     with pytest.raises(RuntimeError, match="no CPU path"):
         shim.l1_loss(torch.zeros(3, 8, 8), torch.zeros(3, 8, 8))
+
+
+def test_cpp_fused_mapper_matches_the_python_host_class(device, shim):
+    """torch_shim/fused_mapper.{h,cpp} (the C++/LibTorch host class of the keyframe-batched step) against
+    segs_slam_b200.mapper.FusedMapper on the same model and views: accumulated gradient bucket, loss, one Adam step."""
+    import copy
+    from segs_slam_b200 import anchor_model, mapper
+    from segs_slam_b200.gaussian_renderer import _weights
+    W, H, fx = 208, 120, 150.0
+    tanx, tany = W / (2 * fx), H / (2 * fx)
+    model = anchor_model.synth_anchor_model(3000, W, H, fx, fx, 1003, device=device)
+    model_c = copy.deepcopy(model)
+    cams = anchor_model.circle_keyframes(8, 1.5, (0.0, 0.0, 3.25), tanx, tany, device)[:3]
+    g = torch.Generator(device="cpu").manual_seed(1)
+    targets = [(torch.rand(3, H, W, generator=g) * 0.5).to(device) for _ in cams]
+    bg = torch.tensor([0.1, 0.2, 0.3], device=device)
+
+    fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01, lrs=2e-3, lanes=1)
+    loss_py = fm.step(cams, targets, optimize=False) * len(cams)
+    bucket_py = fm.bucket.flat.clone()
+    fm.optimizer.step(grad_scale=1.0 / len(cams), zero_grad=True)
+
+    w = _weights(model_c)
+    n_par = 4 + sum(1 for t in w if t is not None)
+    cfg = [model_c.appearance_dim, int(model_c.use_feat_bank), 0, 0, 0]
+    cm = shim.FusedMapper([model_c._anchor.data, model_c._offset.data, model_c._anchor_feat.data, model_c._scaling.data,
+                           model_c._rotation.data], [None if t is None else t.data for t in w], cfg, H, W, tanx, tany, bg, 0.2,
+                          0.01, [2e-3] * n_par, 1e-15, 2)
+    e = torch.empty(0, device=device)
+    views = [(c.world_view_transform_, c.full_proj_transform_, c.camera_center_, list(c.t_) + list(c.R_quaternion_), t, e)
+             for c, t in zip(cams, targets)]
+    loss_c = cm.render_views(views)
+    torch.testing.assert_close(loss_c, loss_py, rtol=1e-5, atol=0)
+    bucket_c = cm.grad_flat().clone()
+    scale = float(bucket_py.abs().max())
+    assert scale > 0 and float((bucket_c - bucket_py).abs().max()) < 1e-4 * scale
+    cm.adam_step(1.0 / len(cams))
+    assert float(cm.grad_flat().abs().max()) == 0.0
+    for a, b in zip(cm.params(), fm.params):
+        assert float((a - b).abs().max()) < 2e-5, float((a - b).abs().max())
+    assert cm.workspace_bytes() > 0
