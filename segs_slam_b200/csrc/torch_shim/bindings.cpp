@@ -5,6 +5,7 @@
 
 #include "fused_mapper.h"
 #include "gaussian_rasterizer.h"
+#include "keyframe_transforms.h"
 #include "loss_utils.h"
 #include "rasterize_points.h"
 
@@ -43,6 +44,19 @@ void lu_adam_step(std::vector<torch::Tensor> params, std::vector<double> lrs, to
     loss_utils::adam_step(params, lrs, grad, m, v, step, beta1, beta2, eps, weight_decay, grad_scale, zero_grad);
 }
 
+std::tuple<torch::Tensor, torch::Tensor, torch::Tensor, torch::Tensor> kf_transforms(std::vector<double> R, std::vector<double> t,
+                                                                                      double FoVx, double FoVy) {
+    TORCH_CHECK(R.size() == 9 && t.size() == 3, "R: 9 row-major floats, t: 3 floats");
+    std::array<float, 9> Ra; std::array<float, 3> ta;
+    for (int i = 0; i < 9; ++i) Ra[i] = static_cast<float>(R[i]);
+    for (int i = 0; i < 3; ++i) ta[i] = static_cast<float>(t[i]);
+    return keyframe_transforms::computeTransformTensors(Ra, ta, static_cast<float>(FoVx), static_cast<float>(FoVy));
+}
+std::vector<double> kf_quat_to_rot(double w, double x, double y, double z) {
+    auto r = keyframe_transforms::quaternionToRotation(w, x, y, z);
+    return std::vector<double>(r.begin(), r.end());
+}
+
 // views: list of (world_view_transform, full_proj_transform, camera_center, pose[7], gt_image, row_mask-or-empty)
 torch::Tensor fm_render_views(FusedMapper& fm, const std::vector<std::tuple<torch::Tensor, torch::Tensor, torch::Tensor,
                                                                              std::vector<double>, torch::Tensor, torch::Tensor>>& views) {
@@ -75,6 +89,8 @@ PYBIND11_MODULE(_segs_torch, m) {
     m.def("psnr", &lu_psnr);
     m.def("l1_ssim", &lu_l1_ssim);
     m.def("adam_step", &lu_adam_step);
+    m.def("computeTransformTensors", &kf_transforms);
+    m.def("quaternionToRotation", &kf_quat_to_rot);
     py::class_<FusedMapper>(m, "FusedMapper")
         .def(py::init([](std::vector<torch::Tensor> model, std::vector<c10::optional<torch::Tensor>> weights, std::vector<int> cfg,
                          int H, int W, double tanx, double tany, torch::Tensor bg, double lambda_dssim, double reg_w,

@@ -34,3 +34,20 @@ def test_transform_tensors_match_reference_dump():
         np.testing.assert_allclose(full, np.asarray(k["full_proj_transform_"]).reshape(4, 4), atol=2e-3)
         # camera_center_ = inverse(world_view_transform_)[3, :3]; R in the dump is orthonormal only to 4 decimals
         np.testing.assert_allclose(campos, np.asarray(k["camera_center_"]), atol=2e-3)
+
+
+def test_cpp_transform_tensors_match_reference_dump():
+    """torch_shim/keyframe_transforms.h (C++ twin of GaussianKeyframe::computeTransformTensors) on the same dump."""
+    import torch  # noqa: F401
+    from segs_slam_b200 import _segs_torch as shim
+    for k in KF:
+        wvt_ref = np.asarray(k["world_view_transform_"], dtype=np.float64).reshape(4, 4)
+        R, t = wvt_ref[:3, :3].T, wvt_ref[3, :3]
+        wvt, proj, full, center = shim.computeTransformTensors([float(x) for x in R.reshape(-1)], [float(x) for x in t],
+                                                               k["FoVx"], k["FoVy"])
+        np.testing.assert_allclose(wvt.numpy(), wvt_ref, atol=1e-4)        # two inversions of a 4-decimal matrix
+        np.testing.assert_allclose(proj.numpy(), np.asarray(k["projection_matrix_"]).reshape(4, 4), atol=1.5e-4)
+        np.testing.assert_allclose(full.numpy(), np.asarray(k["full_proj_transform_"]).reshape(4, 4), atol=2e-3)
+        np.testing.assert_allclose(center.numpy(), np.asarray(k["camera_center_"]), atol=2e-3)
+    r = shim.quaternionToRotation(0.5, 0.5, 0.5, 0.5)                      # 120 degrees about (1,1,1): x -> y -> z
+    np.testing.assert_allclose(np.asarray(r).reshape(3, 3), [[0, 0, 1], [1, 0, 0], [0, 1, 0]], atol=1e-7)
