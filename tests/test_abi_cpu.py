@@ -121,3 +121,22 @@ def test_expon_lr_schedule_matches_reference_formula():
     assert abs(lr(0, 1e-2, 1e-4, 0.01, 1000, lr_delay_steps=100) - 1e-4) < 1e-9
     mid = lr(50, 1e-2, 1e-2, 0.01, 1000, lr_delay_steps=100)
     assert abs(mid - 1e-2 * (0.01 + 0.99 * math.sin(math.pi / 4))) < 1e-7
+
+
+def test_header_is_plain_c(tmp_path):
+    """include/segs_raster.h is a C ABI: it must compile as C99 (no C++-isms, no torch types) and link by name."""
+    import subprocess
+    src = tmp_path / "c_abi.c"
+    src.write_text('#include "segs_raster.h"\n'
+                   'int main(void) {\n'
+                   '    segs_mapper_view_args a; segs_raster_view_args r; segs_adam_tensor t; segs_decode_params p;\n'
+                   '    (void)a; (void)r; (void)t; (void)p;\n'
+                   '    return segs_version() == SEGS_ABI_VERSION ? 0 : 1;\n'
+                   '}\n')
+    inc = os.path.join(ROOT, "include")
+    lib = os.path.join(ROOT, "segs_slam_b200")
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-pedantic", "-fsyntax-only", f"-I{inc}", str(src)])
+    exe = tmp_path / "c_abi"
+    subprocess.check_call(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), f"-L{lib}", "-lsegs_raster",
+                           f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
+    assert subprocess.run([str(exe)]).returncode == 0          # segs_version() needs no GPU
