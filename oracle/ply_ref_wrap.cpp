@@ -46,6 +46,25 @@ int ref_save_ply(const char* path, int A, int F, int k3, float* anchor, float* f
     return 0;
 }
 
+// GaussianModel::saveSparsePointsPly's call sequence (src/gaussian_model.cpp:1319-1352): xyz / normals float, rgb uchar
+int ref_save_sparse_ply(const char* path, int n, float* xyz, unsigned char* rgb)
+{
+    std::vector<float> normals(size_t(n) * 3, 0.f);
+    std::filebuf fb;
+    fb.open(path, std::ios::out | std::ios::binary);
+    std::ostream os(&fb);
+    if (os.fail()) return 1;
+    tinyply::PlyFile file;
+    file.add_properties_to_element("vertex", {"x", "y", "z"}, tinyply::Type::FLOAT32, n, reinterpret_cast<uint8_t*>(xyz),
+                                   tinyply::Type::INVALID, 0);
+    file.add_properties_to_element("vertex", {"nx", "ny", "nz"}, tinyply::Type::FLOAT32, n,
+                                   reinterpret_cast<uint8_t*>(normals.data()), tinyply::Type::INVALID, 0);
+    file.add_properties_to_element("vertex", {"red", "green", "blue"}, tinyply::Type::UINT8, n, rgb, tinyply::Type::INVALID, 0);
+    file.write(os, true);
+    fb.close();
+    return 0;
+}
+
 // reads back with tinyply; returns the anchor count, fills the arrays (same layouts as above)
 int ref_load_ply(const char* path, int F, int k3, float* anchor, float* feat, float* offset_flat, float* opacity, float* scale,
                  float* rot)

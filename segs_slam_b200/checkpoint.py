@@ -104,6 +104,22 @@ def load_ply(path: str) -> dict[str, torch.Tensor]:
     }
 
 
+def save_sparse_points_ply(xyz: torch.Tensor, color: torch.Tensor, path: str) -> None:
+    """GaussianModel::saveSparsePointsPly (gaussian_model.cpp:1319-1352): x y z | nx ny nz (zeros) as float, then
+    red green blue as uchar = (color * 255) truncated like `toType(torch::kUInt8)`; one packed 27-byte row per point."""
+    p = xyz.detach().to("cpu", torch.float32).contiguous().numpy()
+    c = (color.detach().to("cpu", torch.float32) * 255.0).to(torch.uint8).contiguous().numpy()
+    n = p.shape[0]
+    rows = np.zeros(n, dtype=[("p", "<f4", 3), ("n", "<f4", 3), ("c", "u1", 3)])
+    rows["p"], rows["c"] = p, c
+    header = "ply\nformat binary_little_endian 1.0\n" + f"element vertex {n}\n" + \
+        "".join(f"property float {k}\n" for k in ("x", "y", "z", "nx", "ny", "nz")) + \
+        "".join(f"property uchar {k}\n" for k in ("red", "green", "blue")) + "end_header\n"
+    with open(path, "wb") as f:
+        f.write(header.encode("ascii"))
+        f.write(rows.tobytes())
+
+
 def load_into(pc, tensors: dict[str, torch.Tensor]) -> None:
     """Copy a `load_ply` result into a model with the reference's member names (shapes must match)."""
     with torch.no_grad():

@@ -32,3 +32,13 @@ bflat = np.zeros_like(flat)
 n = lib.ref_load_ply(path.encode(), F, 3 * K, p(back["anchor"]), p(back["feat"]), p(bflat), p(back["opacity"]), p(back["scale"]), p(back["rot"]))
 assert n == A and np.array_equal(bflat, flat) and np.array_equal(back["rot"], d["rot"])
 print("wrote", path, os.path.getsize(path), "bytes")
+
+# sparse points (saveSparsePointsPly): float xyz + normals, uchar rgb
+lib.ref_save_sparse_ply.argtypes = [C.c_char_p, C.c_int, fp, C.POINTER(C.c_ubyte)]
+xyz = np.ascontiguousarray(rng.normal(0, 1, (5, 3)), dtype=np.float32)
+col = np.ascontiguousarray(rng.uniform(0, 1, (5, 3)), dtype=np.float32)
+rgb = np.ascontiguousarray((torch.from_numpy(col) * 255.0).to(torch.uint8).numpy())       # toType(kUInt8), :1323
+spath = os.path.join(HERE, "sparse_tinyply.ply")
+assert lib.ref_save_sparse_ply(spath.encode(), 5, p(xyz), rgb.ctypes.data_as(C.POINTER(C.c_ubyte))) == 0
+np.savez(os.path.join(HERE, "sparse_tinyply.npz"), xyz=xyz, color=col)
+print("wrote", spath, os.path.getsize(spath), "bytes")

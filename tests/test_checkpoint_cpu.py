@@ -89,3 +89,10 @@ def test_mlp_text_checkpoints_round_trip(tmp_path):
     for (n1, p1), (_n2, p2) in zip(a.named_parameters(), b.named_parameters()):
         if n1.startswith(("mlp_opacity", "mlp_cov", "mlp_color", "mlp_feature_bank")):
             assert torch.allclose(p1, p2, atol=5.1e-6), n1                          # 5 decimals
+
+
+def test_sparse_points_ply_is_byte_identical_to_tinyply(tmp_path):
+    d = np.load(os.path.join(GOLD, "sparse_tinyply.npz"))
+    out = str(tmp_path / "sparse.ply")
+    checkpoint.save_sparse_points_ply(torch.from_numpy(d["xyz"]), torch.from_numpy(d["color"]), out)
+    assert open(out, "rb").read() == open(os.path.join(GOLD, "sparse_tinyply.ply"), "rb").read()
