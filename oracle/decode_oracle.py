@@ -4,10 +4,15 @@ Restates GaussianRenderer::generate_neural_gaussians
 (/root/reference/src/gaussian_renderer.cpp:214-334) and the module shapes built in
 GaussianModel::GaussianModel (/root/reference/src/gaussian_model.cpp:60-98) with the same ATen
 operations in the same order (index / cat / repeat / Linear / ReLU / Tanh / Sigmoid / Softmax /
-normalize), FP32, TF32 off.  The reference's decode is LibTorch C++ that cannot be compiled in this
-image (its headers need PCL / Sophus / torch_scatter), and the reference ships no test or fixture
-for it: PARITY UNPINNED beyond "same ATen ops, same order".  Only tests/, __graft_entry__.smoke()
-and bench.py's reference arm may import this file; the product never does.
+normalize), FP32, TF32 off.
+
+PINNED to the reference itself: /root/reference/src/gaussian_renderer.cpp and gaussian_model.cpp compile UNMODIFIED in
+this image once declaration-only stand-ins replace the absent Eigen / Sophus / OpenCV / PCL / torch_scatter headers
+(oracle/stub_include/, `make -C oracle modelref` -> oracle/_ref/_model_ref.so).  tests/golden/decode_*.npz hold the
+outputs and gradients of the reference's own generate_neural_gaussians (tests/golden/make_model_golden.py);
+tests/test_decode_cpu.py holds this file to them (bit-identical on the generating machine), and on the GPU box the CUDA
+decode is compared with the compiled reference live.  Only tests/, __graft_entry__.smoke() and bench.py's reference
+arm may import this file; the product never does.
 """
 from __future__ import annotations
 
