@@ -253,6 +253,56 @@ struct RefModel {
         return {loss.item<double>(), Ll1.item<double>(), ssim.item<double>()};
     }
 
+    // Reference baseline "B" (BASELINE.md section 2): the reference's per-view work with gradients ACCUMULATED in .grad
+    // (loss scaled by `loss_scale` = 1 / batch) and no optimizer step; optimizer_step() then applies ONE Adam step.
+    T backward_view(T view, T proj, T center, std::vector<double> t, std::vector<double> q, double fovx, double fovy, int H, int W,
+                    T bg, T gt_image_in, double lambda_dssim, double loss_scale) {
+        auto kf = keyframe(view, proj, center, t, q, fovx, fovy, H, W);
+        T override_color;
+        auto voxel_visible_mask = GaussianRenderer::prefilter_voxel(kf, H, W, m, pipe, bg, override_color);
+        auto pkg = GaussianRenderer::render(kf, H, W, m, pipe, bg, override_color, voxel_visible_mask, true);
+        auto rendered_image = std::get<0>(pkg);
+        auto scaling = std::get<6>(pkg);
+        T gt_image = gt_image_in;
+        T mask_rgb = (gt_image != 0.0f).any(-1).to(torch::kFloat32).unsqueeze(-1);
+        T masked_image = rendered_image * mask_rgb;
+        rendered_image = rendered_image * mask_rgb;
+        gt_image = gt_image * mask_rgb;
+        auto Ll1 = loss_utils::l1_loss(rendered_image, gt_image);
+        auto loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - loss_utils::ssim(masked_image, gt_image, m->device_type_)) +
+                    0.01 * scaling.prod(1).mean();
+        (loss * loss_scale).backward();
+        return loss.detach();
+    }
+    void optimizer_step() {
+        torch::NoGradGuard ng;
+        m->optimizer_->step();
+        m->optimizer_->zero_grad(true);
+    }
+    // BASELINE config 3: prefilter -> decode -> rasterize and the backward of a given dL_dimage (no loss)
+    T render_fwd_bwd(T view, T proj, T center, std::vector<double> t, std::vector<double> q, double fovx, double fovy, int H, int W,
+                     T bg, T dL_dimage) {
+        auto kf = keyframe(view, proj, center, t, q, fovx, fovy, H, W);
+        T override_color;
+        auto voxel_visible_mask = GaussianRenderer::prefilter_voxel(kf, H, W, m, pipe, bg, override_color);
+        auto pkg = GaussianRenderer::render(kf, H, W, m, pipe, bg, override_color, voxel_visible_mask, true);
+        auto image = std::get<0>(pkg);
+        image.backward(dL_dimage);
+        std::vector<T> params = {m->_anchor, m->_offset, m->_anchor_feat, m->_scaling};
+        for (auto& p : mlp_parameters()) params.push_back(p);
+        for (auto& p : params) p.mutable_grad() = T();
+        return image.detach();
+    }
+    // forward only (ground-truth images of the synthetic mapping workload)
+    T render_image(T view, T proj, T center, std::vector<double> t, std::vector<double> q, double fovx, double fovy, int H, int W, T bg) {
+        torch::NoGradGuard ng;
+        auto kf = keyframe(view, proj, center, t, q, fovx, fovy, H, W);
+        T override_color;
+        auto voxel_visible_mask = GaussianRenderer::prefilter_voxel(kf, H, W, m, pipe, bg, override_color);
+        auto pkg = GaussianRenderer::render(kf, H, W, m, pipe, bg, override_color, voxel_visible_mask, false);
+        return std::get<0>(pkg).detach();
+    }
+
     // backward only (no optimizer step): gradients of the loss of ONE view w.r.t. every trainable tensor, for the parity
     // test of the fused mapping view.  -> (loss, grads of [anchor, offset, feat, scaling] + MLP parameters, image,
     // viewspace grad, radii, offset mask, neural opacity, visible mask)
@@ -315,7 +365,20 @@ PYBIND11_MODULE(_model_ref, mod) {
         .def("set_statistics", &RefModel::set_statistics)
         .def("state", &RefModel::state)
         .def("adam_state", &RefModel::adam_state)
-        .def("train_iteration", &RefModel::train_iteration)
-        .def("view_gradients", &RefModel::view_gradients);
+        .def("train_iteration", &RefModel::train_iteration, py::call_guard<py::gil_scoped_release>())
+        .def("backward_view", &RefModel::backward_view, py::call_guard<py::gil_scoped_release>())
+        .def("optimizer_step", &RefModel::optimizer_step, py::call_guard<py::gil_scoped_release>())
+        .def("render_fwd_bwd", &RefModel::render_fwd_bwd, py::call_guard<py::gil_scoped_release>())
+        .def("render_image", &RefModel::render_image, py::call_guard<py::gil_scoped_release>())
+        .def("view_gradients", &RefModel::view_gradients, py::call_guard<py::gil_scoped_release>());
+    // the reference's six tensor-level entry points (include/rasterize_points.h:18-102, third_party/simple-knn/spatial.h:14)
+    mod.def("RasterizeGaussiansCUDA", &RasterizeGaussiansCUDA);
+    mod.def("RasterizeGaussiansBackwardCUDA", &RasterizeGaussiansBackwardCUDA);
+    mod.def("RasterizeGaussiansfilterCUDA", &RasterizeGaussiansfilterCUDA);
+    mod.def("RasterizeGaussiansprojectCUDA", &RasterizeGaussiansprojectCUDA);
+    mod.def("markVisible", &markVisible);
+    mod.def("distCUDA2", &distCUDA2);
+    // tanfovx exactly as GaussianRenderer::render derives it from the keyframe's FoVx_ (gaussian_renderer.cpp:67-68)
+    mod.def("tan_half_fov", [](double fov) { return (double)std::tan((float)fov * 0.5f); });
     mod.def("scatter_max", [](T src, T index) { auto r = scatter_max(src, index, 0, std::nullopt, std::nullopt); return std::vector<T>{std::get<0>(r), std::get<1>(r)}; });
 }

@@ -129,6 +129,10 @@ def load_into(pc, tensors: dict[str, torch.Tensor]) -> None:
 
 
 _MLP_FILES = (("mlp_opacity", "opacity"), ("mlp_cov", "cov"), ("mlp_color", "color"), ("mlp_feature_bank", "feat"))
+# Extension: the reference's save_mlp_checkpoints (gaussian_model.cpp:1262-1317) does NOT write mlp_apperance — the
+# Linear(7, appearance_dim) that this repo's decode trains — so its own round trip loses it.  It is written here under an
+# extra pair of files the reference ignores; loading tolerates their absence (a checkpoint written by the reference).
+_EXTRA_MLP_FILES = (("mlp_apperance", "appearance"),)
 
 
 def _linears(seq):
@@ -153,23 +157,34 @@ def save_mlp_checkpoints(pc, result_path: str) -> None:
     """GaussianModel::save_mlp_checkpoints: <name>_weight{1,2}.txt / <name>_bias{1,2}.txt for the opacity, cov, color
     and (when used) feature-bank MLPs."""
     os.makedirs(result_path, exist_ok=True)
-    for attr, name in _MLP_FILES:
+    for attr, name in _MLP_FILES + _EXTRA_MLP_FILES:
         seq = getattr(pc, attr, None)
         if seq is None:
             continue
         for i, lin in enumerate(_linears(seq), start=1):
             save_tensor_txt(lin.weight, os.path.join(result_path, f"{name}_weight{i}.txt"))
             save_tensor_txt(lin.bias, os.path.join(result_path, f"{name}_bias{i}.txt"))
+    emb = getattr(pc, "embedding_appearance", None)             # :1312-1315 (nn.Embedding weight, when the model has one)
+    if emb is not None and getattr(pc, "appearance_dim", 0) > 0:
+        w = emb.weight if hasattr(emb, "weight") else emb.get_embedding().weight
+        save_tensor_txt(w, os.path.join(result_path, "embedding_weight.txt"))
 
 
 def load_mlp_checkpoints(pc, result_path: str) -> None:
     with torch.no_grad():
-        for attr, name in _MLP_FILES:
+        for attr, name in _MLP_FILES + _EXTRA_MLP_FILES:
             seq = getattr(pc, attr, None)
             if seq is None:
                 continue
             for i, lin in enumerate(_linears(seq), start=1):
+                if (attr, name) in _EXTRA_MLP_FILES and not os.path.exists(os.path.join(result_path, f"{name}_weight{i}.txt")):
+                    continue                                    # written by the reference: it has no such file
                 w = load_tensor_txt(os.path.join(result_path, f"{name}_weight{i}.txt"))
                 b = load_tensor_txt(os.path.join(result_path, f"{name}_bias{i}.txt")).reshape(-1)
-                lin.weight.copy_(w.to(lin.weight.device))
+                lin.weight.copy_(w.to(lin.weight.device).view_as(lin.weight))
                 lin.bias.copy_(b.to(lin.bias.device))
+        emb = getattr(pc, "embedding_appearance", None)
+        path = os.path.join(result_path, "embedding_weight.txt")
+        if emb is not None and os.path.exists(path):
+            w = emb.weight if hasattr(emb, "weight") else emb.get_embedding().weight
+            w.copy_(load_tensor_txt(path).to(w.device).view_as(w))

@@ -120,11 +120,23 @@ static HostWords pinned_words() {
     return w;
 }
 
-// One event per host thread marking "num_rendered has landed in pinned memory".
-static cudaEvent_t readback_event() {
-    static thread_local cudaEvent_t ev = nullptr;
-    if (!ev && cudaEventCreateWithFlags(&ev, readback_event_flags()) != cudaSuccess) ev = nullptr;
-    return ev;
+// One event per (host thread, device) marking "the read-back words have landed in pinned memory".  Events belong to the
+// device that was current when they were created, so the cache is keyed by cudaGetDevice(); an event is re-created when
+// segs_set_blocking_sync() changed the flags it was created with.
+cudaEvent_t readback_event() {
+    struct Slot { cudaEvent_t ev = nullptr; unsigned flags = 0; };
+    constexpr int MAX_DEVICES = 64;
+    static thread_local Slot slots[MAX_DEVICES];
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= MAX_DEVICES) return nullptr;
+    Slot& s = slots[dev];
+    const unsigned flags = readback_event_flags();
+    if (s.ev && s.flags != flags) { cudaEventDestroy(s.ev); s.ev = nullptr; }
+    if (!s.ev) {
+        if (cudaEventCreateWithFlags(&s.ev, flags) != cudaSuccess) { s.ev = nullptr; return nullptr; }
+        s.flags = flags;
+    }
+    return s.ev;
 }
 
 // ---- optional per-stage timing ----------------------------------------------------------

@@ -28,6 +28,7 @@ void set_error(const char* fmt, ...);
     } while (0)
 void count_launch();
 unsigned readback_event_flags();      // flags of the events the host read-backs wait on (segs_set_blocking_sync)
+cudaEvent_t readback_event();         // the calling thread's read-back event on the CURRENT device (nullptr on failure)
 #define SEGS_LAUNCH_CHECK()                  \
     do {                                     \
         ::segs::count_launch();              \

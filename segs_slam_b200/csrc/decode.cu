@@ -1073,17 +1073,20 @@ zero_many_kernel(const ZeroList z)
 struct HostCounts { uint32_t* host = nullptr; uint32_t* dev = nullptr; cudaEvent_t ev = nullptr; };
 HostCounts decode_host_counts()
 {
+    // the mapped words are portable (one address on every device under UVA); the event is per device (capi.cu)
     static thread_local HostCounts h;
     if (!h.host) {
         void *hp = nullptr, *dp = nullptr;
         if (cudaHostAlloc(&hp, 4 * sizeof(uint32_t), cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess &&
-            cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess &&
-            cudaEventCreateWithFlags(&h.ev, readback_event_flags()) == cudaSuccess) {
+            cudaHostGetDevicePointer(&dp, hp, 0) == cudaSuccess) {
             h.host = static_cast<uint32_t*>(hp);
             h.dev = static_cast<uint32_t*>(dp);
         }
     }
-    return h;
+    HostCounts out = h;
+    out.ev = readback_event();
+    if (!out.ev) out.host = nullptr;
+    return out;
 }
 
 int check_params(const segs_decode_params* p)

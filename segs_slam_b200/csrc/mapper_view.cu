@@ -305,11 +305,21 @@ static int run_lanes(int n_views, int n_lanes, segs_workspace* const* ws, void* 
     SEGS_CUDA_CHECK(cudaGetDevice(&device));
     const bool concurrent = n_lanes > 1;
 
-    cudaEvent_t start = nullptr;
-    SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&start, cudaEventDisableTiming));
-    SEGS_CUDA_CHECK(cudaEventRecord(start, main_stream));
-    std::vector<cudaEvent_t> done(n_lanes, nullptr);
-    for (int l = 0; l < n_lanes; ++l) SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&done[l], cudaEventDisableTiming));
+    // RAII: the events are destroyed on every path out of this function (the SEGS_CUDA_CHECK early returns included)
+    struct Events {
+        cudaEvent_t start = nullptr;
+        std::vector<cudaEvent_t> done;
+        ~Events() {
+            if (start) cudaEventDestroy(start);
+            for (cudaEvent_t e : done) if (e) cudaEventDestroy(e);
+        }
+    } evs;
+    evs.done.assign(n_lanes, nullptr);
+    SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&evs.start, cudaEventDisableTiming));
+    SEGS_CUDA_CHECK(cudaEventRecord(evs.start, main_stream));
+    for (int l = 0; l < n_lanes; ++l) SEGS_CUDA_CHECK(cudaEventCreateWithFlags(&evs.done[l], cudaEventDisableTiming));
+    cudaEvent_t start = evs.start;
+    std::vector<cudaEvent_t>& done = evs.done;
 
     auto run_lane = [&](int l) -> int {
         cudaStream_t st = static_cast<cudaStream_t>(streams[l]);
@@ -336,11 +346,7 @@ static int run_lanes(int n_views, int n_lanes, segs_workspace* const* ws, void* 
             set_error("lane %d: %s", l, ws[l]->job_error.c_str());
         }
     }
-    for (int l = 0; l < n_lanes; ++l) {
-        cudaStreamWaitEvent(main_stream, done[l], 0);
-        cudaEventDestroy(done[l]);
-    }
-    cudaEventDestroy(start);
+    for (int l = 0; l < n_lanes; ++l) cudaStreamWaitEvent(main_stream, done[l], 0);
     return rc;
 }
 }  // extern "C++"

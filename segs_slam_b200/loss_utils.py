@@ -42,6 +42,7 @@ class _L1SSIMFunction(torch.autograd.Function):
         ctx.save_for_backward(img_c, gt_c, mask_c if mask_c is not None else torch.empty(0, device=image.device),
                               state)
         ctx.w = (float(w_l1), float(w_ssim))
+        ctx.set_materialize_grads(False)          # unused outputs arrive as None instead of zero tensors: one launch per used one
         return out[0], out[1], out[2]
 
     @staticmethod
@@ -61,6 +62,8 @@ class _L1SSIMFunction(torch.autograd.Function):
                 _lib.check(lib.segs_loss_l1_ssim_backward(C_, H, W, _ptr(img_c), _ptr(gt_c), _ptr(mask_c), a, b,
                                                           _ptr(gc), state.data_ptr(), _ptr(d), _stream()))
             grad = d if grad is None else grad + d
+        if grad is None:
+            grad = torch.zeros_like(img_c)
         return grad, None, None, None, None, None
 
 

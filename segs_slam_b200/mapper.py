@@ -308,14 +308,8 @@ class FusedMapper:
                     loss_terms_out=None):
         """One view: accumulates gradients and the loss.  `_prepare()` must have run this step."""
         C, L = self._C, self._lib_mod
-        a = self._args
-        a.viewmatrix, a.projmatrix = cam.world_view_transform_.data_ptr(), cam.full_proj_transform_.data_ptr()
-        a.campos = cam.camera_center_.data_ptr()
-        t, q = cam.t_, cam.R_quaternion_
-        pose = (C.c_float * 7)(float(t[0]), float(t[1]), float(t[2]), float(q[0]), float(q[1]), float(q[2]), float(q[3]))
-        a.pose = pose
-        a.gt_image = target.data_ptr()
-        a.row_mask = None if row_mask is None else row_mask.data_ptr()
+        a, keep = L.MapperViewArgs(), []         # a private copy: the optional outputs must not leak into later batches
+        self._fill(a, cam, target, row_mask, keep)
         a.image_out = None if image_out is None else image_out.data_ptr()
         a.loss_terms_out = None if loss_terms_out is None else loss_terms_out.data_ptr()
         res = L.MapperViewResult()

@@ -26,7 +26,14 @@ def _ptr(t: torch.Tensor | None) -> int | None:
     return t.data_ptr()
 
 
-def _f32c(t: torch.Tensor) -> torch.Tensor:
+def _f32c(t: torch.Tensor, like: torch.Tensor | None = None, dtype=torch.float32) -> torch.Tensor:
+    """Contiguous tensor of the dtype the kernels read.  The reference's `data_ptr<float>()` throws on any other dtype
+    (src/rasterize_points.cu:88-107); a silent reinterpretation would render garbage or read out of bounds."""
+    if t.numel() != 0:
+        if t.dtype != dtype:
+            raise RuntimeError(f"expected scalar type {str(dtype).replace('torch.', '')} but found {str(t.dtype).replace('torch.', '')}")
+        if not t.is_cuda or (like is not None and t.device != like.device):
+            raise RuntimeError(f"expected a CUDA tensor on {like.device if like is not None else 'the device of means3D'}, got {t.device}")
     return t.contiguous()
 
 
@@ -77,7 +84,7 @@ def RasterizeGaussiansCUDA(background, means3D, colors, opacity, scales, rotatio
     rendered = C.c_int(0)
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0
-        keep = [_f32c(x) for x in (background, means3D, sh, colors, opacity, scales, rotations,
+        keep = [_f32c(x, means3D) for x in (background, means3D, sh, colors, opacity, scales, rotations,
                                    cov3D_precomp, viewmatrix, projmatrix, campos)]
         bg, m3, shc, col, opa, sca, rot, cov, view, proj, cam = keep
         with torch.cuda.device(dev):
@@ -113,10 +120,10 @@ def RasterizeGaussiansBackwardCUDA(background, means3D, radii, colors, scales, r
     dL_dscales = torch.empty((P, 3), **o)
     dL_drotations = torch.empty((P, 4), **o)
     if P != 0:
-        keep = [_f32c(x) for x in (background, means3D, sh, colors, scales, rotations, cov3D_precomp,
+        keep = [_f32c(x, means3D) for x in (background, means3D, sh, colors, scales, rotations, cov3D_precomp,
                                    viewmatrix, projmatrix, campos, dL_dout_color)]
         bg, m3, shc, col, sca, rot, cov, view, proj, cam, dpix = keep
-        rad = radii.contiguous()
+        rad = _f32c(radii, means3D, torch.int32)
         with torch.cuda.device(means3D.device):
             _lib.check(lib.segs_raster_backward(
                 P, int(degree), int(M), int(R),
@@ -138,7 +145,7 @@ def markVisible(means3D, viewmatrix, projmatrix):
     P = means3D.size(0)
     present = torch.zeros((P,), dtype=torch.bool, device=means3D.device)
     if P != 0:
-        m3, view, proj = _f32c(means3D), _f32c(viewmatrix), _f32c(projmatrix)
+        m3, view, proj = _f32c(means3D), _f32c(viewmatrix, means3D), _f32c(projmatrix, means3D)
         with torch.cuda.device(means3D.device):
             _lib.check(lib.segs_mark_visible(P, _ptr(m3), _ptr(view), _ptr(proj), present.data_ptr(), _stream()))
     return present
@@ -153,7 +160,7 @@ def RasterizeGaussiansfilterCUDA(means3D, scales, rotations, scale_modifier, cov
     P = means3D.size(0)
     radii = torch.zeros((P,), dtype=torch.int32, device=means3D.device)
     if P != 0:
-        keep = [_f32c(x) for x in (means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix)]
+        keep = [_f32c(x, means3D) for x in (means3D, scales, rotations, cov3D_precomp, viewmatrix, projmatrix)]
         m3, sca, rot, cov, view, proj = keep
         with torch.cuda.device(means3D.device):
             _lib.check(lib.segs_visible_filter(
@@ -176,7 +183,7 @@ def RasterizeGaussiansprojectCUDA(background, means3D, colors, opacity, scales, 
     points_image = torch.zeros((P, 2), dtype=torch.float32, device=dev)
     if P != 0:
         M = sh.size(1) if sh.numel() != 0 else 0
-        keep = [_f32c(x) for x in (means3D, sh, colors, opacity, scales, rotations, cov3D_precomp,
+        keep = [_f32c(x, means3D) for x in (means3D, sh, colors, opacity, scales, rotations, cov3D_precomp,
                                    viewmatrix, projmatrix, campos)]
         m3, shc, col, opa, sca, rot, cov, view, proj, cam = keep
         with torch.cuda.device(dev):
