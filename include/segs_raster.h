@@ -295,6 +295,47 @@ int segs_training_statis(int A, const char* decode_state, int n_vis, const float
                          const float* dL_dmean2D, float* opacity_accum, float* anchor_demon,
                          float* offset_gradient_accum, float* offset_denom, int atomic, void* stream);
 
+/* ---- densification decisions ---------------------------------------------------------
+ *   segs_anchor_growing_level   one level i of GaussianModel::anchor_growing     src/gaussian_model.cpp:1556-1703
+ *   segs_prune_plan             the statistics update + prune decision of        src/gaussian_model.cpp:1716-1755
+ *                               GaussianModel::adjust_anchor
+ *   segs_compact_rows           the row gathers of GaussianModel::prune_anchor   src/gaussian_model.cpp:1505-1555
+ * The host (segs_slam_b200/densify.py) owns the tensors and their resizing, like the reference's torch::cat /
+ * index sequences; every decision and every new value is computed here.
+ *
+ * segs_anchor_growing_level: candidates are the first `init_slots` (= anchors before growing x n_offsets) offset slots
+ * with |offset_gradient_accum / offset_denom| >= cur_threshold, offset_denom > denom_threshold and
+ * rand_values > rand_threshold (the reference draws rand_values with torch::rand_like).  Their positions
+ * anchor + offset * exp(log_scaling[:, :3]) are snapped to voxels of side cur_size; voxels already occupied by one of the
+ * A_now current anchors are dropped; the survivors come out in lexicographic voxel order (at::unique_dim):
+ *   *new_anchor [n_new,3] = voxel * cur_size,  *new_feat [n_new,feat_dim] = per-voxel maximum of the candidates' anchor
+ *   features (torch_scatter's scatter_max), both inside ONE block obtained from out_alloc.
+ * scratch_alloc is called at most twice and must return a NEW block each time; all blocks stay owned by the caller and
+ * must remain valid until the call returns.  Synchronises `stream` twice (candidate count, n_new). */
+int segs_anchor_growing_level(
+    int A_now, int init_slots, int n_offsets, int feat_dim,
+    const float* anchor, const float* offset, const float* log_scaling, const float* anchor_feat,
+    const float* offset_gradient_accum, const float* offset_denom, const float* rand_values,
+    float denom_threshold, float cur_threshold, float rand_threshold, float cur_size,
+    segs_alloc_fn scratch_alloc, void* scratch_user, segs_alloc_fn out_alloc, void* out_user,
+    float** new_anchor, float** new_feat, int* n_candidates, int* n_new, void* stream);
+
+/* In place over A anchors (A = after growing; the first init_slots offset slots carry statistics):
+ *   offset slots with offset_denom > denom_threshold: offset_denom = offset_gradient_accum = 0;
+ *   keep[a] = !(opacity_accum[a] < min_opacity * anchor_demon[a] && anchor_demon[a] > anchor_threshold);
+ *   anchors with anchor_demon > anchor_threshold: opacity_accum = anchor_demon = 0;
+ *   keep_index = exclusive scan of keep, *n_keep = its total (one stream synchronisation). */
+size_t segs_prune_scratch_words(int A);
+int segs_prune_plan(
+    int A, int init_slots, float* opacity_accum, float* anchor_demon, float* offset_gradient_accum, float* offset_denom,
+    float denom_threshold, float anchor_threshold, float min_opacity,
+    unsigned int* keep, unsigned int* keep_index, unsigned int* scratch, int* n_keep, void* stream);
+
+/* dst[keep_index[a]][:] = src[a][:] for every a with keep[a] (rows of row_floats floats); clamp_from >= 0: columns
+ * >= clamp_from are clamped to <= clamp_max on the way (prune_anchor clamps _scaling[:, 3:] to 0.05). */
+int segs_compact_rows(int A, int row_floats, const unsigned int* keep, const unsigned int* keep_index, const float* src,
+                      float* dst, int clamp_from, float clamp_max, void* stream);
+
 /* ---- one keyframe view of the batched mapping step (BASELINE config 4) -------------
  *   segs_mapper_view      the body of GaussianMapper::trainForOneIteration  src/gaussian_mapper.cpp:870-950:
  *                         prefilter_voxel (src/gaussian_renderer.cpp:131-199) -> generate_neural_gaussians

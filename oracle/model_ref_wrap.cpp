@@ -167,6 +167,17 @@ struct RefModel {
     }
     int n_param_groups() const { return (int)m->optimizer_->param_groups().size(); }
 
+    // Give the four trainable anchor tensors (anchor, offset, feat, scaling) Adam moments: one torch::optim::Adam step on the
+    // given gradients.  With every learning rate at 0 (set_learning_rates) the parameters do not move.
+    void adam_step_with_grads(std::vector<T> grads) {
+        TORCH_CHECK(grads.size() == 4, "expected gradients of anchor, offset, feat, scaling");
+        std::vector<T> ps = {m->_anchor, m->_offset, m->_anchor_feat, m->_scaling};
+        for (int i = 0; i < 4; ++i) ps[i].mutable_grad() = grads[i].to(ps[i].device()).clone();
+        torch::NoGradGuard ng;
+        m->optimizer_->step();
+        m->optimizer_->zero_grad(true);
+    }
+
     // GaussianModel::training_statis (gaussian_model.cpp:1459-1503); reads viewspace_point_tensor.grad()
     void training_statis(T viewspace_grad, T opacity, T update_filter, T offset_selection_mask, T anchor_visible_mask) {
         T v = torch::zeros_like(viewspace_grad).requires_grad_(true);
@@ -314,6 +325,8 @@ struct RefModel {
         auto pkg = GaussianRenderer::render(kf, H, W, m, pipe, bg, override_color, voxel_visible_mask, true);
         auto rendered_image = std::get<0>(pkg);
         auto scaling = std::get<6>(pkg);
+        T raw_image = rendered_image;
+        raw_image.retain_grad();
         T image = rendered_image.detach().clone();
         T gt_image = gt_image_in;
         T mask_rgb = (gt_image != 0.0f).any(-1).to(torch::kFloat32).unsqueeze(-1);
@@ -335,6 +348,7 @@ struct RefModel {
         out.push_back(std::get<4>(pkg));
         out.push_back(std::get<5>(pkg).detach());
         out.push_back(voxel_visible_mask);
+        out.push_back(raw_image.grad().defined() ? raw_image.grad().clone() : torch::zeros_like(image));    // dL/d(rendered image)
         for (auto& p : params) p.mutable_grad() = T();
         return out;
     }
@@ -360,6 +374,7 @@ PYBIND11_MODULE(_model_ref, mod) {
         .def("training_setup", &RefModel::training_setup)
         .def("set_learning_rates", &RefModel::set_learning_rates)
         .def("n_param_groups", &RefModel::n_param_groups)
+        .def("adam_step_with_grads", &RefModel::adam_step_with_grads, py::call_guard<py::gil_scoped_release>())
         .def("training_statis", &RefModel::training_statis)
         .def("adjust_anchor", &RefModel::adjust_anchor)
         .def("set_statistics", &RefModel::set_statistics)

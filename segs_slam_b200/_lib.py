@@ -130,6 +130,19 @@ _PROTOTYPES = {
         C.c_int,
         [C.c_int, C.c_void_p, C.c_int, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p],
     ),
+    "segs_anchor_growing_level": (
+        C.c_int,
+        [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
+         C.c_float, C.c_float, C.c_float, C.c_float, ALLOC_FN, C.c_void_p, ALLOC_FN, C.c_void_p,
+         C.POINTER(C.c_void_p), C.POINTER(C.c_void_p), C.POINTER(C.c_int), C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "segs_prune_scratch_words": (C.c_size_t, [C.c_int]),
+    "segs_prune_plan": (
+        C.c_int,
+        [C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_float, C.c_float, C.c_float, C.c_void_p, C.c_void_p, C.c_void_p,
+         C.POINTER(C.c_int), C.c_void_p],
+    ),
+    "segs_compact_rows": (C.c_int, [C.c_int, C.c_int, C.c_void_p, C.c_void_p, _f32p, _f32p, C.c_int, C.c_float, C.c_void_p]),
     "segs_workspace_create": (C.c_int, [C.POINTER(C.c_void_p)]),
     "segs_workspace_destroy": (C.c_int, [C.c_void_p]),
     "segs_workspace_bytes": (C.c_size_t, [C.c_void_p]),

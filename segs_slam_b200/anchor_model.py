@@ -26,6 +26,8 @@ class AnchorModel(nn.Module):
                  add_cov_dist: bool = False, add_color_dist: bool = False):
         super().__init__()
         self.feat_dim, self.n_offsets = FEAT_DIM, N_OFFSETS
+        # densification parameters, defaults of GaussianModelParams (include/gaussian_parameters.h:35-41)
+        self.voxel_size, self.update_depth, self.update_init_factor, self.update_hierachy_factor = 0.001, 3, 16, 4
         self.appearance_dim, self.use_feat_bank = appearance_dim, use_feat_bank
         self.add_opacity_dist, self.add_cov_dist, self.add_color_dist = add_opacity_dist, add_cov_dist, add_color_dist
         od, cd, kd = int(add_opacity_dist), int(add_cov_dist), int(add_color_dist)

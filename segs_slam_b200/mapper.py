@@ -343,6 +343,68 @@ class FusedMapper:
         return loss / float(n_views)
 
 
+    # ---- densification (GaussianModel::adjust_anchor, gaussian_model.cpp:1705-1762) -------------------------------------
+    def adjust_anchor(self, check_interval: int = 100, success_threshold: float = 0.8, grad_threshold: float = 0.0002,
+                      min_opacity: float = 0.005, rands=None, generator=None, **model):
+        """Grow and prune the anchor set from the running statistics (`statistics=True`), exactly as the reference does
+        every `update_interval` iterations (src/gaussian_mapper.cpp:966-971), then rebuild the flat gradient bucket, the
+        fused Adam's moments (old rows keep theirs, new rows start from zero, the step count is kept — :1663-1681) and the
+        statistics for the new anchor count.  The statistics are all-reduced sums and the random draw comes from
+        `generator` (default: a generator every rank seeds identically), so every replica takes the same decisions
+        without a broadcast.  `model`: n_offsets, update_depth, update_init_factor, update_hierachy_factor, voxel_size
+        (defaults: GaussianModelParams, include/gaussian_parameters.h:35-41).  -> (anchors before, anchors after)"""
+        from . import densify
+        if not self.statistics:
+            raise RuntimeError("FusedMapper.adjust_anchor needs statistics=True")
+        pc, opt = self.pc, self.optimizer
+        dev = pc._anchor.device
+        A0 = pc._anchor.size(0)
+        if generator is None and rands is None:
+            if getattr(self, "_densify_generator", None) is None:
+                self._densify_generator = torch.Generator(device=dev)
+                self._densify_generator.manual_seed(int(getattr(self, "densify_seed", 20260101)))
+            generator = self._densify_generator
+        for k in ("n_offsets", "update_depth", "update_init_factor", "update_hierachy_factor", "voxel_size"):
+            if k not in model and hasattr(pc, k):
+                model[k] = getattr(pc, k)
+        with torch.no_grad():
+            st = {"_anchor": pc._anchor.detach(), "_offset": pc._offset.detach(), "_anchor_feat": pc._anchor_feat.detach(),
+                  "_scaling": pc._scaling.detach(),
+                  "_opacity": pc._opacity.detach() if hasattr(pc, "_opacity") else torch.zeros(A0, 1, device=dev),
+                  "_rotation": pc._rotation.detach() if hasattr(pc, "_rotation") else
+                  torch.tensor([1.0, 0.0, 0.0, 0.0], device=dev).repeat(A0, 1),
+                  "opacity_accum": self.opacity_accum.clone(), "anchor_demon": self.anchor_demon.clone(),
+                  "offset_gradient_accum": self.offset_gradient_accum.clone(), "offset_denom": self.offset_denom.clone()}
+            off = 0
+            for name, p, n in zip(("_anchor", "_offset", "_anchor_feat", "_scaling"), self.params[:4], self.bucket.sizes[:4]):
+                st["m_" + name] = opt.exp_avg[off:off + n].view(p.shape).clone()
+                st["v_" + name] = opt.exp_avg_sq[off:off + n].view(p.shape).clone()
+                off += n
+            tail_m, tail_v = opt.exp_avg[off:].clone(), opt.exp_avg_sq[off:].clone()          # the MLP tensors' moments
+            densify.adjust_anchor(st, check_interval, success_threshold, grad_threshold, min_opacity, rands, generator, **model)
+            for name in ("_anchor", "_offset", "_anchor_feat", "_scaling", "_opacity", "_rotation"):
+                if hasattr(pc, name):
+                    old = getattr(pc, name)
+                    setattr(pc, name, torch.nn.Parameter(st[name].contiguous(), requires_grad=old.requires_grad))
+            A1 = pc._anchor.size(0)
+            self.params = [pc._anchor, pc._offset, pc._anchor_feat, pc._scaling] + [w for w in self.weights if w is not None]
+            self.bucket = GradBucket(self.params)
+            opt.bucket = self.bucket
+            opt.exp_avg = torch.cat([st["m_" + n].reshape(-1) for n in ("_anchor", "_offset", "_anchor_feat", "_scaling")] + [tail_m])
+            opt.exp_avg_sq = torch.cat([st["v_" + n].reshape(-1) for n in ("_anchor", "_offset", "_anchor_feat", "_scaling")] + [tail_v])
+            v = iter(self.bucket.views[4:])
+            self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
+            self.stats = torch.cat([st["opacity_accum"].reshape(-1), st["anchor_demon"].reshape(-1),
+                                    st["offset_gradient_accum"].reshape(-1), st["offset_denom"].reshape(-1)]).contiguous()
+            self.stats_delta = torch.zeros_like(self.stats)
+            cut = lambda t: (t[:A1].view(A1, 1), t[A1:2 * A1].view(A1, 1), t[2 * A1:12 * A1].view(10 * A1, 1), t[12 * A1:].view(10 * A1, 1))
+            self.opacity_accum, self.anchor_demon, self.offset_gradient_accum, self.offset_denom = cut(self.stats)
+            self._stat_delta_views = cut(self.stats_delta)
+            self._dirty = False                                                              # the new bucket starts zeroed
+            self.last_densify = {"growing": st.get("_growing_report"), "prune": st.get("_prune_report")}
+        return A0, A1
+
+
 class RasterBatch:
     """A keyframe batch over EXPLICIT Gaussians (precomputed colours, scale + quaternion) on concurrent lanes
     (`segs_raster_views`, csrc/mapper_view.cu): per view the GaussianRasterizer forward
