@@ -158,11 +158,13 @@ def adjust_anchor(st, check_interval: int = 100, success_threshold: float = 0.8,
         def compact(t, row_floats, clamp_from=-1, clamp_max=0.0):
             src = t.contiguous()
             dst = torch.empty((n, row_floats), **f32)
+            if n == 0:
+                return dst
             _lib.check(lib.segs_compact_rows(A, row_floats, keep.data_ptr(), keep_index.data_ptr(), src.data_ptr(), dst.data_ptr(),
                                              clamp_from, clamp_max, _stream()))
             return dst
 
-        if n != A or True:                       # prune_anchor runs whenever the mask is non-empty (:1757-1760): the clamp too
+        if True:                                 # prune_anchor runs whenever the mask is non-empty (:1757-1760): the clamp too
             st["offset_denom"] = compact(st["offset_denom"], n_offsets).view(-1, 1)
             st["offset_gradient_accum"] = compact(st["offset_gradient_accum"], n_offsets).view(-1, 1)
             st["opacity_accum"] = compact(st["opacity_accum"], 1)

@@ -50,7 +50,10 @@ def reference_model(model_ref, st, grads_adam):
 
 def reference_state(m):
     """dict of the reference model's tensors + the moments of the four trainable anchor tensors."""
-    out = dict(zip(NAMES, m.state()))
+    # RefModel.state() order (oracle/model_ref_wrap.cpp)
+    order = ("_anchor", "_offset", "_anchor_feat", "_scaling", "_rotation", "_opacity", "opacity_accum", "anchor_demon",
+             "offset_gradient_accum", "offset_denom")
+    out = dict(zip(order, m.state()))
     adam = m.adam_state()          # groups: anchor, offset, feat, opacity, scaling, rotation
     for name, g in zip(("_anchor", "_offset", "_anchor_feat", "_opacity", "_scaling", "_rotation"), adam):
         if len(g) == 3:

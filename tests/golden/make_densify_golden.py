@@ -23,7 +23,7 @@ import model_ref  # noqa: E402
 def main(out_dir=HERE):
     os.makedirs(out_dir, exist_ok=True)
     dev = torch.device("cuda:0")
-    for case in ("a257", "a2000"):
+    for case in ("a257",):          # the larger cases are compared live on the GPU (tests/test_densify_gpu.py)
         A, seed = dc.CASES[case]
         st, grads_adam = dc.make_state(A, seed)
         m = dc.reference_model(model_ref, st, grads_adam)
