@@ -41,12 +41,16 @@ class GradBucket:
     At A = 200k anchors: anchor 3 + offset 30 + feat 32 + scaling 6 = 71 floats per anchor
     (56.8 MB) plus ~8.6k MLP floats."""
 
-    def __init__(self, params: Sequence[torch.Tensor]):
+    def __init__(self, params: Sequence[torch.Tensor], tail: int = 0):
+        """tail: extra floats behind the gradients in the same allocation (`self.tail`): the loss sum and the
+        densification-statistics delta ride in the SAME all-reduce as the gradients (`self.everything`)."""
         self.params = list(params)
         self.sizes = [p.numel() for p in self.params]
         total = sum(self.sizes)
         dev = self.params[0].device if self.params else torch.device("cpu")
-        self.flat = torch.zeros(total, dtype=torch.float32, device=dev)
+        self.everything = torch.zeros(total + int(tail), dtype=torch.float32, device=dev)
+        self.flat = self.everything[:total]
+        self.tail = self.everything[total:]
         self.views = []
         off = 0
         for p, n in zip(self.params, self.sizes):
@@ -144,19 +148,44 @@ def make_render_loss(pc, cameras, targets, image_height: int, image_width: int, 
     return render_loss
 
 
+def _one_allocation(*tensors):
+    """The flat tensor covering `tensors` when they are consecutive slices of one allocation, else None."""
+    ts = [t for t in tensors if t is not None]
+    if not ts or any(not t.is_contiguous() for t in ts):
+        return None
+    base = ts[0]._base if ts[0]._base is not None else None
+    if base is None or base.dim() != 1 or any(t._base is not base for t in ts):
+        return None
+    first = (ts[0].data_ptr() - base.data_ptr()) // 4
+    end = first
+    for t in ts:
+        if t.dtype != torch.float32 or (t.data_ptr() - base.data_ptr()) // 4 != end:
+            return None
+        end += t.numel()
+    return base[first:end]
+
+
 def exchange_step(grad_flat: torch.Tensor, loss_accum: torch.Tensor, stats_delta: torch.Tensor | None = None,
                   stats: torch.Tensor | None = None, group=None) -> torch.Tensor:
-    """The exchange of one batched step between the ranks: ONE all-reduce(sum) of the flat gradient
-    bucket, the loss sum, and — when densification statistics are kept — the second, small all-reduce of this step's
-    statistics delta, which is then added to the running accumulators on every rank (so every replica holds the
-    statistics of ALL views and takes the same densification decisions).  Device-agnostic host logic (NCCL on the GPU
-    box, gloo in tests/test_mapper_cpu.py).  -> loss sum over all ranks (a new tensor)."""
-    loss = loss_accum.clone()
+    """The exchange of one batched step between the ranks: the flat gradient bucket, the loss sum and —
+    when densification statistics are kept — this step's statistics delta are summed over the ranks, and the delta is
+    added to the running accumulators on every rank (so every replica holds the statistics of ALL views and takes the
+    same densification decisions).  When the three live back to back in one allocation (FusedMapper: GradBucket with a
+    tail) that is ONE all-reduce; otherwise one per tensor.  Device-agnostic host logic (NCCL on the GPU box, gloo in
+    tests/test_mapper_cpu.py).  -> loss sum over all ranks (a new tensor; `loss_accum` then holds the sum too when fused)."""
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-        dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
-        dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
-        if stats_delta is not None:
-            dist.all_reduce(stats_delta, op=dist.ReduceOp.SUM, group=group)
+        fused = _one_allocation(grad_flat, loss_accum.view(-1), stats_delta)
+        if fused is not None:
+            dist.all_reduce(fused, op=dist.ReduceOp.SUM, group=group)
+            loss = loss_accum.clone()
+        else:
+            loss = loss_accum.clone()
+            dist.all_reduce(grad_flat, op=dist.ReduceOp.SUM, group=group)
+            dist.all_reduce(loss, op=dist.ReduceOp.SUM, group=group)
+            if stats_delta is not None:
+                dist.all_reduce(stats_delta, op=dist.ReduceOp.SUM, group=group)
+    else:
+        loss = loss_accum.clone()
     if stats_delta is not None and stats is not None:
         stats.add_(stats_delta)
     return loss
@@ -195,20 +224,21 @@ class FusedMapper:
         for p in self.params:
             if not p.is_contiguous():
                 raise RuntimeError("FusedMapper: parameters must be contiguous")
-        self.bucket = GradBucket(self.params)
+        self.statistics = bool(statistics)
+        # gradients | loss sum | statistics delta in ONE allocation: one all-reduce per step moves all three
+        self.bucket = GradBucket(self.params, tail=1 + (22 * pc._anchor.size(0) if self.statistics else 0))
         self.optimizer = FusedAdam(self.bucket, lrs, eps=eps)
         v = iter(self.bucket.views[4:])
         self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
-        self.loss_accum = torch.zeros((), dtype=torch.float32, device=pc._anchor.device)
+        self.loss_accum = self.bucket.tail[:1].view(())
         # densification statistics (GaussianModel::training_statis, gaussian_model.cpp:1459-1503): running accumulators
         # opacity_accum [A,1], anchor_demon [A,1], offset_gradient_accum [A*10,1], offset_denom [A*10,1] and the per-step
         # delta the views add to; the delta is all-reduced (the second, small all-reduce of SURVEY §8e) so that the
         # replicas' statistics — and therefore their densification decisions — stay identical
-        self.statistics = bool(statistics)
         if self.statistics:
             A_ = pc._anchor.size(0)
             self.stats = torch.zeros(22 * A_, dtype=torch.float32, device=pc._anchor.device)
-            self.stats_delta = torch.zeros_like(self.stats)
+            self.stats_delta = self.bucket.tail[1:]
             cut = lambda t: (t[:A_].view(A_, 1), t[A_:2 * A_].view(A_, 1), t[2 * A_:12 * A_].view(10 * A_, 1), t[12 * A_:].view(10 * A_, 1))
             self.opacity_accum, self.anchor_demon, self.offset_gradient_accum, self.offset_denom = cut(self.stats)
             self._stat_delta_views = cut(self.stats_delta)
@@ -326,12 +356,10 @@ class FusedMapper:
         world = dist.get_world_size(self.group) if dist.is_available() and dist.is_initialized() else 1
         rank = dist.get_rank(self.group) if world > 1 else 0
         self._prepare()
-        self.loss_accum.zero_()
+        self.bucket.tail.zero_()                                     # loss sum + this step's statistics delta
         if self._dirty:
             self.bucket.zero_()                                      # normally cleared by the previous Adam launch
         self._dirty = True
-        if self.statistics:
-            self.stats_delta.zero_()
         mine = partition_views(n_views, world, rank)
         self.render_views([cameras[v] for v in mine], [targets[v] for v in mine],
                           None if row_masks is None else [row_masks[v] for v in mine])
@@ -388,15 +416,16 @@ class FusedMapper:
                     setattr(pc, name, torch.nn.Parameter(st[name].contiguous(), requires_grad=old.requires_grad))
             A1 = pc._anchor.size(0)
             self.params = [pc._anchor, pc._offset, pc._anchor_feat, pc._scaling] + [w for w in self.weights if w is not None]
-            self.bucket = GradBucket(self.params)
+            self.bucket = GradBucket(self.params, tail=1 + 22 * A1)
             opt.bucket = self.bucket
+            self.loss_accum = self.bucket.tail[:1].view(())
             opt.exp_avg = torch.cat([st["m_" + n].reshape(-1) for n in ("_anchor", "_offset", "_anchor_feat", "_scaling")] + [tail_m])
             opt.exp_avg_sq = torch.cat([st["v_" + n].reshape(-1) for n in ("_anchor", "_offset", "_anchor_feat", "_scaling")] + [tail_v])
             v = iter(self.bucket.views[4:])
             self._wgrad_views = [next(v) if w is not None else None for w in self.weights]
             self.stats = torch.cat([st["opacity_accum"].reshape(-1), st["anchor_demon"].reshape(-1),
                                     st["offset_gradient_accum"].reshape(-1), st["offset_denom"].reshape(-1)]).contiguous()
-            self.stats_delta = torch.zeros_like(self.stats)
+            self.stats_delta = self.bucket.tail[1:]
             cut = lambda t: (t[:A1].view(A1, 1), t[A1:2 * A1].view(A1, 1), t[2 * A1:12 * A1].view(10 * A1, 1), t[12 * A1:].view(10 * A1, 1))
             self.opacity_accum, self.anchor_demon, self.offset_gradient_accum, self.offset_denom = cut(self.stats)
             self._stat_delta_views = cut(self.stats_delta)

@@ -113,3 +113,79 @@ def test_exchange_step_sums_gradients_loss_and_statistics_over_ranks():
     stats = torch.zeros(2)
     total = mapper.exchange_step(torch.ones(3), torch.tensor(2.0), torch.tensor([1.0, 2.0]), stats)
     assert float(total) == 2.0 and torch.equal(stats, torch.tensor([1.0, 2.0]))
+
+
+def _fused_exchange_worker(rank, world, port, out):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    # FusedMapper's layout: gradients | loss | statistics delta in ONE allocation -> one all-reduce
+    bk = mapper.GradBucket([torch.zeros(6, 2), torch.zeros(3)], tail=1 + 4)
+    loss, delta = bk.tail[:1].view(()), bk.tail[1:]
+    stats = torch.zeros(4)
+    calls = []
+    real = dist.all_reduce
+    dist.all_reduce = lambda t, *a, **k: (calls.append(t.numel()), real(t, *a, **k))[1]
+    try:
+        bk.flat += float(rank + 1)
+        loss += 0.25 * (rank + 1)
+        delta += torch.tensor([1.0, 0.0, float(rank), 2.0])
+        total = mapper.exchange_step(bk.flat, loss, delta, stats)
+    finally:
+        dist.all_reduce = real
+    out[rank] = (bk.flat.clone(), float(total), stats.clone(), calls)
+    dist.destroy_process_group()
+
+
+def test_exchange_step_is_one_collective_when_everything_shares_an_allocation():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_fused_exchange_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    for r in (0, 1):
+        g, l, s, calls = out[r]
+        assert calls == [15 + 1 + 4], calls                       # ONE all-reduce over gradients + loss + delta
+        assert torch.equal(g, torch.full((15,), 3.0)) and l == 0.75 and torch.equal(s, torch.tensor([2.0, 0.0, 1.0, 4.0]))
+
+
+def _densify_worker(rank, world, port, out):
+    """Two replicas with identical parameters accumulate the densification statistics of THEIR views, exchange the delta,
+    and take the densification decision with a generator seeded identically on every rank: the anchor sets must come out
+    identical (the decision routine here is the restated oracle — the CUDA one needs a GPU, tests/test_densify_gpu.py)."""
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, os.path.join(root, "oracle"))
+    sys.path.insert(0, os.path.join(root, "tests"))
+    import densify_cases as dc
+    import densify_oracle
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    A = 400
+    st, _g = dc.make_state(A, 9)
+    # split the statistics into per-rank contributions (views seen by rank 0 / rank 1)
+    stat_names = ("opacity_accum", "anchor_demon", "offset_gradient_accum", "offset_denom")
+    full = torch.cat([st[k].reshape(-1) for k in stat_names])
+    g = torch.Generator().manual_seed(3)
+    share = torch.rand(full.numel(), generator=g)
+    mine = torch.where((share < 0.5) == (rank == 0), full, torch.zeros_like(full))      # disjoint, sums to `full` exactly
+    bk = mapper.GradBucket([torch.zeros(4)], tail=1 + full.numel())
+    loss, delta = bk.tail[:1].view(()), bk.tail[1:]
+    delta.copy_(mine)
+    stats = torch.zeros_like(full)
+    mapper.exchange_step(bk.flat, loss, delta, stats)
+    sizes = [st[k].numel() for k in stat_names]
+    for k, chunk in zip(stat_names, torch.split(stats, sizes)):
+        st[k] = chunk.view_as(st[k]).clone()
+    gen = torch.Generator().manual_seed(20260101)                   # the shared densification seed
+    rands = [torch.rand(A * 10, generator=gen) for _ in range(dc.MODEL["update_depth"])]
+    res = densify_oracle.adjust_anchor(st, rands, 100, 0.8, 0.0002, 0.005, **dc.MODEL)
+    out[rank] = {k: res[k].clone() for k in ("_anchor", "_anchor_feat", "_scaling", "offset_denom", "anchor_demon")}
+    dist.destroy_process_group()
+
+
+def test_replicas_take_identical_densification_decisions():
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_densify_worker, args=(2, _free_port(), out), nprocs=2, join=True)
+    a, b = out[0], out[1]
+    assert a["_anchor"].size(0) != 400                              # something was grown / pruned
+    for k in a:
+        assert torch.equal(a[k], b[k]), k
