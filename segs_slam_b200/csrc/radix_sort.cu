@@ -1,74 +1,70 @@
-// Stable LSD radix sort of (u32 key, u32 value) pairs for sm_100a — single-pass-per-digit
-// ("onesweep") formulation.  Used for the depth ordering of the Gaussians, the super-tile
-// grouping of the binning candidates (binning.cu) and the Morton ordering of the kNN (knn.cu);
-// together with binning.cu it replaces the reference's cub::DeviceRadixSort::SortPairs over
-// 64-bit tile|depth keys (cuda_rasterizer/rasterizer_impl.cu:303-309) and simple-knn's
-// cub sort (simple_knn.cu:204-209).
+// Stable LSD radix sort of (u32 key, u32 value) pairs for sm_100a — ONE persistent kernel for the histogram and all digit
+// passes.  Used for the depth ordering of the Gaussians, the super-tile grouping of the binning candidates (binning.cu),
+// the Morton ordering of the kNN (knn.cu) and the voxel ordering of the densification (densify.cu); together with
+// binning.cu it replaces the reference's cub::DeviceRadixSort::SortPairs over 64-bit tile|depth keys
+// (cuda_rasterizer/rasterizer_impl.cu:303-309) and simple-knn's cub sort (simple_knn.cu:204-209).
 //
-//   1. ONE histogram kernel reads the keys once and builds the 256-bin histogram of every digit
-//      that will be sorted on.
-//   2. One kernel per 8-bit digit.  A CTA owns a tile of TILE keys (tile index handed out by an
-//      atomic ticket, so a CTA only ever waits for CTAs that are already running), ranks its keys
-//      per warp with match.any (stable: lanes in order, warps in order, items in order), publishes
-//      its per-digit counts and resolves its scatter base with a decoupled look-back over the
-//      preceding tiles (flag + count packed in one 32-bit word, so no fences are needed), then
-//      scatters.  Traffic per digit: one read + one write of the pairs — the algorithmic minimum —
-//      and 1 launch instead of histogram + scan + scatter.
+// At the sizes of this path (1e5 - 5e6 keys, 33 - 1600 tiles) a pass is one wave of CTAs, so what a sort costs is not
+// bandwidth (8 bytes in + 8 bytes out per pair and pass: 2.5 us at 1M pairs) but launch gaps and the latency of the
+// inter-tile prefix.  Measured on B200 with one kernel per pass and a classic decoupled look-back (round 1): 12 us per CTA,
+// of which 4.3 us walking back over the tile counts, plus ~9 us of launch / ramp / drain per pass.  Hence:
 //
+//   * One launch.  CTAs draw tickets from a global counter: ticket -> (stage, tile).  Stage 0 tiles build the 256-bin
+//     histograms of every digit; stage p+1 tiles run digit p.  A tile of stage s waits until all tiles of stage s-1 have
+//     finished (a counter per stage).  Tickets are handed out in order, so a waiting CTA only ever waits for CTAs that
+//     are already running: no co-residency assumption, no cooperative launch.
+//   * No prefix chain.  Every tile publishes its digit counts EARLY (shared-memory atomics right after the load, before
+//     the ranking); the last tile of every group of 32 also publishes the group's sum.  A tile's scatter base is then
+//     digit base + the counts of the <= 31 preceding tiles of its group + the sums of the preceding groups: independent
+//     loads issued together, not a walk that has to meet a published prefix.
+//   * Peer masks for the stable in-warp ranking come from 8 ballots (one per digit bit) rather than match.any.
+//   * Each digit's run of a tile is staged through shared memory so that it is stored coalesced.
+//
+// Data written earlier in the same launch is read with ld.global.cg / volatile loads (L1 is not coherent).
 // All scratch is caller-provided (radix_sort_temp_words) and zeroed here with one memset.
+#include <algorithm>
 #include "common.cuh"
 
 namespace segs {
 
 namespace {
 
+// dev aid (tools/cuda/sort_bench.cu -DSEGS_RS_PHASE_TIMING): cycles per phase of sort_tile, summed over tiles
+#ifdef SEGS_RS_PHASE_TIMING
+#define RS_T(i) do { __syncthreads(); if (threadIdx.x == 0) rs_t[i] = clock64(); } while (0)
+#else
+#define RS_T(i) do { } while (0)
+#endif
+
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int RS_THREADS = 256;
 constexpr int RS_WARPS = RS_THREADS / 32;
 constexpr int RS_ITEMS = 12;                         // keys per thread
-constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 3072 keys per CTA
+constexpr int RS_TILE = RS_THREADS * RS_ITEMS;       // 3072 keys per tile
 constexpr int RS_MAX_PASSES = 4;
-constexpr uint32_t FLAG_AGG = 1u << 30;              // tile's own count is available
-constexpr uint32_t FLAG_PREFIX = 2u << 30;           // inclusive prefix over tiles [0, tile] is available
-constexpr uint32_t FLAG_MASK = 3u << 30;
+constexpr int RS_GROUP = 32;                         // tiles per group (one published sum per group)
+constexpr uint32_t FLAG_SET = 1u << 31;              // word published (counts stay below 2^31)
 static_assert(RS_THREADS == RADIX_BINS, "one thread per radix bin");
 
 inline int rs_tiles(size_t n) { return int((n + RS_TILE - 1) / RS_TILE); }
+inline int rs_groups(int tiles) { return (tiles + RS_GROUP - 1) / RS_GROUP; }
 
-// temp layout (u32 words): [0,4) tile tickets | [4, 4+4*256) digit histograms | look-back words
-constexpr size_t RS_HIST_OFF = 4;
+// temp layout (u32 words): control [0,16): [0] ticket, [1 + s] tiles finished in stage s |
+//                          digit histograms [4][256] | per pass: tile counts [tiles][256], group sums [groups][256]
+constexpr size_t RS_CTRL_WORDS = 16;
+constexpr size_t RS_HIST_OFF = RS_CTRL_WORDS;
 constexpr size_t RS_LOOK_OFF = RS_HIST_OFF + size_t(RS_MAX_PASSES) * RADIX_BINS;
+inline size_t rs_pass_words(int tiles) { return (size_t(tiles) + rs_groups(tiles)) * RADIX_BINS; }
 
-__global__ void __launch_bounds__(RS_THREADS)
-rs_hist_kernel(const uint32_t* __restrict__ keys, size_t n, int begin_bit, int npasses, uint32_t* __restrict__ ghist)
-{
-    __shared__ uint32_t s_hist[RS_MAX_PASSES][RADIX_BINS];
-    for (int i = threadIdx.x; i < RS_MAX_PASSES * RADIX_BINS; i += RS_THREADS) (&s_hist[0][0])[i] = 0;
-    __syncthreads();
-    for (size_t base = size_t(blockIdx.x) * RS_TILE; base < n; base += size_t(gridDim.x) * RS_TILE) {
-        uint32_t k[RS_ITEMS];
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const size_t e = base + size_t(i) * RS_THREADS + threadIdx.x;
-            k[i] = (e < n) ? __ldg(keys + e) : 0u;
-        }
-#pragma unroll
-        for (int i = 0; i < RS_ITEMS; ++i) {
-            const size_t e = base + size_t(i) * RS_THREADS + threadIdx.x;
-            if (e < n) {
-                const uint32_t v = k[i] >> begin_bit;
-#pragma unroll
-                for (int p = 0; p < RS_MAX_PASSES; ++p)
-                    if (p < npasses) atomicAdd(&s_hist[p][(v >> (8 * p)) & (RADIX_BINS - 1)], 1u);
-            }
-        }
-    }
-    __syncthreads();
-    for (int p = 0; p < npasses; ++p) {
-        const uint32_t c = s_hist[p][threadIdx.x];
-        if (c) atomicAdd(&ghist[p * RADIX_BINS + threadIdx.x], c);
-    }
-}
+struct RsShared {
+    uint32_t wh[RS_WARPS][RADIX_BINS];    // per-warp digit counts -> per-warp offsets inside the tile
+    uint32_t key[RS_TILE], val[RS_TILE];  // the tile, reordered by digit
+    uint32_t tstart[RADIX_BINS];          // first slot of every digit inside the reordered tile
+    uint32_t gbase[RADIX_BINS];           // global position of that first slot
+    uint32_t cnt[RADIX_BINS];             // the tile's digit counts (published early)
+    uint32_t warp_sums[RS_WARPS];
+    uint32_t ticket;
+};
 
 // CTA-wide exclusive scan of one value per thread (256 threads); contains two __syncthreads
 __device__ __forceinline__ uint32_t scan256(uint32_t c, uint32_t* s_warp) {
@@ -89,25 +85,71 @@ __device__ __forceinline__ uint32_t scan256(uint32_t c, uint32_t* s_warp) {
     return woff + inc - c;
 }
 
-template <bool IOTA>
-__global__ void __launch_bounds__(RS_THREADS)
-rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_out,
-               const uint32_t* __restrict__ val_in, uint32_t* __restrict__ val_out, size_t n, int shift,
-               const uint32_t* __restrict__ hist /*[256] of this digit*/, uint32_t* __restrict__ ticket,
-               volatile uint32_t* __restrict__ look /*[tiles][256]*/)
-{
-    __shared__ uint32_t s_wh[RS_WARPS][RADIX_BINS];   // per-warp digit counts -> per-warp offsets inside the tile
-    __shared__ uint32_t s_key[RS_TILE], s_val[RS_TILE];   // the tile, reordered by digit
-    __shared__ uint32_t s_tstart[RADIX_BINS];         // first slot of every digit inside the reordered tile
-    __shared__ uint32_t s_gbase[RADIX_BINS];          // global position of that first slot
-    __shared__ uint32_t s_warp[RS_WARPS];
-    __shared__ uint32_t s_tile;
-    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+// sum of `count` published words p[0], p[stride], ... : RS_BATCH loads in flight per round (their L2 latencies overlap);
+// a word that is not published yet is polled
+constexpr int RS_BATCH = 16;
+__device__ __forceinline__ uint32_t sum_published(const volatile uint32_t* p, long long stride, uint32_t count) {
+    uint32_t sum = 0;
+    for (uint32_t j0 = 0; j0 < count; j0 += RS_BATCH) {
+        uint32_t w[RS_BATCH];
+#pragma unroll
+        for (uint32_t j = 0; j < RS_BATCH; ++j) w[j] = (j0 + j < count) ? p[(long long)(j0 + j) * stride] : uint32_t(FLAG_SET);
+#pragma unroll
+        for (uint32_t j = 0; j < RS_BATCH; ++j) {
+            if (j0 + j < count) {
+                while (!(w[j] & FLAG_SET)) w[j] = p[(long long)(j0 + j) * stride];
+                sum += w[j] & ~FLAG_SET;
+            }
+        }
+    }
+    return sum;
+}
 
-    if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
-    for (int i = threadIdx.x; i < RS_WARPS * RADIX_BINS; i += RS_THREADS) (&s_wh[0][0])[i] = 0;
+// stage 0: the 256-bin histogram of every digit over one tile of the INPUT keys
+__device__ __forceinline__ void hist_tile(RsShared& sm, const uint32_t* __restrict__ keys, size_t n, uint32_t tile, int begin_bit,
+                                          int npasses, uint32_t* __restrict__ ghist)
+{
+    uint32_t* h = sm.key;                // RS_MAX_PASSES * 256 words of scratch
+    for (int i = threadIdx.x; i < RS_MAX_PASSES * RADIX_BINS; i += RS_THREADS) h[i] = 0;
     __syncthreads();
-    const uint32_t tile = s_tile;
+    const size_t base = size_t(tile) * RS_TILE;
+    uint32_t k[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const size_t e = base + size_t(i) * RS_THREADS + threadIdx.x;
+        k[i] = (e < n) ? __ldg(keys + e) : 0u;      // the input is not written by this launch
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const size_t e = base + size_t(i) * RS_THREADS + threadIdx.x;
+        if (e < n) {
+            const uint32_t v = k[i] >> begin_bit;
+#pragma unroll
+            for (int p = 0; p < RS_MAX_PASSES; ++p)
+                if (p < npasses) atomicAdd(&h[p * RADIX_BINS + ((v >> (8 * p)) & (RADIX_BINS - 1))], 1u);
+        }
+    }
+    __syncthreads();
+    for (int p = 0; p < npasses; ++p) {
+        const uint32_t c = h[p * RADIX_BINS + threadIdx.x];
+        if (c) atomicAdd(&ghist[p * RADIX_BINS + threadIdx.x], c);
+    }
+}
+
+// one tile of one digit pass
+__device__ __forceinline__ void sort_tile(RsShared& sm, const uint32_t* key_in, uint32_t* key_out, const uint32_t* val_in,
+                                          uint32_t* val_out, size_t n, int shift, bool iota, bool input_is_fresh,
+                                          const uint32_t* hist /*[256] of this digit*/, volatile uint32_t* tile_counts /*[tiles][256]*/,
+                                          volatile uint32_t* group_sums /*[groups][256]*/, uint32_t tile)
+{
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#ifdef SEGS_RS_PHASE_TIMING
+    long long rs_t[10];
+#endif
+    RS_T(0);
+    for (int i = threadIdx.x; i < RS_WARPS * RADIX_BINS; i += RS_THREADS) (&sm.wh[0][0])[i] = 0;
+    sm.cnt[threadIdx.x] = 0;
+    __syncthreads();
 
     // warp-striped: warp w owns [wbase, wbase + 32*ITEMS); item i of lane l is wbase + 32*i + l
     const size_t tbase = size_t(tile) * RS_TILE;
@@ -117,69 +159,90 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const size_t e = wbase + size_t(i) * 32 + lane;
-        key[i] = (e < n) ? __ldg(key_in + e) : 0xFFFFFFFFu;
-        val[i] = IOTA ? (uint32_t)e : ((e < n) ? __ldg(val_in + e) : 0u);
+        // pass 0 reads the caller's input; later passes read what other CTAs of this launch wrote: L2, never L1
+        key[i] = (e < n) ? (input_is_fresh ? __ldg(key_in + e) : __ldcg(key_in + e)) : 0xFFFFFFFFu;
+        val[i] = iota ? (uint32_t)e : ((e < n) ? (input_is_fresh ? __ldg(val_in + e) : __ldcg(val_in + e)) : 0u);
     }
-    const uint32_t lt_mask = (1u << lane) - 1u;
+#ifdef SEGS_RS_PHASE_TIMING
+    if (key[RS_ITEMS - 1] == 0x12345678u && val[0] == 77u) sm.ticket = 0;      // keep the loads in front of the timer
+#endif
+    RS_T(1);
+    // the tile's digit counts, published as early as possible
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const size_t e = wbase + size_t(i) * 32 + lane;
-        const bool valid = e < n;
-        const uint32_t digit = valid ? ((key[i] >> shift) & (RADIX_BINS - 1)) : RADIX_BINS;
-        const uint32_t peers = __match_any_sync(FULL, digit);
-        const int leader = __ffs(peers) - 1;
-        uint32_t old = 0;
-        if (valid && lane == leader) {
-            old = s_wh[warp][digit];
-            s_wh[warp][digit] = old + __popc(peers);
+        if (e < n) atomicAdd(&sm.cnt[(key[i] >> shift) & (RADIX_BINS - 1)], 1u);
+    }
+    __syncthreads();
+    const int bin = threadIdx.x;
+    const uint32_t count = sm.cnt[bin];
+    tile_counts[size_t(tile) * RADIX_BINS + bin] = FLAG_SET | count;
+    const uint32_t in_group = tile % RS_GROUP, group = tile / RS_GROUP;
+    uint32_t group_excl = 0;                  // counts of the preceding tiles of this tile's group
+    const bool group_leader = in_group == RS_GROUP - 1;
+    if (group_leader) {
+        // last tile of a full group: publish the group's sum (its predecessors drew their tickets earlier and publish
+        // their counts before they rank, so this wait is short)
+        group_excl = sum_published(tile_counts + size_t(tile - 1) * RADIX_BINS + bin, -(long long)RADIX_BINS, RS_GROUP - 1);
+        group_sums[size_t(group) * RADIX_BINS + bin] = FLAG_SET | (group_excl + count);
+    }
+
+    RS_T(2);
+    // stable ranking inside each warp: peers = lanes holding the same digit, from one ballot per digit bit
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    uint32_t peers[RS_ITEMS];
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const size_t e = wbase + size_t(i) * 32 + lane;
+        const uint32_t digit = (key[i] >> shift) & (RADIX_BINS - 1);
+        uint32_t m = __ballot_sync(FULL, e < n);                // invalid items (tail of the last tile) are nobody's peer
+#pragma unroll
+        for (int b = 0; b < RADIX_BITS; ++b) {
+            const bool bit = (digit >> b) & 1u;
+            const uint32_t v = __ballot_sync(FULL, bit);
+            m &= bit ? v : ~v;
         }
-        old = __shfl_sync(FULL, old, leader);
-        rank[i] = old + __popc(peers & lt_mask);
+        peers[i] = m;
+    }
+#pragma unroll
+    for (int i = 0; i < RS_ITEMS; ++i) {
+        const size_t e = wbase + size_t(i) * 32 + lane;
+        const uint32_t digit = (key[i] >> shift) & (RADIX_BINS - 1);
+        const int leader = __ffs(peers[i]) - 1;
+        uint32_t old = 0;
+        if (e < n && lane == leader) {
+            old = sm.wh[warp][digit];
+            sm.wh[warp][digit] = old + __popc(peers[i]);
+        }
+        old = __shfl_sync(FULL, old, leader < 0 ? 0 : leader);
+        rank[i] = old + __popc(peers[i] & lt_mask);
         __syncwarp();
     }
     __syncthreads();
+    RS_T(3);
 
-    // thread t owns bin t
-    const int bin = threadIdx.x;
-    uint32_t count = 0;
+    // thread t owns bin t: exclusive offsets over the warps ...
+    uint32_t run = 0;
 #pragma unroll
     for (int w = 0; w < RS_WARPS; ++w) {
-        const uint32_t c = s_wh[w][bin];
-        s_wh[w][bin] = count;          // exclusive over warps (the digit's first slot is added below)
-        count += c;
+        const uint32_t c = sm.wh[w][bin];
+        sm.wh[w][bin] = run;
+        run += c;
     }
-    volatile uint32_t* mine = look + size_t(tile) * RADIX_BINS + bin;
-    uint32_t excl = 0;
-    if (tile == 0) {
-        *mine = FLAG_PREFIX | count;
-    } else {
-        *mine = FLAG_AGG | count;
-        // decoupled look-back: walk the preceding tiles until one has published its inclusive
-        // prefix.  LOOK words are fetched per round so their L2 latencies overlap (all tiles of a
-        // wave publish their aggregates at about the same time, so the walk is many tiles deep).
-        constexpr int LOOK = 8;
-        bool done = false;
-        for (int t = (int)tile - 1; !done; t -= LOOK) {
-            uint32_t w[LOOK];
+    // ... and over the preceding tiles: the counts of this group's earlier tiles + the sums of the earlier groups,
+    // all loads independent (no prefix chain)
+    if (!group_leader && in_group)
+        group_excl = sum_published(tile_counts + size_t(tile - 1) * RADIX_BINS + bin, -(long long)RADIX_BINS, in_group);
+    const uint32_t excl = group_excl + (group ? sum_published(group_sums + bin, RADIX_BINS, group) : 0u);
+    RS_T(4);
+    const uint32_t gbin = scan256(__ldcg(hist + bin), sm.warp_sums);      // first global slot of this digit
+    const uint32_t tstart = scan256(count, sm.warp_sums);                 // first slot of this digit inside the tile
+    sm.tstart[bin] = tstart;
+    sm.gbase[bin] = gbin + excl;
 #pragma unroll
-            for (int i = 0; i < LOOK; ++i) w[i] = (t - i >= 0) ? look[size_t(t - i) * RADIX_BINS + bin] : uint32_t(FLAG_PREFIX);
-#pragma unroll
-            for (int i = 0; i < LOOK; ++i) {
-                if (done) break;
-                while ((w[i] & FLAG_MASK) == 0u) w[i] = look[size_t(t - i) * RADIX_BINS + bin];
-                excl += w[i] & ~FLAG_MASK;
-                done = (w[i] & FLAG_MASK) == FLAG_PREFIX;
-            }
-        }
-        *mine = FLAG_PREFIX | (excl + count);
-    }
-    const uint32_t gbin = scan256(hist[bin], s_warp);          // first global slot of this digit
-    const uint32_t tstart = scan256(count, s_warp);            // first slot of this digit inside the tile
-    s_tstart[bin] = tstart;
-    s_gbase[bin] = gbin + excl;
-#pragma unroll
-    for (int w = 0; w < RS_WARPS; ++w) s_wh[w][bin] += tstart;
+    for (int w = 0; w < RS_WARPS; ++w) sm.wh[w][bin] += tstart;
     __syncthreads();
+    RS_T(5);
 
     // reorder the tile by digit in shared memory ...
 #pragma unroll
@@ -187,23 +250,84 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
         const size_t e = wbase + size_t(i) * 32 + lane;
         if (e < n) {
             const uint32_t digit = (key[i] >> shift) & (RADIX_BINS - 1);
-            const uint32_t slot = s_wh[warp][digit] + rank[i];
-            s_key[slot] = key[i];
-            s_val[slot] = val[i];
+            const uint32_t slot = sm.wh[warp][digit] + rank[i];
+            sm.key[slot] = key[i];
+            sm.val[slot] = val[i];
         }
     }
     __syncthreads();
+    RS_T(6);
     // ... so that consecutive threads store consecutive addresses inside every digit's run
     // (a direct scatter costs one 32-byte L2 sector write per 4-byte element)
 #pragma unroll
     for (int i = 0; i < RS_ITEMS; ++i) {
         const uint32_t slot = i * RS_THREADS + threadIdx.x;
         if (slot < n_tile) {
-            const uint32_t k = s_key[slot];
+            const uint32_t k = sm.key[slot];
             const uint32_t digit = (k >> shift) & (RADIX_BINS - 1);
-            const uint32_t pos = s_gbase[digit] + (slot - s_tstart[digit]);
+            const uint32_t pos = sm.gbase[digit] + (slot - sm.tstart[digit]);
             key_out[pos] = k;
-            val_out[pos] = s_val[slot];
+            val_out[pos] = sm.val[slot];
+        }
+    }
+#ifdef SEGS_RS_PHASE_TIMING
+    RS_T(7);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 7; ++i) atomicAdd(&g_rs_cycles[i], (unsigned long long)(rs_t[i + 1] - rs_t[i]));
+        atomicAdd(&g_rs_cycles[7], 1ull);
+    }
+#endif
+}
+
+#ifndef RS_MIN_CTAS
+#define RS_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(RS_THREADS, RS_MIN_CTAS)
+rs_sort_kernel(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, size_t n, int tiles, int begin_bit, int npasses,
+               int iota_values, uint32_t* temp)
+{
+    __shared__ RsShared sm;
+    volatile uint32_t* ctrl = temp;
+    uint32_t* ghist = temp + RS_HIST_OFF;
+    const uint32_t total = uint32_t(1 + npasses) * (uint32_t)tiles;
+    const size_t pass_words = (size_t(tiles) + (tiles + RS_GROUP - 1) / RS_GROUP) * RADIX_BINS;
+    for (;;) {
+        __syncthreads();                                      // everyone is done with sm (incl. sm.ticket) of the previous tile
+        if (threadIdx.x == 0) sm.ticket = atomicAdd(temp, 1u);
+        __syncthreads();
+        const uint32_t ticket = sm.ticket;
+#ifdef SEGS_RS_PHASE_TIMING
+        if (ticket == 0 && threadIdx.x == 0) { unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t)); g_rs_phase[0] = t; }
+#endif
+        if (ticket >= total) return;
+        const uint32_t stage = ticket / (uint32_t)tiles, tile = ticket % (uint32_t)tiles;
+        if (stage == 0) {
+            hist_tile(sm, key_a, n, tile, begin_bit, npasses, ghist);
+        } else {
+            // every tile of the previous stage has finished (its scatters and histogram updates are visible)
+            if (threadIdx.x == 0) {
+                while (ctrl[stage] < (uint32_t)tiles) { }
+                __threadfence();
+            }
+            __syncthreads();
+            const int p = int(stage) - 1;
+            const bool even = (p & 1) == 0;
+            uint32_t* look = temp + RS_LOOK_OFF + size_t(p) * pass_words;
+            sort_tile(sm, even ? key_a : key_b, even ? key_b : key_a, even ? val_a : val_b, even ? val_b : val_a, n,
+                      begin_bit + 8 * p, p == 0 && iota_values != 0, p == 0, ghist + p * RADIX_BINS, look,
+                      look + size_t(tiles) * RADIX_BINS, tile);
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            __threadfence();                                  // this tile's global writes before the stage counter
+#ifdef SEGS_RS_PHASE_TIMING
+            if (atomicAdd(temp + 1 + stage, 1u) == (uint32_t)tiles - 1) {
+                unsigned long long t; asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+                g_rs_phase[1 + stage] = t;
+            }
+#else
+            atomicAdd(temp + 1 + stage, 1u);
+#endif
         }
     }
 }
@@ -212,7 +336,7 @@ rs_pass_kernel(const uint32_t* __restrict__ key_in, uint32_t* __restrict__ key_o
 
 size_t radix_sort_temp_words(size_t n, int npasses)
 {
-    return RS_LOOK_OFF + size_t(npasses) * rs_tiles(n) * RADIX_BINS;
+    return RS_LOOK_OFF + size_t(npasses) * rs_pass_words(rs_tiles(n));
 }
 
 int radix_sort_pairs(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t* val_b, size_t n,
@@ -222,23 +346,11 @@ int radix_sort_pairs(uint32_t* key_a, uint32_t* key_b, uint32_t* val_a, uint32_t
     if (npasses > RS_MAX_PASSES) { set_error("radix_sort_pairs: at most %d digits", RS_MAX_PASSES); return SEGS_ERR_INVALID_ARG; }
     const int tiles = rs_tiles(n);
     SEGS_CUDA_CHECK(cudaMemsetAsync(temp, 0, radix_sort_temp_words(n, npasses) * sizeof(uint32_t), stream));
-    uint32_t* ghist = temp + RS_HIST_OFF;
-    rs_hist_kernel<<<min(tiles, SM_COUNT * 4), RS_THREADS, 0, stream>>>(key_a, n, begin_bit, npasses, ghist);
+    // persistent grid: one CTA per tile while the tiles fit the machine (every CTA then runs exactly one tile per stage
+    // and the hardware spreads them evenly over the SMs), else as many CTAs as can be resident
+    const int grid = std::min(tiles, SM_COUNT * RS_MIN_CTAS);
+    rs_sort_kernel<<<grid, RS_THREADS, 0, stream>>>(key_a, key_b, val_a, val_b, n, tiles, begin_bit, npasses, iota_values ? 1 : 0, temp);
     SEGS_LAUNCH_CHECK();
-    uint32_t *ki = key_a, *ko = key_b, *vi = val_a, *vo = val_b;
-    for (int p = 0; p < npasses; ++p) {
-        uint32_t* look = temp + RS_LOOK_OFF + size_t(p) * tiles * RADIX_BINS;
-        if (p == 0 && iota_values)
-            rs_pass_kernel<true><<<tiles, RS_THREADS, 0, stream>>>(ki, ko, vi, vo, n, begin_bit + 8 * p,
-                                                                   ghist + p * RADIX_BINS, temp + p, look);
-        else
-            rs_pass_kernel<false><<<tiles, RS_THREADS, 0, stream>>>(ki, ko, vi, vo, n, begin_bit + 8 * p,
-                                                                    ghist + p * RADIX_BINS, temp + p, look);
-        SEGS_LAUNCH_CHECK();
-        uint32_t* t;
-        t = ki; ki = ko; ko = t;
-        t = vi; vi = vo; vo = t;
-    }
     return SEGS_OK;   // result is in (key_a, val_a) for an even number of passes, (key_b, val_b) otherwise
 }
 
