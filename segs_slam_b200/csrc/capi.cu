@@ -49,7 +49,7 @@ GeomState GeomState::carve(char* base, size_t P, size_t* bytes) {
     g.val_a = c.take<uint32_t>(P);
     g.val_b = c.take<uint32_t>(P);
     g.sort_temp = c.take<uint32_t>(radix_sort_temp_words(P, 4));
-    g.counters = c.take<uint32_t>(8);
+    g.counters = c.take<uint32_t>(COUNTER_WORDS);
     if (bytes) *bytes = c.used(base) + 128;
     return g;
 }
@@ -247,7 +247,7 @@ int segs_raster_forward(
     if (!hw.host) { set_error("cudaHostAlloc for the readback words failed"); return SEGS_ERR_CUDA; }
     volatile uint32_t* host_words = hw.host;
 
-    SEGS_CUDA_CHECK(cudaMemsetAsync(g.counters, 0, 8 * sizeof(uint32_t), stream));
+    SEGS_CUDA_CHECK(cudaMemsetAsync(g.counters, 0, COUNTER_WORDS * sizeof(uint32_t), stream));
     int rc;
     prof_begin(0, stream);
     if ((rc = launch_preprocess(P, D, M, means3D, scales, rotations, opacities, shs, cov3D_precomp,

@@ -52,6 +52,8 @@ struct Carver {
     size_t used(char* base) const { return size_t(p - base); }
 };
 
+constexpr int COUNTER_BASE = 8, COUNTER_SLOTS = 256, COUNTER_WORDS = COUNTER_BASE + 2 * COUNTER_SLOTS;
+
 constexpr int RADIX_BITS = 8;
 constexpr int RADIX_BINS = 1 << RADIX_BITS;
 
@@ -84,10 +86,11 @@ struct GeomState {
     uint32_t* val_a;          // [P]
     uint32_t* val_b;          // [P]  -> depth order after 4 passes lives in val_a
     uint32_t* sort_temp;      // [radix_sort_temp_words(P, 4)]
-    uint32_t* counters;       // [8]: 0 = num_rendered (sum of tiles_touched), 1 = error flag,
+    uint32_t* counters;       // [COUNTER_WORDS]: 0 = num_rendered (sum of tiles_touched), 1 = error flag,
                               //      2 = number of coarse (super-tile, Gaussian) candidates,
                               //      3 = num_rendered as seen by the tile scan (cross-check),
-                              //      4 = preprocess CTAs finished (the last one publishes 0-2 to the host)
+                              //      4 = preprocess CTAs finished (the last one publishes 0-2 to the host),
+                              //      COUNTER_BASE + 2k, + 2k + 1 = partial sums of 0 and 2 (slot k of COUNTER_SLOTS)
     static GeomState carve(char* base, size_t P, size_t* bytes);
 };
 

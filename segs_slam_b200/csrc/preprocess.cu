@@ -3,13 +3,15 @@
 // Replaces FORWARD::preprocess / filter_preprocess / project and checkFrustum of the
 // reference (cuda_rasterizer/forward.cu:156-256, 260-334, 573-673; rasterizer_impl.cu:54-66).
 //
-// Design (B200): one thread per Gaussian, 256-thread CTAs.  The AoS inputs ([P,3] means,
-// scales, colours) are staged through shared memory with fully coalesced 4-byte loads
-// (a CTA's 256 Gaussians are one contiguous 3 KB run), every output is written to this
-// library's own SoA / 16-byte-record layout so that the binning and blend stages read
-// coalesced or gather whole 16-byte sectors.  The pass also emits the depth-sort keys and
-// clears the gradient accumulators of the Gaussians it keeps, which removes two separate
-// passes over P.
+// Design (B200): one thread per Gaussian.  The AoS inputs ([P,3] means, scales, colours) are read
+// directly: the three 4-byte loads of a warp cover one contiguous 384-byte run, so the second and
+// third are L1 hits; every output is written to this library's own SoA / 16-byte-record layout so
+// that the binning and blend stages read coalesced or gather whole 16-byte sectors (the three
+// 16-byte stores of a thread's 48-byte record are merged in L2 before they reach DRAM).  Round 1
+// staged inputs and records through shared memory (two extra barriers, 21 KB per CTA); without the
+// staging the kernel has no barrier between load and store, so more warps are in flight
+// (PRE_MIN_CTAS) and the IEEE divisions / square roots of one warp hide behind the loads of others.
+// The pass also emits the depth-sort keys, which removes a separate pass over P.
 //
 // Bit-exactness: radii / tiles_touched / rect / depth / mean2D / conic decide integer
 // outputs downstream (keys, order, ranges, n_contrib), so the arithmetic below follows the
@@ -21,13 +23,17 @@
 // fast-math).  The pattern was read from the SASS of the reference build (NVVM contracts
 // some pairs in PTX, ptxas fuses more of the remaining mul/add pairs), see DESIGN.md
 // §"bit-exact preprocess".
+#include <algorithm>
 #include "common.cuh"
 
 namespace segs {
 
 namespace {
 
-constexpr int PRE_THREADS = 256;
+constexpr int PRE_THREADS = 128;
+#ifndef PRE_MIN_CTAS
+#define PRE_MIN_CTAS 8         // 1024 threads per SM at 64 registers (48 and 40 spill and are slower; 80 is no faster)
+#endif
 
 __device__ __forceinline__ float dot3c(float a0, float b0, float a1, float b1, float a2, float b2) {
     return __fmaf_rn(a2, b2, __fmaf_rn(a0, b0, __fmul_rn(a1, b1)));
@@ -250,8 +256,136 @@ __device__ __forceinline__ void stage_rows3(const float* __restrict__ src, float
 
 enum class Mode { Render, Filter, Project };
 
+// one Gaussian (`item`) of one thread; returns through tiles_acc / cand_acc the WARP totals of tiles_touched and
+// super-tile candidates (same value in every lane)
 template <Mode MODE>
-__global__ void __launch_bounds__(PRE_THREADS)
+__device__ __forceinline__ void preprocess_one(size_t item, const float* s_view, const float* s_proj, uint32_t& tiles_acc, uint32_t& cand_acc,
+                  int P, int D, int M,
+                  const float* __restrict__ means3D, const float* __restrict__ scales,
+                  const float* __restrict__ rotations, const float* __restrict__ opacities,
+                  const float* __restrict__ shs, const float* __restrict__ cov3D_precomp,
+                  const float* __restrict__ colors_precomp,
+                  const float* __restrict__ cam_pos, const ViewParams& vp, const int prefiltered,
+                  int* __restrict__ radii,
+                  float* __restrict__ depths, uint32_t* __restrict__ tiles_touched,
+                  ushort4* __restrict__ rect, float4* __restrict__ rec, float* __restrict__ cov3D,
+                  uint8_t* __restrict__ clamped, uint32_t* __restrict__ sort_key,
+                  uint32_t* __restrict__ err_flag, float* __restrict__ out_rgb, float* __restrict__ points_image)
+{
+    const bool in_range = item < size_t(P);
+    const size_t idx = in_range ? item : size_t(P) - 1;      // tail lanes re-read the last Gaussian and write nothing
+    // all independent loads first, the matrices' barrier behind them
+    const float px = __ldg(means3D + 3 * idx), py = __ldg(means3D + 3 * idx + 1), pz = __ldg(means3D + 3 * idx + 2);
+    float sc0 = 0.f, sc1 = 0.f, sc2 = 0.f;
+    float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
+    float c3[6];
+    if (cov3D_precomp != nullptr) {
+#pragma unroll
+        for (int k = 0; k < 6; ++k) c3[k] = __ldg(cov3D_precomp + 6 * idx + k);
+    } else {
+        sc0 = __ldg(scales + 3 * idx); sc1 = __ldg(scales + 3 * idx + 1); sc2 = __ldg(scales + 3 * idx + 2);
+        q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
+    }
+    float3 rgb = make_float3(0.f, 0.f, 0.f);
+    float opacity = 0.f;
+    if (MODE == Mode::Render) {
+        if (colors_precomp != nullptr)
+            rgb = make_float3(__ldg(colors_precomp + 3 * idx), __ldg(colors_precomp + 3 * idx + 1), __ldg(colors_precomp + 3 * idx + 2));
+        opacity = __ldg(opacities + idx);
+    }
+    bool visible = false;
+    Projected pr;
+
+    // in_frustum (auxiliary.h:140-166): only the near-plane test is live.
+    const float depth = affine_row(s_view, 2, px, py, pz);
+    if (!in_range) {
+        // tail lanes of the last CTA: nothing to do, but stay for the warp-wide sums below
+    } else if (depth <= 0.2f) {
+        if (prefiltered && err_flag != nullptr) atomicExch(err_flag, 1u);
+    } else {
+        if (cov3D_precomp == nullptr) cov3d_from_scale_rot(vp.scale_modifier, sc0, sc1, sc2, q, c3);
+        visible = project_gaussian(px, py, pz, c3, s_view, s_proj, vp, pr);
+    }
+
+    if (MODE == Mode::Render) {
+        // num_rendered = sum of tiles_touched (what the reference gets from its inclusive scan,
+        // rasterizer_impl.cu:276-281): one atomic per warp
+        const uint32_t warp_tiles = __reduce_add_sync(0xFFFFFFFFu, visible ? pr.tiles : 0u);
+        // ... and the number of (super-tile, Gaussian) candidates of the two-level binning
+        uint32_t cand = 0;
+        if (visible) {
+            const int sh = vp.sshift;
+            cand = (((pr.x1 - 1) >> sh) - (pr.x0 >> sh) + 1) * (((pr.y1 - 1) >> sh) - (pr.y0 >> sh) + 1);
+        }
+        const uint32_t warp_cand = __reduce_add_sync(0xFFFFFFFFu, cand);
+        tiles_acc += warp_tiles;          // warp totals; one pair of REDs per CTA at the end of the kernel
+        cand_acc += warp_cand;
+    }
+    if (MODE != Mode::Render && !in_range) return;
+
+    if (MODE == Mode::Filter) {
+        radii[idx] = visible ? pr.radius : 0;
+        return;
+    }
+
+    bool cl[3] = {false, false, false};
+    if (visible && colors_precomp == nullptr) {
+        const float3 cp = make_float3(__ldg(cam_pos), __ldg(cam_pos + 1), __ldg(cam_pos + 2));
+        rgb = sh_to_rgb(D, shs + size_t(idx) * M * 3, make_float3(px, py, pz), cp, cl);
+    }
+
+    if (MODE == Mode::Project) {
+        // project2_image (rasterizer_impl.cu:494-585): pixel means, radii and the SH colours.
+        radii[idx] = visible ? pr.radius : 0;
+        points_image[2 * idx] = visible ? pr.px : 0.f;
+        points_image[2 * idx + 1] = visible ? pr.py : 0.f;
+        const bool has_rgb = visible && colors_precomp == nullptr;
+        out_rgb[3 * idx] = has_rgb ? rgb.x : 0.f;
+        out_rgb[3 * idx + 1] = has_rgb ? rgb.y : 0.f;
+        out_rgb[3 * idx + 2] = has_rgb ? rgb.z : 0.f;
+        return;
+    }
+
+    // ---- Mode::Render -------------------------------------------------------------
+    if (in_range) {
+        if (radii != nullptr) radii[idx] = visible ? pr.radius : 0;
+        tiles_touched[idx] = visible ? pr.tiles : 0u;
+        if (!visible) {
+            sort_key[idx] = 0xFFFFFFFFu;   // sorts behind every real depth (depth > 0.2 => sign bit 0)
+            depths[idx] = 0.f;
+            rect[idx] = make_ushort4(0, 0, 0, 0);
+            // the record of a culled Gaussian is never read
+        } else {
+            depths[idx] = depth;
+            sort_key[idx] = __float_as_uint(depth);
+            rect[idx] = make_ushort4((unsigned short)pr.x0, (unsigned short)pr.y0,
+                                     (unsigned short)pr.x1, (unsigned short)pr.y1);
+            const float det_inv = __frcp_rn(pr.det);
+            const float conic_x = __fmul_rn(pr.cov_z, det_inv);
+            const float conic_y = __fmul_rn(det_inv, -pr.cov_y);
+            const float conic_z = __fmul_rn(pr.cov_x, det_inv);
+            const float2 ext = cull_extent(opacity, pr.cov_x, pr.cov_z, pr.det);
+            float4* r = rec + 3 * idx;
+            r[0] = make_float4(pr.px, pr.py, ext.x, ext.y);
+            r[1] = make_float4(conic_x, conic_y, conic_z, opacity);
+            r[2] = make_float4(rgb.x, rgb.y, rgb.z, depth);
+            if (cov3D_precomp == nullptr) {
+#pragma unroll
+                for (int k = 0; k < 6; ++k) cov3D[size_t(k) * P + idx] = c3[k];
+            }
+            if (colors_precomp == nullptr) {
+                clamped[3 * idx + 0] = cl[0];
+                clamped[3 * idx + 1] = cl[1];
+                clamped[3 * idx + 2] = cl[2];
+            }
+        }
+    }
+}
+
+// Persistent grid (148 SMs x PRE_MIN_CTAS CTAs), each CTA strides over chunks of PRE_THREADS Gaussians: 7800 short-lived
+// 128-thread CTAs were bound by CTA launch rate, not by memory or issue slots.
+template <Mode MODE>
+__global__ void __launch_bounds__(PRE_THREADS, PRE_MIN_CTAS)
 preprocess_kernel(int P, int D, int M,
                   const float* __restrict__ means3D, const float* __restrict__ scales,
                   const float* __restrict__ rotations, const float* __restrict__ opacities,
@@ -270,157 +404,54 @@ preprocess_kernel(int P, int D, int M,
                   // Project outputs
                   float* __restrict__ out_rgb, float* __restrict__ points_image)
 {
-    __shared__ float s_mean[3 * PRE_THREADS];
-    __shared__ float s_scale[3 * PRE_THREADS];
-    __shared__ float s_color[3 * PRE_THREADS];
-    __shared__ float4 s_rec[3 * PRE_THREADS];          // render records of the CTA, staged for coalesced stores
     __shared__ float s_view[16], s_proj[16];
-
-    const size_t first = size_t(blockIdx.x) * PRE_THREADS;
-    const int n = (int)min(size_t(PRE_THREADS), size_t(P) - first);
-    stage_rows3(means3D, s_mean, first, n);
-    if (cov3D_precomp == nullptr) stage_rows3(scales, s_scale, first, n);
-    if (MODE == Mode::Render && colors_precomp != nullptr) stage_rows3(colors_precomp, s_color, first, n);
+    __shared__ uint32_t s_part[2 * PRE_THREADS / 32];
     if (threadIdx.x < 16) s_view[threadIdx.x] = __ldg(viewmatrix + threadIdx.x);
     else if (threadIdx.x < 32) s_proj[threadIdx.x - 16] = __ldg(projmatrix + threadIdx.x - 16);
     __syncthreads();
-
-    const int t = threadIdx.x;
-    const bool in_range = t < n;
-    const size_t idx = first + (in_range ? t : 0);
-
-    const float px = s_mean[3 * (in_range ? t : 0)], py = s_mean[3 * (in_range ? t : 0) + 1],
-                pz = s_mean[3 * (in_range ? t : 0) + 2];
-
-    bool visible = false;
-    Projected pr;
-    float c3[6];
-
-    // in_frustum (auxiliary.h:140-166): only the near-plane test is live.
-    const float depth = affine_row(s_view, 2, px, py, pz);
-    if (!in_range) {
-        // tail lanes of the last CTA: nothing to do, but stay for the warp-wide sum below
-    } else if (depth <= 0.2f) {
-        if (prefiltered && err_flag != nullptr) atomicExch(err_flag, 1u);
-    } else {
-        if (cov3D_precomp != nullptr) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) c3[k] = __ldg(cov3D_precomp + 6 * idx + k);
-        } else {
-            const float4 q = __ldg(reinterpret_cast<const float4*>(rotations) + idx);
-            cov3d_from_scale_rot(vp.scale_modifier, s_scale[3 * t], s_scale[3 * t + 1], s_scale[3 * t + 2], q, c3);
-        }
-        visible = project_gaussian(px, py, pz, c3, s_view, s_proj, vp, pr);
+    (void)acc;   // the gradient accumulators are cleared by the backward (forward-only renders never touch them)
+    (void)sort_val;
+    uint32_t tiles_acc = 0, cand_acc = 0;
+    const size_t chunks = (size_t(P) + PRE_THREADS - 1) / PRE_THREADS;
+    for (size_t chunk = blockIdx.x; chunk < chunks; chunk += gridDim.x)
+        preprocess_one<MODE>(chunk * PRE_THREADS + threadIdx.x, s_view, s_proj, tiles_acc, cand_acc, P, D, M, means3D, scales, rotations,
+                             opacities, shs, cov3D_precomp, colors_precomp, cam_pos, vp, prefiltered, radii, depths, tiles_touched, rect,
+                             rec, cov3D, clamped, sort_key, err_flag, out_rgb, points_image);
+    if (MODE != Mode::Render) return;
+    if ((threadIdx.x & 31) == 0) {
+        s_part[threadIdx.x >> 5] = tiles_acc;
+        s_part[PRE_THREADS / 32 + (threadIdx.x >> 5)] = cand_acc;
     }
-
-    if (MODE == Mode::Render) {
-        // num_rendered = sum of tiles_touched (what the reference gets from its inclusive scan,
-        // rasterizer_impl.cu:276-281): one atomic per warp
-        const uint32_t warp_tiles = __reduce_add_sync(0xFFFFFFFFu, visible ? pr.tiles : 0u);
-        // ... and the number of (super-tile, Gaussian) candidates of the two-level binning
-        uint32_t cand = 0;
-        if (visible) {
-            const int sh = vp.sshift;
-            cand = (((pr.x1 - 1) >> sh) - (pr.x0 >> sh) + 1) * (((pr.y1 - 1) >> sh) - (pr.y0 >> sh) + 1);
-        }
-        const uint32_t warp_cand = __reduce_add_sync(0xFFFFFFFFu, cand);
-        if ((threadIdx.x & 31) == 0 && warp_tiles) {
-            atomicAdd(num_rendered, warp_tiles);
-            atomicAdd(num_rendered + 2, warp_cand);
-        }
-        // The host needs the totals to size the binning buffer (rasterizer_impl.cu:279-285).  The
-        // last CTA to get here stores them straight into mapped pinned host memory: no copy
-        // engine is involved, so the read-back never queues behind a caller's bulk D2H copies.
+    // The host needs the totals to size the binning buffer (rasterizer_impl.cu:279-285).  The
+    // last CTA to get here stores them straight into mapped pinned host memory: no copy
+    // engine is involved, so the read-back never queues behind a caller's bulk D2H copies.
+    if (host_counters != nullptr) {
         __syncthreads();
-        if (threadIdx.x == 0 && host_counters != nullptr) {
+        if (threadIdx.x == 0) {
+            uint32_t tiles_cta = 0, cand_cta = 0;
+#pragma unroll
+            for (int w = 0; w < PRE_THREADS / 32; ++w) { tiles_cta += s_part[w]; cand_cta += s_part[PRE_THREADS / 32 + w]; }
+            if (tiles_cta) {
+                uint32_t* slot = num_rendered + COUNTER_BASE + 2 * (blockIdx.x % COUNTER_SLOTS);
+                atomicAdd(slot, tiles_cta);
+                atomicAdd(slot + 1, cand_cta);
+            }
             __threadfence();
             if (atomicAdd(num_rendered + 4, 1u) == gridDim.x - 1) {
                 __threadfence();
-                host_counters[0] = atomicAdd(num_rendered, 0u);
+                uint32_t tiles = 0, cands = 0;
+                for (int k = 0; k < COUNTER_SLOTS; ++k) {
+                    tiles += atomicAdd(num_rendered + COUNTER_BASE + 2 * k, 0u);
+                    cands += atomicAdd(num_rendered + COUNTER_BASE + 2 * k + 1, 0u);
+                }
+                num_rendered[0] = tiles;
+                num_rendered[2] = cands;
+                host_counters[0] = tiles;
                 host_counters[1] = atomicAdd(num_rendered + 1, 0u);
-                host_counters[2] = atomicAdd(num_rendered + 2, 0u);
+                host_counters[2] = cands;
                 __threadfence_system();
             }
         }
-    }
-    if (MODE != Mode::Render && !in_range) return;
-
-    if (MODE == Mode::Filter) {
-        radii[idx] = visible ? pr.radius : 0;
-        return;
-    }
-
-    float3 rgb = make_float3(0.f, 0.f, 0.f);
-    bool cl[3] = {false, false, false};
-    if (visible) {
-        if (colors_precomp == nullptr) {
-            const float3 cp = make_float3(__ldg(cam_pos), __ldg(cam_pos + 1), __ldg(cam_pos + 2));
-            rgb = sh_to_rgb(D, shs + size_t(idx) * M * 3, make_float3(px, py, pz), cp, cl);
-        } else if (MODE == Mode::Render) {
-            rgb = make_float3(s_color[3 * t], s_color[3 * t + 1], s_color[3 * t + 2]);
-        }
-    }
-
-    if (MODE == Mode::Project) {
-        // project2_image (rasterizer_impl.cu:494-585): pixel means, radii and the SH colours.
-        radii[idx] = visible ? pr.radius : 0;
-        points_image[2 * idx] = visible ? pr.px : 0.f;
-        points_image[2 * idx + 1] = visible ? pr.py : 0.f;
-        const bool has_rgb = visible && colors_precomp == nullptr;
-        out_rgb[3 * idx] = has_rgb ? rgb.x : 0.f;
-        out_rgb[3 * idx + 1] = has_rgb ? rgb.y : 0.f;
-        out_rgb[3 * idx + 2] = has_rgb ? rgb.z : 0.f;
-        return;
-    }
-
-    // ---- Mode::Render -------------------------------------------------------------
-    float4 r0 = make_float4(0.f, 0.f, 0.f, 0.f), r1 = r0, r2 = r0;
-    if (in_range) {
-    if (radii != nullptr) radii[idx] = visible ? pr.radius : 0;
-    tiles_touched[idx] = visible ? pr.tiles : 0u;
-    if (!visible) {
-        sort_key[idx] = 0xFFFFFFFFu;   // sorts behind every real depth (depth > 0.2 => sign bit 0)
-        depths[idx] = 0.f;
-        rect[idx] = make_ushort4(0, 0, 0, 0);
-    } else {
-        depths[idx] = depth;
-        sort_key[idx] = __float_as_uint(depth);
-        rect[idx] = make_ushort4((unsigned short)pr.x0, (unsigned short)pr.y0,
-                                 (unsigned short)pr.x1, (unsigned short)pr.y1);
-
-        const float det_inv = __frcp_rn(pr.det);
-        const float conic_x = __fmul_rn(pr.cov_z, det_inv);
-        const float conic_y = __fmul_rn(det_inv, -pr.cov_y);
-        const float conic_z = __fmul_rn(pr.cov_x, det_inv);
-        const float opacity = __ldg(opacities + idx);
-        const float2 ext = cull_extent(opacity, pr.cov_x, pr.cov_z, pr.det);
-        r0 = make_float4(pr.px, pr.py, ext.x, ext.y);
-        r1 = make_float4(conic_x, conic_y, conic_z, opacity);
-        r2 = make_float4(rgb.x, rgb.y, rgb.z, depth);
-        if (cov3D_precomp == nullptr) {
-#pragma unroll
-            for (int k = 0; k < 6; ++k) cov3D[size_t(k) * P + idx] = c3[k];
-        }
-        if (colors_precomp == nullptr) {
-            clamped[3 * idx + 0] = cl[0];
-            clamped[3 * idx + 1] = cl[1];
-            clamped[3 * idx + 2] = cl[2];
-        }
-    }
-    }
-    // The CTA's 48-byte records and gradient accumulators are one contiguous 12 KB run each:
-    // staged through shared memory and written with fully coalesced 16-byte stores (a per-thread
-    // 48-byte stride would touch every sector three times).  Records of culled Gaussians are
-    // zeros (never read).
-    s_rec[3 * t + 0] = r0;
-    s_rec[3 * t + 1] = r1;
-    s_rec[3 * t + 2] = r2;
-    __syncthreads();
-    (void)acc;   // the gradient accumulators are cleared by the backward (forward-only renders never touch them)
-#pragma unroll
-    for (int k = 0; k < 3; ++k) {
-        const int j = threadIdx.x + k * PRE_THREADS;
-        if (j < 3 * n) rec[3 * first + j] = s_rec[j];
     }
 }
 
@@ -439,7 +470,8 @@ mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __res
     present[first + t] = !(depth <= 0.2f);
 }
 
-inline int grid_for(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
+inline int grid_for(int P) { return std::min((P + PRE_THREADS - 1) / PRE_THREADS, SM_COUNT * PRE_MIN_CTAS); }
+inline int grid_small(int P) { return (P + PRE_THREADS - 1) / PRE_THREADS; }
 
 }  // namespace
 
@@ -491,7 +523,7 @@ int launch_project(int P, int D, int M, const float* means3D, const float* scale
 int launch_mark_visible(int P, const float* means3D, const float* viewmatrix,
                         unsigned char* present, cudaStream_t stream)
 {
-    mark_visible_kernel<<<grid_for(P), PRE_THREADS, 0, stream>>>(P, means3D, viewmatrix, present);
+    mark_visible_kernel<<<grid_small(P), PRE_THREADS, 0, stream>>>(P, means3D, viewmatrix, present);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
