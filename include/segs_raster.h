@@ -295,6 +295,26 @@ int segs_training_statis(int A, const char* decode_state, int n_vis, const float
                          const float* dL_dmean2D, float* opacity_accum, float* anchor_demon,
                          float* offset_gradient_accum, float* offset_denom, int atomic, void* stream);
 
+/* ---- frequency-domain regularisation ---------------------------------------------------
+ *   segs_freq_*   loss_utils::high_frequency_loss / multi_scale_loss      include/loss_utils.h:125-169, 210-237,
+ *                 as called at                                             src/gaussian_mapper.cpp:930-945
+ * value = weight * sum_s scales[s] * mean over [C,h_s,w_s] of | |fft2(D_s image)| - |fft2(D_s gt)| |, D_s = ATen's bilinear
+ * interpolate(scale_factor = s, align_corners = false, recompute_scale_factor = true) ([h_s, w_s] = floor([H, W] * s));
+ * high_frequency_loss is the single scale 1.  The reference's frequency mask is empty for C = 3 (it is indexed on the
+ * channel dimension), so the whole spectrum counts; low_freq_loss is identically zero for the same reason (see freq.cu).
+ * A plan owns the cuFFT plans of its scales and a working spectrum on the device it was created on; it serves one stream
+ * at a time. */
+typedef struct segs_freq_plan segs_freq_plan;
+int    segs_freq_plan_create(int C, int H, int W, int n_scales /* <= 4 */, const float* scales /* HOST, each <= 1 */, segs_freq_plan** out);
+int    segs_freq_plan_destroy(segs_freq_plan* plan);
+size_t segs_freq_mag_floats(const segs_freq_plan* plan);          /* floats of a target-magnitude buffer */
+/* gt_mag (DEVICE, segs_freq_mag_floats floats) = |fft2(D_s (gt * row_mask))| of every scale: per keyframe, reusable */
+int    segs_freq_target(segs_freq_plan* plan, const float* gt, const float* row_mask /* [C,H] or NULL */, float* gt_mag, void* stream);
+/* loss_out (DEVICE scalar, may be NULL) += value;  dL_dimage [C,H,W] (may be NULL) += dL_dloss (DEVICE scalar, NULL = 1) *
+ * d value / d image (through the row mask).  Deterministic. */
+int    segs_freq_loss(segs_freq_plan* plan, const float* image, const float* row_mask, const float* gt_mag, float weight,
+                      const float* dL_dloss, float* loss_out, float* dL_dimage, void* stream);
+
 /* ---- densification decisions ---------------------------------------------------------
  *   segs_anchor_growing_level   one level i of GaussianModel::anchor_growing     src/gaussian_model.cpp:1556-1703
  *   segs_prune_plan             the statistics update + prune decision of        src/gaussian_model.cpp:1716-1755
@@ -388,6 +408,13 @@ typedef struct segs_mapper_view_args {
     float* stat_anchor_demon;           /* [A]    */
     float* stat_offset_gradient_accum;  /* [A*10] */
     float* stat_offset_denom;           /* [A*10] */
+    /* optional frequency regularisation (src/gaussian_mapper.cpp:930-945): loss += lambda_frequency_high *
+     * (use_multi_resolution ? multi_scale_loss(scales 1, 1/2, ..., 1/2^(freq_scale_num-1)) : high_frequency_loss);
+     * 0 = off.  gt_freq_mag: segs_freq_target of this keyframe's gt_image for the same scales, or NULL (computed on the fly). */
+    float lambda_frequency_high;
+    int   use_multi_resolution;
+    int   freq_scale_num;               /* 1..4 */
+    const float* gt_freq_mag;
 } segs_mapper_view_args;
 
 typedef struct segs_mapper_view_result {
@@ -506,6 +533,11 @@ int segs_profile_enable(int on);
  * waiting threads (ranks x lanes) than they have cores.  Call before the first forward. */
 int segs_set_blocking_sync(int on);
 int segs_profile_read(float* ms /* [SEGS_PROFILE_STAGES] */);
+
+/* Work counters of the blend kernels (development builds with -DSEGS_BLEND_STATS; zeros otherwise):
+ * forward {records staged, (Gaussian, sub-tile) pairs evaluated, pairs reaching a pixel, blended (Gaussian, pixel) pairs},
+ * backward likewise. */
+int segs_debug_blend_stats(unsigned long long* out8, int reset);
 
 /* ---- inspection of the opaque buffers (parity tests, debugging) --------------------- */
 /* Returns in *ptr / *bytes the device address and size of a named section of the

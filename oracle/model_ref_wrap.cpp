@@ -48,6 +48,18 @@ struct RefModel {
     GaussianOptimizationParams opt;
     GaussianPipelineParams pipe;
     int iteration = 0;
+    // frequency regularisation of the call site (src/gaussian_mapper.cpp:930-945); 0 = off.  Replica yamls:
+    // lambda_frequency_high 0.01, use_multi_resolution 1, scale_num 3 (cfg/gaussian_mapper/RGB-D/Replica/office0.yaml:140-146)
+    double lambda_frequency_high = 0.0;
+    bool use_multi_resolution = true;
+    int scale_num = 3;
+    void set_frequency(double lambda_high, bool multi, int n) { lambda_frequency_high = lambda_high; use_multi_resolution = multi; scale_num = n; }
+    T frequency_term(const T& rendered_image, const T& gt_image) const {
+        std::vector<float> scales(scale_num, 0.f);
+        for (int i = 0; i < scale_num; ++i) scales[i] = float(1.0 / pow(2, i));                 // gaussian_mapper.cpp:514-517
+        if (use_multi_resolution) return lambda_frequency_high * loss_utils::multi_scale_loss(rendered_image, gt_image, scales);
+        return lambda_frequency_high * loss_utils::high_frequency_loss(rendered_image, gt_image);
+    }
 
     // reference_ctor = true : GaussianModel(const GaussianModelParams&) itself (gaussian_model.cpp:33-180; hard-codes
     //                         torch::kCUDA, so GPU only).
@@ -243,10 +255,7 @@ struct RefModel {
         auto ssim = loss_utils::ssim(masked_image, gt_image, m->device_type_);
         auto scaling_reg = scaling.prod(1).mean();
         auto loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - ssim) + 0.01 * scaling_reg;
-        if (frequency) {                                   // :927-942 with the Replica yaml's weights (office0.yaml:140-146)
-            loss = loss + 0.01 * loss_utils::low_freq_loss(rendered_image, gt_image);
-            loss = loss + 0.01 * loss_utils::high_frequency_loss(rendered_image, gt_image);
-        }
+        if (frequency && lambda_frequency_high != 0.0) loss = loss + frequency_term(rendered_image, gt_image);     // :930-945
         loss.backward();
         if (sync) torch::cuda::synchronize();
         {
@@ -282,6 +291,7 @@ struct RefModel {
         auto Ll1 = loss_utils::l1_loss(rendered_image, gt_image);
         auto loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - loss_utils::ssim(masked_image, gt_image, m->device_type_)) +
                     0.01 * scaling.prod(1).mean();
+        if (lambda_frequency_high != 0.0) loss = loss + frequency_term(rendered_image, gt_image);
         (loss * loss_scale).backward();
         return loss.detach();
     }
@@ -336,6 +346,7 @@ struct RefModel {
         auto Ll1 = loss_utils::l1_loss(rendered_image, gt_image);
         auto loss = (1.0 - lambda_dssim) * Ll1 + lambda_dssim * (1.0 - loss_utils::ssim(masked_image, gt_image, m->device_type_)) +
                     0.01 * scaling.prod(1).mean();
+        if (lambda_frequency_high != 0.0) loss = loss + frequency_term(rendered_image, gt_image);
         std::vector<T> params = {m->_anchor, m->_offset, m->_anchor_feat, m->_scaling};
         for (auto& p : mlp_parameters()) params.push_back(p);
         for (auto& p : params) if (p.grad().defined()) p.mutable_grad() = T();
@@ -365,6 +376,7 @@ PYBIND11_MODULE(_model_ref, mod) {
              py::arg("appearance_dim") = 32, py::arg("add_opacity_dist") = false, py::arg("add_cov_dist") = false,
              py::arg("add_color_dist") = false, py::arg("reference_ctor") = false)
         .def("device", &RefModel::device)
+        .def("set_frequency", &RefModel::set_frequency)
         .def("set_state", &RefModel::set_state)
         .def("mlp_parameters", &RefModel::mlp_parameters)
         .def("load_mlp_parameters", &RefModel::load_mlp_parameters)
@@ -395,5 +407,19 @@ PYBIND11_MODULE(_model_ref, mod) {
     mod.def("distCUDA2", &distCUDA2);
     // tanfovx exactly as GaussianRenderer::render derives it from the keyframe's FoVx_ (gaussian_renderer.cpp:67-68)
     mod.def("tan_half_fov", [](double fov) { return (double)std::tan((float)fov * 0.5f); });
+    // loss_utils::high_frequency_loss / multi_scale_loss of the reference's own header on the tensors' device, with the
+    // gradient w.r.t. the first image: -> (value, d value / d img1)
+    mod.def("high_frequency_loss", [](T a, T b) {
+        T x = a.detach().clone().requires_grad_(true);
+        T l = loss_utils::high_frequency_loss(x, b, 0.4f, a.device().type());
+        { py::gil_scoped_release nogil; l.backward(); }
+        return std::vector<T>{l.detach(), x.grad()};
+    });
+    mod.def("multi_scale_loss", [](T a, T b, std::vector<float> scales) {
+        T x = a.detach().clone().requires_grad_(true);
+        T l = loss_utils::multi_scale_loss(x, b, scales, a.device().type());
+        { py::gil_scoped_release nogil; l.backward(); }
+        return std::vector<T>{l.detach(), x.grad()};
+    });
     mod.def("scatter_max", [](T src, T index) { auto r = scatter_max(src, index, 0, std::nullopt, std::nullopt); return std::vector<T>{std::get<0>(r), std::get<1>(r)}; });
 }

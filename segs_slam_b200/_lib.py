@@ -47,7 +47,9 @@ class MapperViewArgs(C.Structure):
                 ("grad_scaling", C.c_void_p), ("grad_params", C.POINTER(DecodeGrads)), ("loss_accum", C.c_void_p),
                 ("image_out", C.c_void_p), ("loss_terms_out", C.c_void_p), ("dL_dmean2D_out", C.c_void_p),
                 ("radii_out", C.c_void_p), ("stat_opacity_accum", C.c_void_p), ("stat_anchor_demon", C.c_void_p),
-                ("stat_offset_gradient_accum", C.c_void_p), ("stat_offset_denom", C.c_void_p)]
+                ("stat_offset_gradient_accum", C.c_void_p), ("stat_offset_denom", C.c_void_p),
+                ("lambda_frequency_high", C.c_float), ("use_multi_resolution", C.c_int), ("freq_scale_num", C.c_int),
+                ("gt_freq_mag", C.c_void_p)]
 
 
 class RasterViewArgs(C.Structure):
@@ -130,6 +132,11 @@ _PROTOTYPES = {
         C.c_int,
         [C.c_int, C.c_void_p, C.c_int, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p],
     ),
+    "segs_freq_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_void_p)]),
+    "segs_freq_plan_destroy": (C.c_int, [C.c_void_p]),
+    "segs_freq_mag_floats": (C.c_size_t, [C.c_void_p]),
+    "segs_freq_target": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "segs_freq_loss": (C.c_int, [C.c_void_p, _f32p, _f32p, _f32p, C.c_float, _f32p, _f32p, _f32p, C.c_void_p]),
     "segs_anchor_growing_level": (
         C.c_int,
         [C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p, _f32p,
@@ -179,6 +186,7 @@ _PROTOTYPES = {
     "segs_profile_enable": (C.c_int, [C.c_int]),
     "segs_set_blocking_sync": (C.c_int, [C.c_int]),
     "segs_profile_read": (C.c_int, [C.POINTER(C.c_float)]),
+    "segs_debug_blend_stats": (C.c_int, [C.POINTER(C.c_ulonglong), C.c_int]),
     "segs_buffer_section": (
         C.c_int,
         [C.c_char_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int,

@@ -36,6 +36,14 @@ namespace segs {
 
 namespace {
 
+// dev aid (make EXTRA=-DSEGS_BLEND_STATS): work counters of the two kernels, read with segs_debug_blend_stats
+#ifdef SEGS_BLEND_STATS
+__device__ unsigned long long g_blend_stats[8];
+#define BSTAT(i, v) do { const unsigned long long bstat_v = (unsigned long long)(v); if ((threadIdx.x & 31) == 0) atomicAdd(&g_blend_stats[i], bstat_v); } while (0)
+#else
+#define BSTAT(i, v) do { (void)sizeof(v); } while (0)
+#endif
+
 constexpr unsigned FULL = 0xFFFFFFFFu;
 constexpr int BATCH = 256;
 
@@ -185,6 +193,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
         const int n_in = min(BATCH, len - b * BATCH);
         compute_masks(s_mask, s_rec[buf][0], n_in, tile_x0, tile_y0);
         __syncthreads();
+        if (threadIdx.x == 0) BSTAT(0, n_in);                 // records staged
 
         if (!__all_sync(FULL, done0 && done1)) {
             const int base = b * BATCH;
@@ -196,6 +205,7 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     const int j = __ffs(mask) - 1;
                     mask &= mask - 1;
                     const int slot = c * 32 + j;
+                    BSTAT(1, 1);                                  // (Gaussian, sub-tile) pairs evaluated
                     // Straight-line body (no divergent branches): every lane evaluates both of its pixels,
                     // pixels that are done / miss the reference's tests simply do not commit.
                     const float4 g0 = s_rec[buf][0][slot];
@@ -211,6 +221,8 @@ blend_forward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restric
                     const bool contrib1 = !done1 && !(power1 > 0.0f) && !(alpha1 < 1.0f / 255.0f);
                     // the extent test is a bounding box: a fifth of the hits reach no pixel of the sub-tile at all
                     if (!__any_sync(FULL, contrib0 || contrib1)) continue;
+                    BSTAT(2, 1);                                  // ... that reach at least one pixel
+                    BSTAT(3, __popc(__ballot_sync(FULL, contrib0)) + __popc(__ballot_sync(FULL, contrib1)));   // blended (Gaussian, pixel) pairs
                     const float4 g2 = s_rec[buf][2][slot];
                     const float test_T0 = __fmul_rn(T0, __fsub_rn(1.f, alpha0));
                     const float test_T1 = __fmul_rn(T1, __fsub_rn(1.f, alpha1));
@@ -375,6 +387,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
         __syncthreads();
         compute_masks(s_mask, s_rec[buf][0], n_in, tile_x0, tile_y0);
         __syncthreads();
+        if (threadIdx.x == 0) BSTAT(4, n_in);
 
         if (lo < wmax) {
             for (int c = (n_in - 1) >> 5; c >= 0; --c) {
@@ -386,6 +399,7 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                     mask &= ~(1u << j);
                     const int slot = c * 32 + j;
                     const int pos = lo + slot;
+                    BSTAT(5, 1);
                     const float4 g0 = s_rec[buf][0][slot];
                     const float4 g1 = s_rec[buf][1][slot];
                     const float dx = __fsub_rn(g0.x, pixfx);
@@ -398,6 +412,8 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
                     const bool act0 = (pos < p0.last) && !(power0 > 0.0f) && !(ar0 < 1.0f / 255.0f);
                     const bool act1 = (pos < p1.last) && !(power1 > 0.0f) && !(ar1 < 1.0f / 255.0f);
                     if (!__any_sync(FULL, act0 || act1)) continue;
+                    BSTAT(6, 1);
+                    BSTAT(7, __popc(__ballot_sync(FULL, act0)) + __popc(__ballot_sync(FULL, act1)));
 
                     // Straight-line maths: a pixel that does not contribute runs with G = alpha = 0, which makes
                     // every gradient term exactly 0 and leaves T and S unchanged (1/(1-0) = 1, 0 c + 1 S = S).
@@ -456,6 +472,20 @@ blend_backward_kernel(const uint2* __restrict__ ranges, const uint32_t* __restri
 }
 
 }  // namespace
+
+int debug_blend_stats(unsigned long long* out, bool reset)
+{
+#ifdef SEGS_BLEND_STATS
+    SEGS_CUDA_CHECK(cudaDeviceSynchronize());
+    SEGS_CUDA_CHECK(cudaMemcpyFromSymbol(out, g_blend_stats, sizeof(g_blend_stats)));
+    if (reset) { unsigned long long z[8] = {0}; SEGS_CUDA_CHECK(cudaMemcpyToSymbol(g_blend_stats, z, sizeof(z))); }
+    return SEGS_OK;
+#else
+    (void)reset;
+    for (int i = 0; i < 8; ++i) out[i] = 0;
+    return SEGS_OK;
+#endif
+}
 
 int launch_blend_forward(const ViewParams& vp, const GeomState& g, const BinningState& b,
                          ImageState& img, const float* background, float* out_color,

@@ -387,6 +387,8 @@ int segs_project(
                           viewmatrix, projmatrix, cam_pos, vp, false, out_rgb, points_image, radii, stream);
 }
 
+int segs_debug_blend_stats(unsigned long long* out8, int reset) { return out8 ? debug_blend_stats(out8, reset != 0) : SEGS_ERR_INVALID_ARG; }
+
 int segs_buffer_section(const char* name, char* geom_buffer, char* binning_buffer, char* image_buffer,
                         int P, int R, int width, int height, void** ptr, size_t* bytes)
 {

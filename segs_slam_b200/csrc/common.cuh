@@ -162,6 +162,8 @@ int launch_depth_order(int P, GeomState& g, cudaStream_t stream);
 int launch_binning(int P, int R, int Rc, const ViewParams& vp, GeomState& g, BinningState& b,
                    ImageState& img, cudaStream_t stream);
 
+int debug_blend_stats(unsigned long long* out8, bool reset);   // zeros unless built with -DSEGS_BLEND_STATS
+
 int launch_blend_forward(const ViewParams& vp, const GeomState& g, const BinningState& b,
                          ImageState& img, const float* background, float* out_color,
                          cudaStream_t stream);

@@ -9,6 +9,7 @@
 // ~150 ATen launches with autograd bookkeeping; here it is 27 launches, two host read-backs (the
 // decode's row count and num_rendered — both shape the next allocation, as in the reference) and no
 // temporary that outlives the view: everything is carved from a reusable workspace arena.
+#include <cmath>
 #include <condition_variable>
 #include <functional>
 #include <mutex>
@@ -34,6 +35,12 @@ struct segs_workspace {
     size_t granule = size_t(256) << 20;
     size_t total = 0;
     bool failed = false;
+
+    // frequency regularisation: cuFFT plans + working spectrum for the last (H, W, scales) used on this lane, and the
+    // target magnitudes when the caller did not precompute them
+    segs_freq_plan* freq = nullptr;
+    int freq_H = 0, freq_W = 0, freq_ns = 0;
+    float* freq_gt_mag = nullptr;
 
     // lane thread (segs_mapper_views): persistent, so the per-thread pinned read-back words and events of the
     // library are created once, not once per step
@@ -138,6 +145,8 @@ int segs_workspace_destroy(segs_workspace* ws)
 {
     if (!ws) return SEGS_OK;
     ws->stop_worker();
+    if (ws->freq) segs_freq_plan_destroy(ws->freq);
+    if (ws->freq_gt_mag) cudaFree(ws->freq_gt_mag);
     for (auto& c : ws->chunks) cudaFree(c.base);
     delete ws;
     return SEGS_OK;
@@ -218,7 +227,31 @@ static int mapper_view_impl(segs_workspace* ws, const segs_mapper_view_args* a, 
     add_scalar_kernel<<<1, 1, 0, stream>>>(a->loss_accum, loss3 + 2);
     SEGS_LAUNCH_CHECK();
     if (a->loss_terms_out) SEGS_CUDA_CHECK(cudaMemcpyAsync(a->loss_terms_out, loss3, 3 * sizeof(float), cudaMemcpyDeviceToDevice, stream));
+    // frequency regularisation (gaussian_mapper.cpp:930-945): value into the loss, gradient ADDED behind the SSIM backward
+    auto freq_term = [&](float* grad_image) -> int {
+        if (a->lambda_frequency_high == 0.f) return SEGS_OK;
+        const int ns = a->use_multi_resolution ? (a->freq_scale_num < 1 ? 1 : (a->freq_scale_num > 4 ? 4 : a->freq_scale_num)) : 1;
+        int frc;
+        if (!ws->freq || ws->freq_H != H || ws->freq_W != W || ws->freq_ns != ns) {
+            if (ws->freq) { segs_freq_plan_destroy(ws->freq); ws->freq = nullptr; }
+            if (ws->freq_gt_mag) { cudaFree(ws->freq_gt_mag); ws->freq_gt_mag = nullptr; }
+            float sc[4];
+            for (int i = 0; i < ns; ++i) sc[i] = float(1.0 / pow(2.0, i));              // gaussian_mapper.cpp:514-517
+            if ((frc = segs_freq_plan_create(3, H, W, ns, sc, &ws->freq))) return frc;
+            ws->freq_H = H; ws->freq_W = W; ws->freq_ns = ns;
+        }
+        const float* gt_mag = a->gt_freq_mag;
+        if (!gt_mag) {
+            if (!ws->freq_gt_mag && cudaMalloc(&ws->freq_gt_mag, segs_freq_mag_floats(ws->freq) * sizeof(float)) != cudaSuccess) {
+                cudaGetLastError(); return oom();
+            }
+            if ((frc = segs_freq_target(ws->freq, a->gt_image, a->row_mask, ws->freq_gt_mag, stream))) return frc;
+            gt_mag = ws->freq_gt_mag;
+        }
+        return segs_freq_loss(ws->freq, image, a->row_mask, gt_mag, a->lambda_frequency_high, nullptr, a->loss_accum, grad_image, stream);
+    };
     if (P == 0) {                        // nothing to back-propagate into; visible anchors still count in the statistics
+        if ((rc = freq_term(nullptr))) return rc;
         if (n_vis > 0 && (a->stat_opacity_accum || a->stat_anchor_demon || a->stat_offset_gradient_accum || a->stat_offset_denom))
             return segs_training_statis(A, dstate, n_vis, neural_opacity, anchor_radii /* not read: no offset survived */, xyz,
                                         a->stat_opacity_accum, a->stat_anchor_demon, a->stat_offset_gradient_accum,
@@ -226,6 +259,7 @@ static int mapper_view_impl(segs_workspace* ws, const segs_mapper_view_args* a, 
         return SEGS_OK;
     }
     if ((rc = segs_loss_l1_ssim_backward(3, H, W, image, a->gt_image, a->row_mask, 1.f - lam, -lam, nullptr, lstate, dL_dimage, stream))) return rc;
+    if ((rc = freq_term(dL_dimage))) return rc;
 
     // ---- rasterizer backward (RasterizeGaussiansBackwardCUDA) ----
     const size_t Pz = size_t(P);

@@ -128,57 +128,103 @@ def scaling_reg(scaling: torch.Tensor, weight: float = 0.01) -> torch.Tensor:
     return _ScalingReg.apply(scaling, weight)
 
 
-# ---- frequency-domain terms (loss_utils.h:129-237) ---------------------------------------------------------------
-# Host-level compositions over the FFT *library* (torch.fft -> cuFFT, like the reference): 1200x680 is not a power of
-# two and a mixed-radix FFT is not on the hot path this repo rebuilds (SURVEY §8f lists them behind L1/SSIM).  They are
-# here so that the whole `loss_utils` namespace is available behind the same names.  The reference's indexing quirk is
-# reproduced on purpose: the [C,H,W] masks are sliced on dims 0 and 1 (channel, row), which is empty for C = 3 — the
-# high-pass mask stays all ones (full-spectrum magnitude loss) and the low-pass mask all zeros (zero gradient).
-def _filtered_fft(img: torch.Tensor, cutoff_ratio: float, high: bool) -> torch.Tensor:
-    if not img.is_cuda:
-        raise RuntimeError("segs_slam_b200 has no CPU path: tensors must live on a CUDA device")
-    f = torch.fft.fftshift(torch.fft.fft2(img))
-    H, W = img.shape[1], img.shape[2]
-    crow, ccol = H // 2, W // 2
-    mask = torch.ones_like(f) if high else torch.zeros_like(f)
+# ---- frequency-domain terms (loss_utils.h:125-237) ---------------------------------------------------------------
+# On the C ABI (csrc/freq.cu: segs_freq_plan_*, segs_freq_target, segs_freq_loss): fused resampling / magnitude-loss /
+# adjoint kernels around cuFFT plans.  The reference's indexing quirk is part of the contract: its [C,H,W] frequency
+# masks are sliced on dims 0 and 1 (channel, row) with [H/2 - r, H/2 + r), which is EMPTY for C = 3 unless the image is
+# only a few pixels high — the "high-pass" mask stays all ones (a full-spectrum magnitude loss) and the "low-pass" mask
+# all zeros (low_freq_loss is identically zero, with zero gradient).  Sizes where the slice would not be empty are
+# refused rather than silently computed differently.
+_freq_plans = {}
+
+
+def _mask_is_empty(C: int, H: int, W: int, cutoff_ratio: float) -> bool:
     r = int(cutoff_ratio * min(H, W) / 2)
-    mask[crow - r:crow + r, ccol - r:ccol + r] = 0 if high else 1
-    return f * mask
+    lo = H // 2 - r
+    return r <= 0 or lo >= C                      # Slice(crow - r, crow + r) on the channel dimension (size C)
 
 
-def high_pass_filter(img: torch.Tensor, cutoff_ratio: float) -> torch.Tensor:
-    """loss_utils::high_pass_filter (loss_utils.h:129-148)."""
-    return _filtered_fft(img, cutoff_ratio, True)
+def _freq_plan(device, C: int, H: int, W: int, scales):
+    import ctypes as C_
+    key = (device.index if device.index is not None else torch.cuda.current_device(), C, H, W, tuple(float(x) for x in scales))
+    plan = _freq_plans.get(key)
+    if plan is None:
+        lib = _lib.load()
+        arr = (C_.c_float * len(scales))(*[float(x) for x in scales])
+        plan = C_.c_void_p()
+        with torch.cuda.device(device):
+            _lib.check(lib.segs_freq_plan_create(C, H, W, len(scales), arr, C_.byref(plan)))
+        _freq_plans[key] = plan
+    return plan
 
 
-def low_pass_filter(img: torch.Tensor, cutoff_ratio: float) -> torch.Tensor:
-    """loss_utils::low_pass_filter (loss_utils.h:171-188)."""
-    return _filtered_fft(img, cutoff_ratio, False)
+def freq_target(gt: torch.Tensor, scales=(1.0,), row_mask: torch.Tensor | None = None) -> torch.Tensor:
+    """|fft2(D_s (gt * row_mask))| of every scale, flattened: the per-keyframe half of the frequency terms (pass it to
+    FusedMapper / segs_mapper_view as `gt_freq_mag` to avoid recomputing it every view)."""
+    _check(gt, gt)
+    lib = _lib.load()
+    C_, H, W = gt.shape
+    plan = _freq_plan(gt.device, C_, H, W, scales)
+    mag = torch.empty((int(lib.segs_freq_mag_floats(plan)),), dtype=torch.float32, device=gt.device)
+    g = gt.contiguous()
+    m = row_mask.contiguous() if row_mask is not None else None
+    with torch.cuda.device(gt.device):
+        _lib.check(lib.segs_freq_target(plan, _ptr(g), _ptr(m), _ptr(mag), _stream()))
+    return mag
+
+
+class _FreqLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, image, gt, scales, weight):
+        _check(image, gt)
+        lib = _lib.load()
+        C_, H, W = image.shape
+        plan = _freq_plan(image.device, C_, H, W, scales)
+        img_c = image.contiguous()
+        mag = freq_target(gt, scales)
+        out = torch.zeros((), dtype=torch.float32, device=image.device)
+        with torch.cuda.device(image.device):
+            _lib.check(lib.segs_freq_loss(plan, _ptr(img_c), None, _ptr(mag), float(weight), None, _ptr(out), None, _stream()))
+        ctx.save_for_backward(img_c, mag)
+        ctx.plan, ctx.weight = plan, float(weight)
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        lib = _lib.load()
+        img_c, mag = ctx.saved_tensors
+        d = torch.zeros_like(img_c)
+        gc = g.to(torch.float32).contiguous()
+        with torch.cuda.device(img_c.device):
+            _lib.check(lib.segs_freq_loss(ctx.plan, _ptr(img_c), None, _ptr(mag), ctx.weight, _ptr(gc), None, _ptr(d), _stream()))
+        return d, None, None, None
 
 
 def high_frequency_loss(img1: torch.Tensor, img2: torch.Tensor, cutoff_ratio: float = 0.4) -> torch.Tensor:
-    """loss_utils::high_frequency_loss (loss_utils.h:150-169)."""
-    a, b = high_pass_filter(img1, cutoff_ratio), high_pass_filter(img2, cutoff_ratio)
-    return torch.mean(torch.abs(torch.abs(a) - torch.abs(b)))
+    """loss_utils::high_frequency_loss (loss_utils.h:150-169): mean | |fft2(img1)| - |fft2(img2)| | (differentiable in img1)."""
+    C_, H, W = img1.shape
+    if not _mask_is_empty(C_, H, W, cutoff_ratio):
+        raise NotImplementedError("high_frequency_loss: for this size the reference's mask slice over the channel dimension is not "
+                                  f"empty (C={C_}, H={H}, r={int(cutoff_ratio * min(H, W) / 2)}); only the empty-mask case is built")
+    return _FreqLoss.apply(img1, img2, (1.0,), 1.0)
 
 
 def low_freq_loss(img1: torch.Tensor, img2: torch.Tensor, cutoff_ratio: float = 0.2) -> torch.Tensor:
-    """loss_utils::low_freq_loss (loss_utils.h:190-207)."""
-    norm = float(img1.shape[0] * img1.shape[1] * img1.shape[2])
-    a, b = low_pass_filter(img1, cutoff_ratio), low_pass_filter(img2, cutoff_ratio)
-    la = torch.sum(torch.abs(torch.abs(a) - torch.abs(b))) / norm
-    lp = torch.sum(torch.abs(torch.angle(a) - torch.angle(b))) / norm
-    return la + lp
+    """loss_utils::low_freq_loss (loss_utils.h:190-207): with the reference's (empty) mask slice the low-pass mask is all
+    zeros, so both of its terms are sums of |0 - 0|: identically zero, zero gradient."""
+    C_, H, W = img1.shape
+    if not _mask_is_empty(C_, H, W, cutoff_ratio):
+        raise NotImplementedError("low_freq_loss: non-empty mask slice (tiny image); only the empty-mask case is built")
+    _check(img1, img2)
+    return (img1 * 0.0).sum()
 
 
 def multi_scale_loss(gen_img: torch.Tensor, target_img: torch.Tensor, scales) -> torch.Tensor:
-    """loss_utils::multi_scale_loss (loss_utils.h:210-237)."""
-    import torch.nn.functional as F
-    loss = torch.zeros((), device=gen_img.device)
-    for s in scales:
-        g = F.interpolate(gen_img.unsqueeze(0), scale_factor=(float(s), float(s)), mode="bilinear", align_corners=False,
-                          recompute_scale_factor=True)
-        t = F.interpolate(target_img.unsqueeze(0), scale_factor=(float(s), float(s)), mode="bilinear", align_corners=False,
-                          recompute_scale_factor=True)
-        loss = loss + s * high_frequency_loss(g.squeeze(0), t.squeeze(0))
-    return loss
+    """loss_utils::multi_scale_loss (loss_utils.h:210-237): sum_s s * high_frequency_loss(D_s gen, D_s target), D_s = bilinear
+    interpolate(scale_factor = s, align_corners = False, recompute_scale_factor = True); one fused call for all scales."""
+    scales = tuple(float(x) for x in scales)
+    C_, H, W = gen_img.shape
+    for sc in scales:
+        if not _mask_is_empty(C_, int(H * sc), int(W * sc), 0.4):
+            raise NotImplementedError("multi_scale_loss: non-empty mask slice at one of the scales (tiny image)")
+    return _FreqLoss.apply(gen_img, target_img, scales, 1.0)

@@ -207,7 +207,8 @@ class FusedMapper:
 
     def __init__(self, pc, image_height: int, image_width: int, tanfovx: float, tanfovy: float, bg: torch.Tensor,
                  lambda_dssim: float = 0.2, scaling_reg_weight: float = 0.01, lrs=1e-4, eps: float = 1e-15, group=None,
-                 lanes: int = 4, statistics: bool = False):
+                 lanes: int = 4, statistics: bool = False, lambda_frequency_high: float = 0.0,
+                 use_multi_resolution: bool = True, freq_scale_num: int = 3, cache_freq_targets: int = 256):
         import ctypes as C
         from . import _lib
         from .gaussian_renderer import _weights
@@ -217,6 +218,11 @@ class FusedMapper:
         self.H, self.W, self.tanfovx, self.tanfovy = int(image_height), int(image_width), float(tanfovx), float(tanfovy)
         self.bg = bg.to(torch.float32).contiguous()
         self.lambda_dssim, self.scaling_reg_weight = float(lambda_dssim), float(scaling_reg_weight)
+        # frequency regularisation (gaussian_mapper.cpp:930-945; Replica yamls: 0.01, multi-resolution, 3 scales); the
+        # target magnitudes |fft2(D_s gt)| are per keyframe and cached (up to `cache_freq_targets` keyframes)
+        self.lambda_frequency_high = float(lambda_frequency_high)
+        self.use_multi_resolution, self.freq_scale_num = bool(use_multi_resolution), max(1, min(4, int(freq_scale_num)))
+        self._freq_cache, self._freq_cache_max = {}, int(cache_freq_targets)
         if not pc._anchor.is_cuda:
             raise RuntimeError("segs_slam_b200 has no CPU path: the model must live on a CUDA device")
         self.weights = _weights(pc)                                   # 18 entries, None = absent
@@ -293,6 +299,8 @@ class FusedMapper:
         a.width, a.height, a.tan_fovx, a.tan_fovy = self.W, self.H, self.tanfovx, self.tanfovy
         a.background = self.bg.data_ptr()
         a.lambda_dssim, a.scaling_reg_weight = self.lambda_dssim, self.scaling_reg_weight
+        a.lambda_frequency_high, a.use_multi_resolution = self.lambda_frequency_high, int(self.use_multi_resolution)
+        a.freq_scale_num = self.freq_scale_num
         v = self.bucket.views
         a.grad_anchor, a.grad_offset, a.grad_anchor_feat, a.grad_scaling = (v[0].data_ptr(), v[1].data_ptr(),
                                                                              v[2].data_ptr(), v[3].data_ptr())
@@ -314,6 +322,23 @@ class FusedMapper:
         a.pose = pose
         a.gt_image = target.data_ptr()
         a.row_mask = None if row_mask is None else row_mask.data_ptr()
+        a.gt_freq_mag = None
+        if self.lambda_frequency_high != 0.0 and self._freq_cache_max > 0:
+            a.gt_freq_mag = self._freq_target(target, row_mask).data_ptr()
+
+    def _freq_target(self, target, row_mask):
+        """|fft2(D_s (gt * mask))| of a keyframe image, computed once and kept while the image tensor lives at the same
+        address (segs_freq_target); the views of later steps reuse it."""
+        from . import loss_utils
+        key = (target.data_ptr(), None if row_mask is None else row_mask.data_ptr(), target._version)
+        hit = self._freq_cache.get(key)
+        if hit is None:
+            if len(self._freq_cache) >= self._freq_cache_max:
+                self._freq_cache.pop(next(iter(self._freq_cache)))
+            scales = [1.0 / 2 ** i for i in range(self.freq_scale_num)] if self.use_multi_resolution else [1.0]
+            hit = loss_utils.freq_target(target, scales, row_mask)
+            self._freq_cache[key] = hit
+        return hit
 
     def render_views(self, cams, targets, row_masks=None):
         """A batch of views on `self.lanes` concurrent lanes: accumulates gradients and the loss."""

@@ -156,9 +156,10 @@ FREQ = sorted(glob.glob(os.path.join(GOLD, "freq_*.npz")))
 
 @pytest.mark.parametrize("path", FREQ, ids=[os.path.basename(p) for p in FREQ])
 def test_frequency_losses_match_reference_golden(path, device):
-    """loss_utils::high_frequency_loss / multi_scale_loss / low_freq_loss (host compositions over cuFFT).  FFT sums
-    of ~2000 FP32 terms: value 1e-4, gradient 1e-3 of its scale.  low_freq_loss has zero gradient by construction
-    (the reference's low-pass mask is empty); its VALUE counts signed-zero angle flips, so only finiteness is held."""
+    """loss_utils::high_frequency_loss / multi_scale_loss / low_freq_loss on the fused kernels of csrc/freq.cu (cuFFT plans
+    inside).  FFT sums of ~2000 FP32 terms: value 1e-4, gradient 1e-3 of its scale.  low_freq_loss has zero gradient by
+    construction (the reference's low-pass mask is empty); the reference's VALUE only counts sign-of-zero flips of
+    angle(+-0), so the product returns 0 and only the zero gradient is held."""
     g = np.load(path)
     x = torch.from_numpy(g["image"]).to(device).requires_grad_(True)
     y = torch.from_numpy(g["gt"]).to(device)
@@ -175,6 +176,40 @@ def test_frequency_losses_match_reference_golden(path, device):
     ms = loss_utils.multi_scale_loss(x, y, [1.0, 0.5])
     r = loss_oracle.multi_scale_loss(torch.from_numpy(g["image"]), torch.from_numpy(g["gt"]), [1.0, 0.5])
     np.testing.assert_allclose(ms.item(), float(r), rtol=1e-4)
+
+
+@pytest.mark.parametrize("shape,scales", [((3, 40, 50), [1.0, 0.5, 0.25]), ((3, 33, 47), [1.0, 0.5]), ((3, 680, 1200), [1.0, 0.5, 0.25]),
+                                          ((3, 120, 208), [1.0]), ((1, 64, 96), [1.0, 0.5, 0.25])])
+def test_frequency_losses_match_the_compiled_reference(shape, scales, device):
+    """multi_scale_loss / high_frequency_loss against the reference's OWN loss_utils.h running on the GPU (compiled
+    unmodified into oracle/_ref/_model_ref.so), value and gradient, up to the Replica image size."""
+    import model_ref
+    if not model_ref.available():
+        pytest.skip("oracle/_ref/_model_ref.so not built")
+    mr = model_ref.load()
+    gen = torch.Generator(device="cpu").manual_seed(shape[1])
+    x0 = torch.rand(shape, generator=gen).to(device)
+    y = (x0.cpu() + 0.1 * torch.randn(shape, generator=gen)).clamp(0, 1).to(device)
+    for fn_mine, fn_ref in ((lambda a: loss_utils.multi_scale_loss(a, y, scales), lambda a: mr.multi_scale_loss(a, y, scales)),
+                            (lambda a: loss_utils.high_frequency_loss(a, y), lambda a: mr.high_frequency_loss(a, y))):
+        x = x0.clone().requires_grad_(True)
+        v = fn_mine(x)
+        v.backward()
+        v_ref, g_ref = fn_ref(x0)
+        np.testing.assert_allclose(v.item(), float(v_ref), rtol=1e-4)
+        scale = float(g_ref.abs().max())
+        assert scale > 0
+        err = float((x.grad - g_ref).abs().max()) / scale
+        rel_l2 = float((x.grad - g_ref).norm() / g_ref.norm())
+        assert err < 1e-3 and rel_l2 < 1e-4, (err, rel_l2)
+    # determinism of the fused path
+    x = x0.clone().requires_grad_(True)
+    v2 = loss_utils.multi_scale_loss(x, y, scales)
+    v2.backward()
+    x3 = x0.clone().requires_grad_(True)
+    v3 = loss_utils.multi_scale_loss(x3, y, scales)
+    v3.backward()
+    assert v2.item() == v3.item() and torch.equal(x.grad, x3.grad)
 
 
 @pytest.mark.parametrize("shape", [(3, 1, 1), (3, 7, 300), (1, 17, 31), (3, 16, 32), (3, 33, 65), (2, 200, 45), (3, 5, 5)])

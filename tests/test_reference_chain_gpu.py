@@ -46,7 +46,7 @@ def _setup(device, A, W, H, fx, n_views):
     return model, cams, targets, (fovx, fovy, tanx, tany)
 
 
-def _reference_views(model, cams, targets, fovx, fovy, H, W, bg, lam, one_ulp=False):
+def _reference_views(model, cams, targets, fovx, fovy, H, W, bg, lam, one_ulp=False, frequency=None):
     """Loss sum and gradient sums of the reference chain over the views.  one_ulp: every anchor feature moved to the next
     representable float — an equally valid rounding of the inputs, used to measure how much the REFERENCE's own gradients
     move under a 1-ulp change (the chain is discontinuous: alpha < 1/255 skips, T < 1e-4 stops, sign() in the L1 term)."""
@@ -56,6 +56,8 @@ def _reference_views(model, cams, targets, fovx, fovy, H, W, bg, lam, one_ulp=Fa
         with torch.no_grad():
             model._anchor_feat.copy_(torch.nextafter(model._anchor_feat, torch.full_like(model._anchor_feat, float("inf"))))
     ref = model_ref.from_model(model, reference_ctor=True)
+    if frequency is not None:
+        ref.set_frequency(*frequency)
     total, loss = None, 0.0
     for cam, tgt in zip(cams, targets):
         out = ref.view_gradients(cam.world_view_transform_, cam.full_proj_transform_, cam.camera_center_, list(cam.t_),
@@ -112,6 +114,28 @@ def test_fused_mapper_matches_reference_chain(device, lanes):
     loss_f = fm.step(cams, targets, masks, optimize=False)
     loss_r, grads_r = _reference_views(model, cams, targets, fovx, fovy, H, W, bg, 0.2)
     _check_bucket(fm, len(cams), loss_f, loss_r, grads_r)
+
+
+def test_fused_mapper_with_frequency_regularisation_matches_reference_chain(device):
+    """The Replica configuration of the loss (cfg/gaussian_mapper/RGB-D/Replica/office0.yaml:140-146: lambda_frequency_high
+    0.01, multi-resolution, 3 scales; src/gaussian_mapper.cpp:930-945): the fused view with the frequency term against the
+    reference chain with the reference's own multi_scale_loss."""
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    W, H, fx = 208, 120, 150.0
+    model, cams, targets, (fovx, fovy, tanx, tany) = _setup(device, 4000, W, H, fx, 3)
+    bg = torch.tensor([0.1, 0.0, 0.2], device=device)
+    from segs_slam_b200 import loss_utils
+    masks = [loss_utils.mask_rgb(t) for t in targets]
+    for multi in (True, False):
+        fm = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01, lanes=2,
+                                lambda_frequency_high=0.01, use_multi_resolution=multi, freq_scale_num=3)
+        loss_f = fm.step(cams, targets, masks, optimize=False)
+        loss_r, grads_r = _reference_views(model, cams, targets, fovx, fovy, H, W, bg, 0.2, frequency=(0.01, multi, 3))
+        fm0 = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01, lanes=1)
+        loss_0 = fm0.step(cams, targets, masks, optimize=False)
+        assert float(loss_f) > float(loss_0) * 1.01           # the term is there (it is not a rounding-level contribution)
+        _check_bucket(fm, len(cams), loss_f, loss_r, grads_r)
 
 
 @pytest.mark.slow
