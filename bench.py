@@ -724,7 +724,30 @@ def mapping_ours(args, dev, rank, n_ranks, distributed):
     if distributed:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms = float(t.item())
-    return {"metric": "mapping keyframes/s", "value": round(MAP_VIEWS * steps / (ms * 1e-3), 2),
+    # the Replica configuration of the loss: + 0.01 * multi_scale_loss over 3 scales (office0.yaml:140-146)
+    fq = mapper.FusedMapper(model, H, W, tanx, tany, torch.zeros(3, device=dev), lambda_dssim=0.2, lrs=1e-4, lanes=args.lanes,
+                            lambda_frequency_high=0.01, use_multi_resolution=True, freq_scale_num=3)
+    for _ in range(2):
+        fq.step(cams, targets)
+    barrier()
+    fsteps = max(2, steps // 4)
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tf = time.perf_counter()
+    f0.record()
+    for _ in range(fsteps):
+        fq.step(cams, targets)
+    f1.record()
+    barrier()
+    fms = max(f0.elapsed_time(f1), (time.perf_counter() - tf) * 1e3)
+    tfm = torch.tensor([fms], dtype=torch.float64, device=dev)
+    if distributed:
+        dist.all_reduce(tfm, op=dist.ReduceOp.MAX)
+    fms = float(tfm.item())
+    with_frequency = {"value": round(MAP_VIEWS * fsteps / (fms * 1e-3), 2), "unit": "keyframes/s", "steps": fsteps,
+                      "ms_per_step": round(fms / fsteps, 3),
+                      "what": "use_frequency_regularization: 1 — loss + 0.01 * multi_scale_loss(scales 1, 1/2, 1/4) fused into the view "
+                              "(csrc/freq.cu), target spectra cached per keyframe"}
+    return {"metric": "mapping keyframes/s", "value": round(MAP_VIEWS * steps / (ms * 1e-3), 2), "with_frequency": with_frequency,
             "unit": "keyframes/s", "n_gpus": n_ranks, "views_per_step": MAP_VIEWS, "steps": steps,
             "ms_per_step": round(ms / steps, 3), "ms_per_step_rank0": _stats(per_step), "scaling": "strong",
             "config": {"workload": "C4: 64 keyframes 1200x680, C3 anchor model (200k anchors x 10 offsets, appearance "
@@ -801,6 +824,21 @@ def mapping_reference(args, dev):
     ms = (time.perf_counter() - t0) * 1e3
     out.update({"value": round(n / (ms * 1e-3), 2), "views_per_step": 1, "steps": n, "ms_per_step": round(ms / n, 3),
                 "losses": [round(float(x), 5) for x in losses[:4]]})
+    del m
+    # (A') the same with the Replica configuration of the loss (use_frequency_regularization: 1, office0.yaml:140-146)
+    m = fresh()
+    m.set_frequency(0.01, True, 3)
+    for v in range(5):
+        m.train_iteration(*args_of(v), False, False, True, True)
+    torch.cuda.synchronize()
+    nf = MAP_VIEWS
+    t0 = time.perf_counter()
+    for v in range(nf):
+        m.train_iteration(*args_of(v), False, False, True, True)
+    torch.cuda.synchronize()
+    msf = (time.perf_counter() - t0) * 1e3
+    out["with_frequency"] = {"value": round(nf / (msf * 1e-3), 2), "unit": "keyframes/s", "steps": nf, "ms_per_step": round(msf / nf, 3),
+                             "what": "use_frequency_regularization: 1 — the reference's own multi_scale_loss (3 scales, lambda 0.01)"}
     del m
     # (B) 64 reference views with gradient accumulation + ONE Adam step (the 1-GPU equivalent of the batched step)
     m = fresh()
