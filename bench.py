@@ -228,10 +228,14 @@ def main():
     dL = base["dL_dout"]
     arm = Arm(args.impl, scene0, base, dev)
     lib = arm.lib
-    if ours:
-        # more waiting host threads (ranks x lanes) than cores: sleep in the read-back waits instead of spinning
-        blocking = args.blocking_sync if args.blocking_sync >= 0 else int(world * args.lanes * 2 > (os.cpu_count() or 1))
+    def set_wait_mode(threads_per_rank):
+        """Read-back waits spin unless there are more waiting host threads on the box than cores (then they sleep)."""
+        if not ours:
+            return
+        blocking = args.blocking_sync if args.blocking_sync >= 0 else int(world * threads_per_rank > (os.cpu_count() or 1))
         lib.segs_set_blocking_sync(blocking)
+
+    set_wait_mode(1)                    # M1: one host thread per rank
 
     # flat gradient bucket = what the mapper all-reduces (segs_slam_b200/mapper.py: one contiguous FP32
     # slice per tensor: means3D 3, means2D 3, colors 3, opacity 1, scales 3, rotations 4 floats per Gaussian)
@@ -319,6 +323,7 @@ def main():
     batch = None
     LANES = args.lanes
     if ours:
+        set_wait_mode(LANES + 1)        # lane threads + the NCCL / interpreter threads of the rank
         rb = mapper.RasterBatch(dev, lanes=LANES)
         step_images = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in cams]
         dLs_same = [dL] * len(cams)
@@ -349,12 +354,14 @@ def main():
     # hold the same bucket).  Copies ride on two copy streams (H2D / D2H), double-buffered against the compute
     # stream, and are drained inside the timed region.  Identical harness for both arms.
     e2e = e2e_b = None
+    set_wait_mode(1)
     if not args.no_e2e:
         e2e, e2e_b = e2e_measure(args, arm, gb, shapes, base, dL, cams, dev, P, W, H, NV, accumulate, barrier, use_dist,
-                                 rank, n_ranks, (rb, run_batch) if ours else None)
+                                 rank, n_ranks, (rb, run_batch) if ours else None, set_wait_mode)
     clocks = sampler.stop() if rank == 0 else None
 
     mapping = None
+    set_wait_mode(LANES + 1)
     if not args.no_mapping:
         mapping = mapping_ours(args, dev, rank, n_ranks, use_dist) if ours else mapping_reference(args, dev)
     configs = None
@@ -460,7 +467,8 @@ def main():
 
 
 # ---------------------------------------------------------------------------------------------
-def e2e_measure(args, arm, gb, shapes, base, dL, cams, dev, P, W, H, NV, accumulate, barrier, use_dist, rank, n_ranks, batch_api):
+def e2e_measure(args, arm, gb, shapes, base, dL, cams, dev, P, W, H, NV, accumulate, barrier, use_dist, rank, n_ranks, batch_api,
+                set_wait_mode):
     import torch
     import torch.distributed as dist
     from segs_slam_b200 import mapper
@@ -588,6 +596,7 @@ def e2e_measure(args, arm, gb, shapes, base, dL, cams, dev, P, W, H, NV, accumul
     e2e_b = None
     if batch_api is not None:
         rb, run_batch = batch_api
+        set_wait_mode(rb.lanes + 1)
         nv = len(cams)
         dev_dLs = [[torch.empty_like(dL) for _ in range(nv)] for _ in range(2)]
         dev_imgs = [[torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(nv)] for _ in range(2)]
