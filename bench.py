@@ -323,7 +323,7 @@ def main():
     batch = None
     LANES = args.lanes
     if ours:
-        set_wait_mode(LANES + 1)        # lane threads + the NCCL / interpreter threads of the rank
+        set_wait_mode(LANES)            # lane 0 is the calling thread; measured at 8 ranks x 4 lanes on 32 cores: spinning 6012, sleeping 5769 keyframes/s
         rb = mapper.RasterBatch(dev, lanes=LANES)
         step_images = [torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in cams]
         dLs_same = [dL] * len(cams)
@@ -361,7 +361,7 @@ def main():
     clocks = sampler.stop() if rank == 0 else None
 
     mapping = None
-    set_wait_mode(LANES + 1)
+    set_wait_mode(LANES)
     if not args.no_mapping:
         mapping = mapping_ours(args, dev, rank, n_ranks, use_dist) if ours else mapping_reference(args, dev)
     configs = None
@@ -596,7 +596,7 @@ def e2e_measure(args, arm, gb, shapes, base, dL, cams, dev, P, W, H, NV, accumul
     e2e_b = None
     if batch_api is not None:
         rb, run_batch = batch_api
-        set_wait_mode(rb.lanes + 1)
+        set_wait_mode(rb.lanes)
         nv = len(cams)
         dev_dLs = [[torch.empty_like(dL) for _ in range(nv)] for _ in range(2)]
         dev_imgs = [[torch.empty((3, H, W), dtype=torch.float32, device=dev) for _ in range(nv)] for _ in range(2)]
