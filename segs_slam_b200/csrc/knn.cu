@@ -9,10 +9,14 @@
 //    caller's allocation callback), everything on the caller's stream;
 //  * points are gathered ONCE into Morton order as float4 (xyz + original index), so the
 //    search streams contiguous 16-byte records instead of chasing points[indices[i]];
-//  * one CTA per query box: candidate boxes are staged into shared memory with coalesced
-//    loads and scanned with broadcast reads by all of the CTA's queries; a CTA-level
-//    box-vs-box bound skips whole boxes before the per-query box-vs-point bound
-//    (simple_knn.cu:121-132) is even evaluated.
+//  * the search is a 2-D grid: CTA = (256 consecutive queries, one share of the candidate boxes), so
+//    that 1e3 - 1e5 points (what SLAM hands over per call) still fill 148 SMs — one CTA per
+//    1024-point box (round 1) left 2 - 98 CTAs on the machine.  Candidate boxes are staged into
+//    shared memory with coalesced loads and scanned with broadcast reads by all of the CTA's
+//    queries; a CTA-level box-vs-box bound (against the AABB of the CTA's own 256 queries) skips
+//    whole boxes before the per-query box-vs-point bound (simple_knn.cu:121-132) is even evaluated;
+//    every share scans the query's own box first to get a tight bound (only share 0 keeps those
+//    results), and a merge kernel takes the three smallest of the shares' candidates.
 // The result is the exact 3-NN, and each squared distance is evaluated with the same
 // operations as the reference (d = other - query; fma(dz,dz, fma(dx,dx, dy*dy))), so the
 // output is bit-identical whenever the reference's own pruning is exact.
@@ -159,86 +163,84 @@ __device__ __forceinline__ void update3(float3 q, float x, float y, float z, flo
         if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
 }
 
-constexpr int QPT = BOX / KNN_THREADS;   // queries per thread
+constexpr int QG = KNN_THREADS;      // queries per CTA (one per thread)
+constexpr int MAX_SHARES = 16;
 
 __global__ void __launch_bounds__(KNN_THREADS)
-knn_search_kernel(int P, const float4* __restrict__ sorted, const Box* __restrict__ boxes, int nboxes,
-                  float* __restrict__ mean_dists)
+knn_search_kernel(int P, const float4* __restrict__ sorted, const Box* __restrict__ boxes, int nboxes, int shares,
+                  float* __restrict__ partial /*[shares][P][3], by Morton position*/)
 {
     __shared__ float4 s_pts[BOX];
-    __shared__ float s_red[KNN_THREADS / 32];
-    __shared__ float s_bound;
-    const int qb = blockIdx.x;
+    __shared__ float s_red[KNN_THREADS / 32][7];
+    __shared__ float s_bound[7];
+    const int share = blockIdx.y;
+    const size_t g0 = size_t(blockIdx.x) * QG;                 // first query (Morton position) of this CTA
+    const int qb = (int)(g0 / BOX);                            // the box these queries live in
     const size_t q0 = size_t(qb) * BOX;
     const int nq = (int)min(size_t(BOX), size_t(P) - q0);
-
-    float3 q[QPT];
-    float best[QPT][3];
-    float reject[QPT];
-    uint32_t qid[QPT];
-    bool valid[QPT];
+    const size_t gi = g0 + threadIdx.x;
+    const bool valid = gi < (size_t)P;
+    const int li = (int)(gi - q0);
 
     // own box -> smem (also the first box to scan)
     for (int i = threadIdx.x; i < BOX; i += KNN_THREADS)
         if (i < nq) s_pts[i] = __ldg(sorted + q0 + i);
     __syncthreads();
 
-#pragma unroll
-    for (int r = 0; r < QPT; ++r) {
-        const int li = r * KNN_THREADS + threadIdx.x;
-        valid[r] = li < nq;
-        best[r][0] = best[r][1] = best[r][2] = FLT_MAX;
-        reject[r] = FLT_MAX;
-        qid[r] = 0;
-        q[r] = make_float3(0.f, 0.f, 0.f);
-        if (valid[r]) {
-            const float4 me = s_pts[li];
-            q[r] = make_float3(me.x, me.y, me.z);
-            qid[r] = __float_as_uint(me.w);
-            // seed from the +-3 Morton neighbours (simple_knn.cu:157-163); they may live in
-            // the adjacent boxes
-            const long long gi = (long long)q0 + li;
-            for (long long i = max(0LL, gi - 3); i <= min((long long)P - 1, gi + 3); ++i) {
-                if (i == gi) continue;
-                const float4 o = (i >= (long long)q0 && i < (long long)q0 + nq) ? s_pts[i - q0] : __ldg(sorted + i);
-                update3(q[r], o.x, o.y, o.z, best[r]);
-            }
-            reject[r] = best[r][2];
-            best[r][0] = best[r][1] = best[r][2] = FLT_MAX;
+    float3 q = make_float3(0.f, 0.f, 0.f);
+    float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    float reject = FLT_MAX;
+    if (valid) {
+        const float4 me = s_pts[li];
+        q = make_float3(me.x, me.y, me.z);
+        // seed from the +-3 Morton neighbours (simple_knn.cu:157-163); they may live in the adjacent boxes
+        for (long long i = max(0LL, (long long)gi - 3); i <= min((long long)P - 1, (long long)gi + 3); ++i) {
+            if (i == (long long)gi) continue;
+            const float4 o = (i >= (long long)q0 && i < (long long)q0 + nq) ? s_pts[i - q0] : __ldg(sorted + i);
+            update3(q, o.x, o.y, o.z, best);
         }
-    }
-
-    // scan own box
-#pragma unroll
-    for (int r = 0; r < QPT; ++r) {
-        if (!valid[r]) continue;
-        const int li = r * KNN_THREADS + threadIdx.x;
+        reject = best[2];
+        best[0] = best[1] = best[2] = FLT_MAX;
+        // scan own box
         for (int i = 0; i < nq; ++i) {
             if (i == li) continue;
             const float4 o = s_pts[i];
-            update3(q[r], o.x, o.y, o.z, best[r]);
+            update3(q, o.x, o.y, o.z, best);
         }
     }
 
-    // CTA-wide bound: no query of this box needs anything farther than this
-    float bound = 0.f;
+    // CTA-wide: the AABB of these 256 queries and the largest distance any of them still needs
+    float r7[7] = {valid ? fminf(reject, best[2]) : 0.f, valid ? q.x : FLT_MAX, valid ? q.y : FLT_MAX, valid ? q.z : FLT_MAX,
+                   valid ? q.x : -FLT_MAX, valid ? q.y : -FLT_MAX, valid ? q.z : -FLT_MAX};
 #pragma unroll
-    for (int r = 0; r < QPT; ++r)
-        if (valid[r]) bound = fmaxf(bound, fminf(reject[r], best[r][2]));
+    for (int o = 16; o > 0; o >>= 1) {
+        r7[0] = fmaxf(r7[0], __shfl_xor_sync(FULL, r7[0], o));
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) bound = fmaxf(bound, __shfl_xor_sync(FULL, bound, o));
-    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = bound;
+        for (int k = 1; k < 4; ++k) r7[k] = fminf(r7[k], __shfl_xor_sync(FULL, r7[k], o));
+#pragma unroll
+        for (int k = 4; k < 7; ++k) r7[k] = fmaxf(r7[k], __shfl_xor_sync(FULL, r7[k], o));
+    }
+    if ((threadIdx.x & 31) == 0)
+        for (int k = 0; k < 7; ++k) s_red[threadIdx.x >> 5][k] = r7[k];
     __syncthreads();
-    if (threadIdx.x == 0) {
-        float b = s_red[0];
-        for (int w = 1; w < KNN_THREADS / 32; ++w) b = fmaxf(b, s_red[w]);
-        s_bound = b;
+    if (threadIdx.x < 7) {
+        float v = s_red[0][threadIdx.x];
+        for (int w = 1; w < KNN_THREADS / 32; ++w)
+            v = (threadIdx.x >= 1 && threadIdx.x <= 3) ? fminf(v, s_red[w][threadIdx.x]) : fmaxf(v, s_red[w][threadIdx.x]);
+        s_bound[threadIdx.x] = v;
     }
     __syncthreads();
-    const float cta_bound = s_bound;
-    const Box mybox = boxes[qb];
+    const float cta_bound = s_bound[0];
+    Box mybox;
+    mybox.lo = make_float3(s_bound[1], s_bound[2], s_bound[3]);
+    mybox.hi = make_float3(s_bound[4], s_bound[5], s_bound[6]);
 
-    for (int b = 0; b < nboxes; ++b) {
+    if (share != 0) {
+        // the own box only served as a bound here: its neighbours are reported by share 0
+        reject = fminf(reject, best[2]);
+        best[0] = best[1] = best[2] = FLT_MAX;
+    }
+    for (int b = share; b < nboxes; b += shares) {
         if (b == qb) continue;
         const Box box = boxes[b];
         if (dist_box_box(mybox, box) > cta_bound) continue;   // CTA-uniform
@@ -247,22 +249,40 @@ knn_search_kernel(int P, const float4* __restrict__ sorted, const Box* __restric
         __syncthreads();
         for (int i = threadIdx.x; i < nb; i += KNN_THREADS) s_pts[i] = __ldg(sorted + b0 + i);
         __syncthreads();
-#pragma unroll
-        for (int r = 0; r < QPT; ++r) {
-            if (!valid[r]) continue;
-            const float d = dist_box_point(box, q[r]);
-            if (d > reject[r] || d > best[r][2]) continue;      // simple_knn.cu:172-174
-            for (int i = 0; i < nb; ++i) {
-                const float4 o = s_pts[i];
-                update3(q[r], o.x, o.y, o.z, best[r]);
-            }
+        if (!valid) continue;
+        const float d = dist_box_point(box, q);
+        if (d > reject || d > best[2]) continue;              // simple_knn.cu:172-174
+        for (int i = 0; i < nb; ++i) {
+            const float4 o = s_pts[i];
+            update3(q, o.x, o.y, o.z, best);
         }
     }
+    if (valid) {
+        float* out = partial + (size_t(share) * P + gi) * 3;
+        out[0] = best[0]; out[1] = best[1]; out[2] = best[2];
+    }
+}
 
+// the three smallest of the shares' candidates -> mean (simple_knn.cu:181), written at the point's original index
+__global__ void __launch_bounds__(KNN_THREADS)
+knn_merge_kernel(int P, int shares, const float* __restrict__ partial, const float4* __restrict__ sorted,
+                 float* __restrict__ mean_dists)
+{
+    const size_t gi = size_t(blockIdx.x) * KNN_THREADS + threadIdx.x;
+    if (gi >= (size_t)P) return;
+    float best[3] = {FLT_MAX, FLT_MAX, FLT_MAX};
+    for (int s = 0; s < shares; ++s) {
+        const float* in = partial + (size_t(s) * P + gi) * 3;
 #pragma unroll
-    for (int r = 0; r < QPT; ++r)
-        if (valid[r])
-            mean_dists[qid[r]] = __fdiv_rn(__fadd_rn(__fadd_rn(best[r][0], best[r][1]), best[r][2]), 3.0f);
+        for (int k = 0; k < 3; ++k) {
+            float dist = in[k];
+#pragma unroll
+            for (int j = 0; j < 3; ++j)
+                if (best[j] > dist) { const float t = best[j]; best[j] = dist; dist = t; }
+        }
+    }
+    const uint32_t qid = __float_as_uint(__ldg(sorted + gi).w);
+    mean_dists[qid] = __fdiv_rn(__fadd_rn(__fadd_rn(best[0], best[1]), best[2]), 3.0f);
 }
 
 }  // namespace
@@ -278,10 +298,13 @@ extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists
     if (P < 0 || !points || !mean_dists || !scratch_alloc) { set_error("invalid argument"); return SEGS_ERR_INVALID_ARG; }
     const int nboxes = (P + BOX - 1) / BOX;
     const int npartial = min(SM_COUNT * 2, (P + 255) / 256);
+    // 2-D search grid: enough (query group, share of the candidate boxes) CTAs to fill the machine
+    const int groups = (P + QG - 1) / QG;
+    const int shares = max(1, min(min(nboxes, MAX_SHARES), (SM_COUNT * 4 + groups - 1) / groups));
     // scratch layout
     Carver probe(nullptr);
     auto carve = [&](Carver& c, uint32_t*& ka, uint32_t*& kb, uint32_t*& va, uint32_t*& vb, uint32_t*& bh,
-                     uint32_t*& gh, float*& partial, float4*& sorted, Box*& boxes) {
+                     uint32_t*& gh, float*& partial, float4*& sorted, Box*& boxes, float*& part3) {
         ka = c.take<uint32_t>(P); kb = c.take<uint32_t>(P);
         va = c.take<uint32_t>(P); vb = c.take<uint32_t>(P);
         bh = c.take<uint32_t>(radix_sort_temp_words(P, 4));
@@ -289,14 +312,15 @@ extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists
         partial = c.take<float>(size_t(npartial) * 6);
         sorted = c.take<float4>(P);
         boxes = c.take<Box>(nboxes);
+        part3 = c.take<float>(size_t(shares) * P * 3);
     };
-    uint32_t *ka, *kb, *va, *vb, *bh, *gh; float* partial; float4* sorted; Box* boxes;
-    carve(probe, ka, kb, va, vb, bh, gh, partial, sorted, boxes);
+    uint32_t *ka, *kb, *va, *vb, *bh, *gh; float* partial; float4* sorted; Box* boxes; float* part3;
+    carve(probe, ka, kb, va, vb, bh, gh, partial, sorted, boxes, part3);
     const size_t bytes = probe.used(nullptr) + 128;
     char* base = scratch_alloc(scratch_user, bytes);
     if (!base) { set_error("kNN scratch allocation of %zu bytes failed", bytes); return SEGS_ERR_ALLOC; }
     Carver real(base);
-    carve(real, ka, kb, va, vb, bh, gh, partial, sorted, boxes);
+    carve(real, ka, kb, va, vb, bh, gh, partial, sorted, boxes, part3);
 
     bbox_partial_kernel<<<npartial, 256, 0, stream>>>(P, points, partial);
     SEGS_LAUNCH_CHECK();
@@ -307,7 +331,9 @@ extern "C" int segs_knn_mean_dist2(int P, const float* points, float* mean_dists
     if (rc) return rc;
     gather_box_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, points, va, sorted, boxes);
     SEGS_LAUNCH_CHECK();
-    knn_search_kernel<<<nboxes, KNN_THREADS, 0, stream>>>(P, sorted, boxes, nboxes, mean_dists);
+    knn_search_kernel<<<dim3(groups, shares), KNN_THREADS, 0, stream>>>(P, sorted, boxes, nboxes, shares, part3);
+    SEGS_LAUNCH_CHECK();
+    knn_merge_kernel<<<groups, KNN_THREADS, 0, stream>>>(P, shares, part3, sorted, mean_dists);
     SEGS_LAUNCH_CHECK();
     return SEGS_OK;
 }
