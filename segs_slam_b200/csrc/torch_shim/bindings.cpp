@@ -3,6 +3,7 @@
 // C++ autograd function (gaussian_rasterizer.h).  Built in-tree as segs_slam_b200/_segs_torch.so.
 #include <torch/extension.h>
 
+#include "densify.h"
 #include "fused_mapper.h"
 #include "gaussian_rasterizer.h"
 #include "keyframe_transforms.h"
@@ -74,6 +75,43 @@ torch::Tensor fm_render_views(FusedMapper& fm, const std::vector<std::tuple<torc
     return fm.render_views(kv);
 }
 
+// densify::adjust_anchor over a dict of tensors under the reference's member names (+ "m_<name>" / "v_<name>" moments);
+// -> the new dict (+ "_growing_report", "_prune_report")
+py::dict dn_adjust_anchor(py::dict st, int check_interval, double success_threshold, double grad_threshold, double min_opacity,
+                          int n_offsets, int update_depth, int update_init_factor, int update_hierachy_factor, double voxel_size) {
+    static const char* names[6] = {"_anchor", "_offset", "_anchor_feat", "_opacity", "_scaling", "_rotation"};
+    densify::AnchorState s;
+    auto get = [&](const char* k) { return st[k].cast<torch::Tensor>(); };
+    s.anchor = get("_anchor"); s.offset = get("_offset"); s.anchor_feat = get("_anchor_feat"); s.opacity = get("_opacity");
+    s.scaling = get("_scaling"); s.rotation = get("_rotation");
+    s.opacity_accum = get("opacity_accum"); s.anchor_demon = get("anchor_demon");
+    s.offset_gradient_accum = get("offset_gradient_accum"); s.offset_denom = get("offset_denom");
+    for (int g = 0; g < 6; ++g) {
+        const std::string m = std::string("m_") + names[g], v = std::string("v_") + names[g];
+        if (st.contains(m.c_str())) s.exp_avg[g] = st[m.c_str()].cast<torch::Tensor>();
+        if (st.contains(v.c_str())) s.exp_avg_sq[g] = st[v.c_str()].cast<torch::Tensor>();
+    }
+    densify::ModelParams mp;
+    mp.n_offsets = n_offsets; mp.update_depth = update_depth; mp.update_init_factor = update_init_factor;
+    mp.update_hierachy_factor = update_hierachy_factor; mp.voxel_size = static_cast<float>(voxel_size);
+    densify::adjust_anchor(s, mp, check_interval, static_cast<float>(success_threshold), static_cast<float>(grad_threshold),
+                           static_cast<float>(min_opacity));
+    py::dict out;
+    torch::Tensor* ps[6] = {&s.anchor, &s.offset, &s.anchor_feat, &s.opacity, &s.scaling, &s.rotation};
+    for (int g = 0; g < 6; ++g) {
+        out[names[g]] = *ps[g];
+        if (s.exp_avg[g].defined()) out[(std::string("m_") + names[g]).c_str()] = s.exp_avg[g];
+        if (s.exp_avg_sq[g].defined()) out[(std::string("v_") + names[g]).c_str()] = s.exp_avg_sq[g];
+    }
+    out["opacity_accum"] = s.opacity_accum; out["anchor_demon"] = s.anchor_demon;
+    out["offset_gradient_accum"] = s.offset_gradient_accum; out["offset_denom"] = s.offset_denom;
+    py::list rep;
+    for (auto& r : s.growing_report) rep.append(py::make_tuple(r[0], r[1]));
+    out["_growing_report"] = rep;
+    out["_prune_report"] = py::make_tuple(s.prune_report[0], s.prune_report[1]);
+    return out;
+}
+
 }  // namespace
 
 PYBIND11_MODULE(_segs_torch, m) {
@@ -89,6 +127,9 @@ PYBIND11_MODULE(_segs_torch, m) {
     m.def("psnr", &lu_psnr);
     m.def("l1_ssim", &lu_l1_ssim);
     m.def("adam_step", &lu_adam_step);
+    m.def("adjust_anchor", &dn_adjust_anchor, py::arg("state"), py::arg("check_interval") = 100, py::arg("success_threshold") = 0.8,
+          py::arg("grad_threshold") = 0.0002, py::arg("min_opacity") = 0.005, py::arg("n_offsets") = 10, py::arg("update_depth") = 3,
+          py::arg("update_init_factor") = 16, py::arg("update_hierachy_factor") = 4, py::arg("voxel_size") = 0.001);
     m.def("computeTransformTensors", &kf_transforms);
     m.def("quaternionToRotation", &kf_quat_to_rot);
     py::class_<FusedMapper>(m, "FusedMapper")
@@ -106,5 +147,6 @@ PYBIND11_MODULE(_segs_torch, m) {
         .def("grad_flat", &FusedMapper::grad_flat)
         .def("params", &FusedMapper::params)
         .def("adam_step", &FusedMapper::adam_step)
+        .def("set_frequency", &FusedMapper::set_frequency)
         .def("workspace_bytes", &FusedMapper::workspace_bytes);
 }

@@ -113,6 +113,10 @@ torch::Tensor FusedMapper::render_views(const std::vector<KeyframeView>& views) 
         a.grad_anchor_feat = grad_views_[2].data_ptr<float>(); a.grad_scaling = grad_views_[3].data_ptr<float>();
         a.grad_params = &dg;
         a.loss_accum = loss_accum_.data_ptr<float>();
+        a.lambda_frequency_high = static_cast<float>(freq_lambda_);
+        a.use_multi_resolution = freq_multi_ ? 1 : 0;
+        a.freq_scale_num = freq_scales_;
+        a.gt_freq_mag = nullptr;                            // computed per view in the lane's workspace
         args[v] = a;
     }
     const int lanes = static_cast<int>(std::min<size_t>(lanes_, views.size()));

@@ -43,6 +43,10 @@ public:
     torch::Tensor grad_flat() { return grad_flat_; }
     std::vector<torch::Tensor> params() { return params_; }
     void adam_step(double grad_scale);
+    // frequency regularisation of the loss (src/gaussian_mapper.cpp:930-945): 0 = off; Replica yamls: (0.01, true, 3)
+    void set_frequency(double lambda_frequency_high, bool use_multi_resolution, int scale_num) {
+        freq_lambda_ = lambda_frequency_high; freq_multi_ = use_multi_resolution; freq_scales_ = scale_num;
+    }
     int64_t workspace_bytes() const;
 
 private:
@@ -55,6 +59,9 @@ private:
     double lambda_, reg_w_, eps_;
     std::vector<double> lrs_;
     int lanes_;
+    double freq_lambda_ = 0.0;
+    bool freq_multi_ = true;
+    int freq_scales_ = 3;
     int64_t step_ = 0;
     std::vector<segs_workspace*> ws_;
     std::vector<c10::cuda::CUDAStream> streams_;

@@ -116,3 +116,23 @@ def test_fused_mapper_densifies_and_keeps_training(device):
     for _ in range(5):
         l1 = float(a.step(cams, targets))
     assert np.isfinite(l0) and np.isfinite(l1) and l1 < l0 * 1.05
+
+
+@needs_ref
+def test_cpp_host_layer_is_identical_to_the_reference(device):
+    """densify::adjust_anchor of the LibTorch host layer (csrc/torch_shim/densify.{h,cpp}, the C++ twin of densify.py — the
+    reference's own host language) against the reference's GaussianModel::adjust_anchor: every tensor bit-identical."""
+    from segs_slam_b200 import _segs_torch as shim
+    A, seed = dc.CASES["a2000"]
+    st, grads_adam = dc.make_state(A, seed)
+    m = dc.reference_model(model_ref, st, grads_adam)
+    before = dc.reference_state(m)
+    cpp_in = _product_input(before, device)
+    torch.manual_seed(99)
+    m.adjust_anchor(100, 0.8, 0.0002, 0.005)
+    after = dc.reference_state(m)
+    torch.manual_seed(99)
+    out = shim.adjust_anchor(cpp_in, 100, 0.8, 0.0002, 0.005, **dc.MODEL)
+    names = list(dc.NAMES) + [k for k in after if k[:2] in ("m_", "v_")]
+    _assert_same(out, after, names)
+    assert sum(n for _c, n in out["_growing_report"]) > 0 and out["_prune_report"][1] < out["_prune_report"][0]

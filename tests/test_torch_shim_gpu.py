@@ -215,3 +215,14 @@ def test_cpp_fused_mapper_matches_the_python_host_class(device, shim):
     for a, b in zip(cm.params(), fm.params):
         assert float((a - b).abs().max()) < 2e-5, float((a - b).abs().max())
     assert cm.workspace_bytes() > 0
+    # the Replica configuration of the loss (frequency regularisation) through the C++ class
+    fq = mapper.FusedMapper(model, H, W, tanx, tany, bg, lambda_dssim=0.2, scaling_reg_weight=0.01, lrs=2e-3, lanes=1,
+                            lambda_frequency_high=0.01, use_multi_resolution=True, freq_scale_num=3)
+    loss_fq = fq.step(cams, targets, optimize=False) * len(cams)
+    cm.set_frequency(0.01, True, 3)
+    # NOTE: cm's parameters took one Adam step above, like fm's (both hold the same values to 2e-5)
+    loss_cq = cm.render_views(views)
+    torch.testing.assert_close(loss_cq, loss_fq, rtol=1e-4, atol=0)
+    assert float(loss_cq) > float(loss_c)
+    scale = float(fq.bucket.flat.abs().max())
+    assert float((cm.grad_flat() - fq.bucket.flat).abs().max()) < 2e-3 * scale
