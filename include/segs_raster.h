@@ -315,6 +315,18 @@ int    segs_freq_target(segs_freq_plan* plan, const float* gt, const float* row_
 int    segs_freq_loss(segs_freq_plan* plan, const float* image, const float* row_mask, const float* gt_mag, float weight,
                       const float* dL_dloss, float* loss_out, float* dL_dimage, void* stream);
 
+/* ---- keyframe image ingest ----------------------------------------------------------------
+ *   segs_ingest_image      camera.undistortImage (cv::remap, INTER_LINEAR)      include/camera.h:106-115
+ *                          + tensor_utils::cvMat2TorchTensor_Float32            include/tensor_utils.h:40-69
+ *   segs_resize_bilinear   the Gaussian-pyramid levels (cv::cuda::resize)       src/gaussian_mapper.cpp:621-632, 1289-1298
+ * src_hwc: DEVICE [src_H, src_W, C] interleaved FP32 (the uploaded cv::Mat); map_x / map_y: DEVICE [H, W] FP32 from
+ * cv::initUndistortRectifyMap(..., CV_32F, ...) (both NULL = no undistortion, src size = output size);
+ * dst_chw: DEVICE [C, H, W].  OpenCV's arithmetic: maps quantised to 1/32 pixel, FP32 bilinear table, constant-0 border. */
+int segs_ingest_image(int H, int W, int C, int src_H, int src_W, const float* src_hwc, const float* map_x, const float* map_y,
+                      float* dst_chw, void* stream);
+/* cv::resize(INTER_LINEAR) of a planar FP32 image [C,H,W] -> [C,h,w] */
+int segs_resize_bilinear(int C, int H, int W, const float* src_chw, int h, int w, float* dst_chw, void* stream);
+
 /* ---- densification decisions ---------------------------------------------------------
  *   segs_anchor_growing_level   one level i of GaussianModel::anchor_growing     src/gaussian_model.cpp:1556-1703
  *   segs_prune_plan             the statistics update + prune decision of        src/gaussian_model.cpp:1716-1755

@@ -132,6 +132,8 @@ _PROTOTYPES = {
         C.c_int,
         [C.c_int, C.c_void_p, C.c_int, _f32p, _i32p, _f32p, _f32p, _f32p, _f32p, _f32p, C.c_int, C.c_void_p],
     ),
+    "segs_ingest_image": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, _f32p, _f32p, _f32p, _f32p, C.c_void_p]),
+    "segs_resize_bilinear": (C.c_int, [C.c_int, C.c_int, C.c_int, _f32p, C.c_int, C.c_int, _f32p, C.c_void_p]),
     "segs_freq_plan_create": (C.c_int, [C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float), C.POINTER(C.c_void_p)]),
     "segs_freq_plan_destroy": (C.c_int, [C.c_void_p]),
     "segs_freq_mag_floats": (C.c_size_t, [C.c_void_p]),
