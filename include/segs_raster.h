@@ -244,6 +244,15 @@ int segs_decode_forward(
     char* state, int* counts,
     void* stream);
 
+/* Which forward kernel segs_decode_forward launches (both are sm_100a tcgen05 kernels, same results to ~1e-6):
+ *   2 (default)  visible anchors are listed first, tile = 128 visible anchors, 512 threads per CTA, BOTH layers of the
+ *                three MLPs on the tensor cores (51 tcgen05.mma per tile, 3xTF32), rows assembled by thread = row;
+ *   1            round 1's kernel: tiles in anchor-index order, thread = anchor, first layers on the tensor cores,
+ *                second layers as FP32 FFMA chains.
+ * The environment variable SEGS_DECODE_VARIANT (1 | 2) sets the initial value. */
+int segs_decode_set_variant(int variant);
+int segs_decode_get_variant(void);
+
 /* g_* are the gradients w.r.t. the compacted row outputs (n_out rows); g_neural_opacity
  * ([n_vis*10], may be NULL) the gradient w.r.t. the un-masked opacity output.  d_anchor [A,3],
  * d_anchor_feat [A,32], d_offset [A,10,3], d_scaling [A,6] (w.r.t. the `scaling` input) and every

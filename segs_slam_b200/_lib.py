@@ -111,6 +111,8 @@ _PROTOTYPES = {
     ),
     "segs_knn_mean_dist2": (C.c_int, [C.c_int, _f32p, _f32p, ALLOC_FN, C.c_void_p, C.c_void_p]),
     "segs_decode_state_bytes": (C.c_size_t, [C.c_int]),
+    "segs_decode_set_variant": (C.c_int, [C.c_int]),
+    "segs_decode_get_variant": (C.c_int, []),
     "segs_decode_forward": (
         C.c_int,
         [C.c_int, C.c_void_p, _f32p, _f32p, _f32p, _f32p, _f32p, C.POINTER(C.c_float), C.POINTER(DecodeParams),

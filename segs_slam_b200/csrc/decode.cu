@@ -26,6 +26,8 @@
 // GEMM-shaped parts (layer products, weight-gradient sums) are the tcgen05 candidates of the path;
 // see DESIGN.md §decode.
 #include <algorithm>
+#include <atomic>
+#include <cstdlib>
 #include "common.cuh"
 
 namespace segs {
@@ -393,6 +395,20 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 }
 
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
+// round-to-nearest TF32 (the tensor core ignores the 13 low mantissa bits of its operands, i.e. truncates: rounding
+// both parts of a hi / lo split here halves the representation error of the split and removes its bias)
+__device__ __forceinline__ float tf32_rn(float v) {
+    uint32_t r;
+    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
+    return __uint_as_float(r);
+}
+struct Split4 { float4 hi, lo; };
+__device__ __forceinline__ Split4 split4(float v0, float v1, float v2, float v3) {
+    Split4 s;
+    s.hi = make_float4(tf32_rn(v0), tf32_rn(v1), tf32_rn(v2), tf32_rn(v3));
+    s.lo = make_float4(tf32_rn(v0 - s.hi.x), tf32_rn(v1 - s.hi.y), tf32_rn(v2 - s.hi.z), tf32_rn(v3 - s.hi.w));
+    return s;
+}
 
 }  // namespace tc
 
@@ -642,6 +658,478 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
     tc::fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc(tmem, tc::TMEM_COLS);
+}
+
+// =======================================================================================
+// forward, variant 2 (round 2): BOTH layers of the three MLPs on the tensor cores, tile = 128 VISIBLE anchors
+// =======================================================================================
+// Variant 1 above walks the anchors in index order (a tile of 128 anchors holds ~25 visible ones in a mapping view),
+// runs the second layers as scalar FFMA chains with thread = anchor / thread = row, and keeps 128 threads busy with
+// ~8000 dependent instructions per tile: 43 us per tile, 12 % occupancy, issue slots 19 % busy.  Variant 2:
+//   * `decode_compact_kernel` lists the visible anchors first (one scan + look-back pass over the mask bytes), so a
+//     tile is 128 consecutive visible ORDINALS: 5x fewer tiles in a mapping view, and the visible prefix of a tile is
+//     its index (one look-back per tile instead of two);
+//   * CTA = 512 threads, one per SM (all operands of a tile stay in its 192 KB of shared memory); the input rows are
+//     built by 4 threads per anchor (feature-bank hidden units split 4 ways, logits reduced with two shuffles);
+//   * layer 1:  H[128 x 96]  = X[128 x 40] W1cat^T            15 tcgen05.mma (M 128, N 96, K 8, 3xTF32) -> TMEM cols 0..95
+//     epilogue 1 (12 warps, one MLP's 32 hidden units of 32 anchors each): bias + ReLU, hi/lo split, written straight
+//     back to shared memory as the K-major A operands of
+//   * layer 2:  O_m[128 x N_m] = relu(H_m)[128 x 32] W2_m^T    3 x 12 tcgen05.mma, N = 16 / 80 / 32 (opacity / cov /
+//     colour, zero-padded rows) -> TMEM cols 128.. / 160.. / 96..
+//     epilogue 2 (16 warps x 32 columns): bias, tanh + mask for the opacity columns, everything else to a
+//     [128][113]-float tile in shared memory (it overlays the dead A operands);
+//   * the compacted rows are then assembled by thread = output row exactly as in variant 1 (activation, quaternion
+//     normalisation, coalesced stores), now with no dot products left in the loop.
+// 51 UTCHMMA per tile; every scalar FMA chain of the MLPs is gone from the forward.
+namespace tc2 {
+
+constexpr int THREADS = 512;
+constexpr int KB2 = FEAT / 4;                          // 16-byte K-blocks per row of a layer-2 operand (K = 32)
+constexpr uint32_t SBO1 = tc::KB * tc::CORE;           // layer-1 operands (K = 40)
+constexpr uint32_t SBO2 = KB2 * tc::CORE;              // layer-2 operands
+constexpr int N_OP = 16, N_COV = 80, N_COL = 32;       // MMA N of the second layers (10 / 70 / 30 outputs, zero-padded)
+constexpr int B2_OP = 0;                               // byte offsets of the three W2 tiles inside the B2 buffer
+constexpr int B2_COV = B2_OP + N_OP * FEAT * 4;        // 2048
+constexpr int B2_COL = B2_COV + N_COV * FEAT * 4;      // 12288
+constexpr int B2_BYTES = B2_COL + N_COL * FEAT * 4;    // 16384
+constexpr int A2_BYTES = tc::TM * FEAT * 4;            // 16384 per MLP and per hi / lo
+constexpr int COL_D2C = 96, COL_D2O = 128, COL_D2S = 160;   // TMEM columns of the layer-2 accumulators (layer 1: 0..95)
+constexpr int TMEM_COLS = 256;
+constexpr int OUT_W = 113;                             // floats per anchor in s_out: op(10) | scale_rot(70) | colour(30); odd stride
+constexpr int O_OP = 0, O_COV = NOFF, O_COL = NOFF + 7 * NOFF;
+constexpr int U_BYTES = 6 * A2_BYTES;                  // union: A1 hi|lo  /  A2 hi[3] | lo[3]  /  s_out
+static_assert(2 * tc::A_BYTES <= U_BYTES && tc::TM * OUT_W * 4 <= U_BYTES, "operand union");
+
+__host__ __device__ constexpr uint32_t idesc(int n) {
+    return (1u << 4) | (2u << 7) | (2u << 10) | (uint32_t(n >> 3) << 17) | (uint32_t(tc::TM >> 4) << 24);
+}
+// byte offset of element (row, k) of a K-major no-swizzle operand with KB2 K-blocks per row
+__device__ __forceinline__ uint32_t canon2(int row, int k) {
+    return uint32_t(((row >> 3) * KB2 + (k >> 2)) * tc::CORE + (row & 7) * 16 + (k & 3) * 4);
+}
+__device__ __forceinline__ uint64_t make_desc(uint32_t smem_addr, uint32_t sbo) {
+    return uint64_t((smem_addr & 0x3FFFFu) >> 4) | (uint64_t(tc::LBO >> 4) << 16) | (uint64_t(sbo >> 4) << 32) | (uint64_t(1) << 46);
+}
+__device__ __forceinline__ void umma_tf32(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t id, uint32_t accumulate) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "setp.ne.b32 p, %4, 0;\n"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+        "}\n" ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(id), "r"(accumulate) : "memory");
+}
+
+constexpr size_t OFF_B1H = align128(sizeof(SWF));
+constexpr size_t OFF_B1L = OFF_B1H + tc::B_BYTES;
+constexpr size_t OFF_B2H = OFF_B1L + tc::B_BYTES;
+constexpr size_t OFF_B2L = OFF_B2H + B2_BYTES;
+constexpr size_t OFF_U = (OFF_B2L + B2_BYTES + 1023) & ~size_t(1023);
+constexpr size_t OFF_REC = OFF_U + U_BYTES;
+constexpr size_t OFF_ROW = OFF_REC + sizeof(float) * tc::TM * REC_W;          // uint32 [TM + 4]
+constexpr size_t OFF_AID = OFF_ROW + sizeof(uint32_t) * (tc::TM + 4);          // uint32 [TM]
+constexpr size_t OFF_MSK = OFF_AID + sizeof(uint32_t) * tc::TM;                // uint32 [TM]
+constexpr size_t SMEM = OFF_MSK + sizeof(uint32_t) * tc::TM;
+static_assert(SMEM <= 227 * 1024, "decode forward v2: shared memory");
+
+}  // namespace tc2
+
+constexpr int CMP_PER = 8;                             // anchors per thread of the compaction pass
+constexpr int CMP_TILE = DEC_THREADS * CMP_PER;
+
+// Visible-anchor list: anchor_index[ordinal] = a for the visible anchors in ascending order, counters[1] = their number.
+__global__ void __launch_bounds__(DEC_THREADS)
+decode_compact_kernel(int A, const unsigned char* __restrict__ visible_mask, DecodeState st)
+{
+    __shared__ uint32_t s_warp[DEC_THREADS / 32];
+    __shared__ uint32_t s_tile, s_base;
+    const int tid = threadIdx.x, lane = tid & 31;
+    const uint32_t ntiles = (uint32_t)((A + CMP_TILE - 1) / CMP_TILE);
+    if (tid == 0) s_tile = atomicAdd(st.counters + 2, 1u);          // ticket: a tile only waits for tiles that run
+    __syncthreads();
+    const uint32_t tile = s_tile;
+    if (tile >= ntiles) return;
+    const size_t a0 = size_t(tile) * CMP_TILE + size_t(tid) * CMP_PER;
+    uint32_t bits = 0;
+    if ((reinterpret_cast<uintptr_t>(visible_mask) & 7u) == 0 && a0 + CMP_PER <= (size_t)A) {
+        const unsigned long long v = __ldg(reinterpret_cast<const unsigned long long*>(visible_mask + a0));
+#pragma unroll
+        for (int k = 0; k < CMP_PER; ++k) if ((v >> (8 * k)) & 0xFFull) bits |= 1u << k;
+    } else {
+#pragma unroll
+        for (int k = 0; k < CMP_PER; ++k) if (a0 + k < (size_t)A && visible_mask[a0 + k] != 0) bits |= 1u << k;
+    }
+    uint32_t total;
+    const uint32_t ord = cta_exclusive_scan(__popc(bits), s_warp, &total);
+    if (tid < 32) {
+        const uint32_t b = lookback(st.look_vis, tile, total, lane);
+        if (lane == 0) {
+            s_base = b;
+            if (tile == ntiles - 1) st.counters[1] = b + total;
+        }
+    }
+    __syncthreads();
+    uint32_t o = s_base + ord;
+#pragma unroll
+    for (int k = 0; k < CMP_PER; ++k) if ((bits >> k) & 1u) st.anchor_index[o++] = (uint32_t)(a0 + k);
+}
+
+__global__ void __launch_bounds__(tc2::THREADS, 1)
+decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ anchor,
+                         const float* __restrict__ anchor_feat, const float* __restrict__ offset,
+                         const float* __restrict__ scaling, const float* __restrict__ cam, const Pose7 pose,
+                         const segs_decode_params p, float* __restrict__ out_xyz, float* __restrict__ out_color,
+                         float* __restrict__ out_opacity, float* __restrict__ out_scaling, float* __restrict__ out_rot,
+                         float* __restrict__ neural_opacity, unsigned char* __restrict__ out_mask, DecodeState st,
+                         volatile uint32_t* __restrict__ host_counts)
+{
+    extern __shared__ __align__(1024) unsigned char s_dec[];
+    SWF& sw = *reinterpret_cast<SWF*>(s_dec);
+    unsigned char* sB1_hi = s_dec + tc2::OFF_B1H;
+    unsigned char* sB1_lo = s_dec + tc2::OFF_B1L;
+    unsigned char* sB2_hi = s_dec + tc2::OFF_B2H;
+    unsigned char* sB2_lo = s_dec + tc2::OFF_B2L;
+    unsigned char* sU = s_dec + tc2::OFF_U;
+    unsigned char* sA1_hi = sU;                                            // layer-1 A operand, hi / lo
+    unsigned char* sA1_lo = sU + tc::A_BYTES;
+    unsigned char* sA2_hi = sU;                                            // layer-2 A operands [3], hi / lo
+    unsigned char* sA2_lo = sU + 3 * tc2::A2_BYTES;
+    float* s_out = reinterpret_cast<float*>(sU);                           // [128][OUT_W] layer-2 outputs (+ bias)
+    float* s_rec = reinterpret_cast<float*>(s_dec + tc2::OFF_REC);         // [128][REC_W]: anchor, scaling, opacities
+    uint32_t* s_row = reinterpret_cast<uint32_t*>(s_dec + tc2::OFF_ROW);   // [129] first row of every anchor of the tile
+    uint32_t* s_aid = reinterpret_cast<uint32_t*>(s_dec + tc2::OFF_AID);   // [128] anchor ids
+    uint32_t* s_msk = reinterpret_cast<uint32_t*>(s_dec + tc2::OFF_MSK);   // [128] surviving-offset bits
+    __shared__ uint32_t s_warp[4];
+    __shared__ uint32_t s_tile[2], s_row_base, s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int lq = warp & 3, grp = warp >> 2;          // TMEM lane quarter this warp may read; column group
+    const uint32_t n_vis = identity ? (uint32_t)A : st.counters[1];
+    const uint32_t ntiles = (n_vis + tc::TM - 1) / tc::TM;
+
+    // ---- once per (persistent) CTA: TMEM, mbarrier, weights ----
+    if (warp == 0) tc::tmem_alloc(&s_tmem, tc2::TMEM_COLS);
+    if (tid == 0) {
+        tc::mbar_init(&s_bar, 1);
+        s_tile[0] = atomicAdd(st.counters, 1u);
+        if (ntiles == 0 && blockIdx.x == 0 && host_counts != nullptr) {    // nothing visible: nobody else reports
+            host_counts[0] = 0;
+            host_counts[1] = 0;
+            __threadfence_system();
+        }
+    }
+    {
+        // B operands.  Layer 1: W1cat[n][k], n = 32 * mlp + hidden unit, k = input column (as in variant 1);
+        // layer 2: one tile per MLP, row = output unit (zero rows pad N to 16 / 80 / 32), k = hidden unit.
+        const int in_o = 35 + (p.add_opacity_dist ? 1 : 0), in_s = 35 + (p.add_cov_dist ? 1 : 0);
+        const int in_c = 35 + (p.add_color_dist ? 1 : 0), ld_c = in_c + p.appearance_dim;
+        for (int e = tid; e < tc::TN * tc::TK; e += tc2::THREADS) {
+            const int n = e / tc::TK, k = e % tc::TK, j = n & 31;
+            float w = 0.f;
+            if (n < 32) { if (k < in_o) w = __ldg(p.opacity_w1 + j * in_o + k); }
+            else if (n < 64) { if (k < in_s) w = __ldg(p.cov_w1 + j * in_s + k); }
+            else { if (k < in_c) w = __ldg(p.color_w1 + j * ld_c + k); }
+            const float hi = tc::tf32_rn(w);
+            const uint32_t off = tc::canon_off(n, k);
+            *reinterpret_cast<float*>(sB1_hi + off) = hi;
+            *reinterpret_cast<float*>(sB1_lo + off) = tc::tf32_rn(w - hi);
+        }
+        for (int e = tid; e < 128 * FEAT; e += tc2::THREADS) {
+            const int n = e / FEAT, k = e % FEAT;
+            float w = 0.f;
+            uint32_t off;
+            if (n < tc2::N_OP) {
+                if (n < NOFF) w = __ldg(p.opacity_w2 + n * FEAT + k);
+                off = tc2::B2_OP + tc2::canon2(n, k);
+            } else if (n < tc2::N_OP + tc2::N_COV) {
+                const int r = n - tc2::N_OP;
+                if (r < 7 * NOFF) w = __ldg(p.cov_w2 + r * FEAT + k);
+                off = tc2::B2_COV + tc2::canon2(r, k);
+            } else {
+                const int r = n - tc2::N_OP - tc2::N_COV;
+                if (r < 3 * NOFF) w = __ldg(p.color_w2 + r * FEAT + k);
+                off = tc2::B2_COL + tc2::canon2(r, k);
+            }
+            const float hi = tc::tf32_rn(w);
+            *reinterpret_cast<float*>(sB2_hi + off) = hi;
+            *reinterpret_cast<float*>(sB2_lo + off) = tc::tf32_rn(w - hi);
+        }
+    }
+    stage_weights(sw, p, pose);          // biases, feature-bank weights, appearance fold; contains __syncthreads
+    tc::fence_async_smem();
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+    const bool use_bank = p.use_feat_bank != 0;
+    uint32_t phase = 0;
+    // descriptors of the operand tiles (the start address sits in the low bits in units of 16 bytes: stepping along K or to
+    // another tile is an add)
+    const uint64_t dA1_hi = tc2::make_desc(tc::smem_u32(sA1_hi), tc2::SBO1), dA1_lo = tc2::make_desc(tc::smem_u32(sA1_lo), tc2::SBO1);
+    const uint64_t dB1_hi = tc2::make_desc(tc::smem_u32(sB1_hi), tc2::SBO1), dB1_lo = tc2::make_desc(tc::smem_u32(sB1_lo), tc2::SBO1);
+    const uint64_t dA2_hi = tc2::make_desc(tc::smem_u32(sA2_hi), tc2::SBO2), dA2_lo = tc2::make_desc(tc::smem_u32(sA2_lo), tc2::SBO2);
+    const uint64_t dB2_hi = tc2::make_desc(tc::smem_u32(sB2_hi), tc2::SBO2), dB2_lo = tc2::make_desc(tc::smem_u32(sB2_lo), tc2::SBO2);
+
+    for (int it = 0;; ++it) {
+        const uint32_t tile = s_tile[it & 1];
+        if (tile >= ntiles) break;
+        const uint32_t ord0 = tile * tc::TM;                               // visible ordinal of row 0
+        const uint32_t n_act = min((uint32_t)tc::TM, n_vis - ord0);
+
+        // ---- D1-D3: MLP input rows -> layer-1 A operand (hi / lo).  4 threads per anchor: thread q owns the
+        //      feature columns / bank hidden units [8q, 8q + 8) ----
+        if (tid < tc::TM) s_msk[tid] = 0u;               // filled with atomicOr after the second layer
+        {
+            const int i = tid >> 2, q = tid & 3;
+            const bool act = (uint32_t)i < n_act;        // idle slots compute on the tile's first anchor (the shuffles
+            {                                            // below need every lane) and store nothing
+                const uint32_t oi = ord0 + (act ? (uint32_t)i : 0u);
+                const size_t a = identity ? size_t(oi) : size_t(st.anchor_index[oi]);
+                const float ax = __ldg(anchor + 3 * a), ay = __ldg(anchor + 3 * a + 1), az = __ldg(anchor + 3 * a + 2);
+                const float vx = ax - __ldg(cam), vy = ay - __ldg(cam + 1), vz = az - __ldg(cam + 2);
+                const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
+                const float ux = vx / dist, uy = vy / dist, uz = vz / dist;
+                const float* frow = anchor_feat + a * FEAT;
+                float x[8];
+                {
+                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q);
+                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q + 1);
+                    x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
+                }
+                if (use_bank) {
+                    // bank weights = softmax(W2 relu(W1 [view, dist] + b1) + b2)   (gaussian_renderer.cpp:236-239)
+                    float l0 = 0.f, l1 = 0.f, l2 = 0.f;
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const int j = 8 * q + jj;
+                        const float4 w4 = *reinterpret_cast<const float4*>(sw.wb1[j]);
+                        float hb = sw.bb1[j];
+                        hb = fmaf(w4.x, ux, hb); hb = fmaf(w4.y, uy, hb); hb = fmaf(w4.z, uz, hb); hb = fmaf(w4.w, dist, hb);
+                        hb = fmaxf(hb, 0.f);
+                        l0 = fmaf(sw.wb2[0][j], hb, l0); l1 = fmaf(sw.wb2[1][j], hb, l1); l2 = fmaf(sw.wb2[2][j], hb, l2);
+                    }
+                    // the four threads of an anchor are adjacent lanes: butterfly sums are identical in all four
+                    l0 += __shfl_xor_sync(FULL, l0, 1); l1 += __shfl_xor_sync(FULL, l1, 1); l2 += __shfl_xor_sync(FULL, l2, 1);
+                    l0 += __shfl_xor_sync(FULL, l0, 2); l1 += __shfl_xor_sync(FULL, l1, 2); l2 += __shfl_xor_sync(FULL, l2, 2);
+                    l0 += sw.bb2[0]; l1 += sw.bb2[1]; l2 += sw.bb2[2];
+                    const float mx = fmaxf(l0, fmaxf(l1, l2));
+                    const float e0 = expf(l0 - mx), e1 = expf(l1 - mx), e2 = expf(l2 - mx);
+                    const float den = e0 + e1 + e2;
+                    const float w0 = e0 / den, w1 = e1 / den, w2 = e2 / den;
+                    // feat'[j] = feat[4 (j mod 8)] w0 + feat[2 (j mod 16)] w1 + feat[j] w2   (:241-248; repeat = tiling)
+#pragma unroll
+                    for (int jj = 0; jj < 8; ++jj) {
+                        const float fa = __ldg(frow + 4 * jj);                      // j mod 8 = jj
+                        const float fb = __ldg(frow + 16 * (q & 1) + 2 * jj);       // j mod 16 = 8 (q & 1) + jj
+                        x[jj] = fa * w0 + fb * w1 + x[jj] * w2;
+                    }
+                }
+                auto put4 = [&](int kb, float v0, float v1, float v2, float v3) {
+                    if (!act) return;
+                    const tc::Split4 sp = tc::split4(v0, v1, v2, v3);
+                    const uint32_t off = tc::canon_off(i, 4 * kb);
+                    *reinterpret_cast<float4*>(sA1_hi + off) = sp.hi;
+                    *reinterpret_cast<float4*>(sA1_lo + off) = sp.lo;
+                };
+                put4(2 * q, x[0], x[1], x[2], x[3]);
+                put4(2 * q + 1, x[4], x[5], x[6], x[7]);
+                if (q == 0 && act) {
+                    put4(8, ux, uy, uz, dist);
+                    float* rec = s_rec + i * REC_W;
+                    rec[0] = ax; rec[1] = ay; rec[2] = az;
+#pragma unroll
+                    for (int k = 0; k < 6; ++k) rec[3 + k] = __ldg(scaling + 6 * a + k);
+                    s_aid[i] = (uint32_t)a;
+                } else if (q == 1) {
+                    put4(9, 0.f, 0.f, 0.f, 0.f);          // K padding: the weights there are zero, the operand must be finite
+                }
+            }
+        }
+        tc::fence_async_smem();          // generic-proxy writes -> visible to the tensor core (async proxy)
+        tc::fence_before_sync();
+        __syncthreads();
+
+        // ---- D4, first layers: 5 K-steps x 3 split products ----
+        if (tid == 0) {
+            tc::fence_after_sync();
+            constexpr uint32_t id = tc2::idesc(tc::TN);
+#pragma unroll
+            for (int j = 0; j < tc::TK / 8; ++j) {
+                const uint64_t ko = (2 * j * tc::CORE) >> 4;        // two K-blocks per instruction
+                tc2::umma_tf32(tmem, dA1_hi + ko, dB1_hi + ko, id, j > 0 ? 1u : 0u);
+                tc2::umma_tf32(tmem, dA1_hi + ko, dB1_lo + ko, id, 1u);
+                tc2::umma_tf32(tmem, dA1_lo + ko, dB1_hi + ko, id, 1u);
+            }
+            tc::umma_commit(&s_bar);
+        }
+        tc::mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+
+        // ---- epilogue 1: warp (lq, grp < 3) = 32 anchors x the 32 hidden units of MLP grp.  bias + ReLU, hi / lo
+        //      split, straight into the layer-2 A operand (the layer-1 operand it overlays has been consumed) ----
+        const int row = lq * 32 + lane;                  // TMEM lane = anchor slot of this thread in both epilogues
+        const uint32_t lane_base = tmem + (uint32_t(lq * 32) << 16);
+        if (grp < 3) {
+            float h[FEAT];
+            tc::tmem_ld32(lane_base + grp * FEAT, h);
+            unsigned char* a_hi = sA2_hi + grp * tc2::A2_BYTES;
+            unsigned char* a_lo = sA2_lo + grp * tc2::A2_BYTES;
+#pragma unroll
+            for (int kb = 0; kb < tc2::KB2; ++kb) {
+                const float v0 = fmaxf(h[4 * kb] + sw.b1[grp][4 * kb], 0.f), v1 = fmaxf(h[4 * kb + 1] + sw.b1[grp][4 * kb + 1], 0.f);
+                const float v2 = fmaxf(h[4 * kb + 2] + sw.b1[grp][4 * kb + 2], 0.f), v3 = fmaxf(h[4 * kb + 3] + sw.b1[grp][4 * kb + 3], 0.f);
+                const tc::Split4 sp = tc::split4(v0, v1, v2, v3);
+                const uint32_t off = tc2::canon2(row, 4 * kb);
+                *reinterpret_cast<float4*>(a_hi + off) = sp.hi;
+                *reinterpret_cast<float4*>(a_lo + off) = sp.lo;
+            }
+        }
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+
+        // ---- D4, second layers: per MLP 4 K-steps x 3 split products ----
+        if (tid == 0) {
+            tc::fence_after_sync();
+#pragma unroll
+            for (int mlp = 0; mlp < 3; ++mlp) {
+                const uint32_t boff = mlp == 0 ? tc2::B2_OP : mlp == 1 ? tc2::B2_COV : tc2::B2_COL;
+                const uint32_t id = mlp == 0 ? tc2::idesc(tc2::N_OP) : mlp == 1 ? tc2::idesc(tc2::N_COV) : tc2::idesc(tc2::N_COL);
+                const uint32_t d = tmem + (mlp == 0 ? tc2::COL_D2O : mlp == 1 ? tc2::COL_D2S : tc2::COL_D2C);
+#pragma unroll
+                for (int j = 0; j < FEAT / 8; ++j) {
+                    const uint64_t ka = (mlp * tc2::A2_BYTES + 2 * j * tc::CORE) >> 4, kb = (boff + 2 * j * tc::CORE) >> 4;
+                    tc2::umma_tf32(d, dA2_hi + ka, dB2_hi + kb, id, j > 0 ? 1u : 0u);
+                    tc2::umma_tf32(d, dA2_hi + ka, dB2_lo + kb, id, 1u);
+                    tc2::umma_tf32(d, dA2_lo + ka, dB2_hi + kb, id, 1u);
+                }
+            }
+            tc::umma_commit(&s_bar);
+            s_tile[(it + 1) & 1] = atomicAdd(st.counters, 1u);   // next ticket: its latency hides behind the epilogue
+        }
+        tc::mbar_wait(&s_bar, phase);
+        phase ^= 1u;
+        tc::fence_after_sync();
+
+        // ---- epilogue 2: 16 warps x 32 accumulator columns -> s_out (+ bias); the opacity warps apply tanh and
+        //      take the mask.  s_out overlays the layer-2 A operands, which the MMAs have consumed. ----
+        {
+            float v[32];
+            float* so = s_out + row * tc2::OUT_W;
+            if (grp == 0) {                                  // colour pre-activations
+                tc::tmem_ld32(lane_base + tc2::COL_D2C, v);
+#pragma unroll
+                for (int c = 0; c < 3 * NOFF; ++c) so[tc2::O_COL + c] = v[c] + sw.b2c[c];
+            } else if (grp == 1) {                           // opacity pre-activations
+                tc::tmem_ld32(lane_base + tc2::COL_D2O, v);
+#pragma unroll
+                for (int o = 0; o < NOFF; ++o) so[tc2::O_OP + o] = v[o] + sw.b2o[o];
+                tc::tmem_ld32(lane_base + tc2::COL_D2S + 64, v);     // scale_rot units 64..69
+#pragma unroll
+                for (int c = 0; c < 7 * NOFF - 64; ++c) so[tc2::O_COV + 64 + c] = v[c] + sw.b2s[64 + c];
+            } else {                                         // scale_rot units 0..31 / 32..63
+                const int c0 = (grp - 2) * 32;
+                tc::tmem_ld32(lane_base + tc2::COL_D2S + c0, v);
+#pragma unroll
+                for (int c = 0; c < 32; ++c) so[tc2::O_COV + c0 + c] = v[c] + sw.b2s[c0 + c];
+            }
+        }
+        tc::fence_before_sync();         // TMEM reads are ordered before the next tile's MMAs (across the barriers below)
+        __syncthreads();
+
+        // ---- opacity = tanh, mask = neural_opacity > 0 (:278-279): one (anchor, offset) pair per thread and step ----
+        for (uint32_t e = tid; e < n_act * NOFF; e += tc2::THREADS) {
+            const uint32_t k = e / NOFF, o = e - k * NOFF;
+            const float t = tanhf(s_out[k * tc2::OUT_W + tc2::O_OP + o]);
+            s_rec[k * REC_W + 9 + o] = t;
+            if (t > 0.0f) atomicOr(&s_msk[k], 1u << o);
+        }
+        __syncthreads();
+
+        // ---- rows of the tile: exclusive scan of the surviving offsets per anchor (warps 0..3) ----
+        uint32_t cnt = 0, inc = 0;
+        if (tid < tc::TM) {
+            cnt = __popc(s_msk[tid]);
+            inc = cnt;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t y = __shfl_up_sync(FULL, inc, o);
+                if (lane >= o) inc += y;
+            }
+            if (lane == 31) s_warp[warp] = inc;
+        }
+        __syncthreads();
+        const uint32_t n_rows = s_warp[0] + s_warp[1] + s_warp[2] + s_warp[3];
+        if (tid < tc::TM) {
+            uint32_t woff = 0;
+#pragma unroll
+            for (int w = 0; w < 4; ++w) if (w < warp) woff += s_warp[w];
+            s_row[tid] = woff + inc - cnt;
+        }
+        if (tid == 0) s_row[tc::TM] = n_rows;                 // sentinel for the search below
+        if (tid < 32) {
+            // ---- order across CTAs: exclusive prefix of the surviving rows (the visible prefix is ord0) ----
+            const uint32_t rb = lookback(st.look_row, tile, n_rows, lane);
+            if (lane == 0) {
+                s_row_base = rb;
+                if (tile == ntiles - 1 && host_counts != nullptr) {
+                    host_counts[0] = n_vis;
+                    host_counts[1] = rb + n_rows;
+                    __threadfence_system();
+                }
+            }
+        } else {
+            // ---- per-anchor outputs, coalesced over (ordinal, offset) ----
+            for (uint32_t e = tid - 32; e < n_act * NOFF; e += tc2::THREADS - 32) {
+                const uint32_t k = e / NOFF, o = e - k * NOFF;
+                neural_opacity[size_t(ord0) * NOFF + e] = s_rec[k * REC_W + 9 + o];
+                out_mask[size_t(ord0) * NOFF + e] = (unsigned char)((s_msk[k] >> o) & 1u);
+            }
+        }
+        __syncthreads();
+        const size_t row_base = s_row_base;
+        if ((uint32_t)tid < n_act) {
+            if (identity) st.anchor_index[ord0 + tid] = s_aid[tid];
+            st.row_start[ord0 + tid] = (uint32_t)(row_base + s_row[tid]);
+            st.mask_bits[ord0 + tid] = s_msk[tid];
+        }
+
+        // ---- D5: thread = output row; consecutive threads write consecutive rows ----
+        for (uint32_t r = tid; r < n_rows; r += tc2::THREADS) {
+            int lo = 0, hi = tc::TM;                     // s_row[lo] <= r < s_row[hi]
+#pragma unroll
+            for (int step = 0; step < 7; ++step) {
+                const int mid = (lo + hi) >> 1;
+                if (mid > lo && s_row[mid] <= r) lo = mid; else if (mid > lo) hi = mid;
+            }
+            const float* rec = s_rec + lo * REC_W;
+            const int o = __fns(s_msk[lo], 0, (int)(r - s_row[lo]) + 1);     // the (r - first)-th surviving offset
+            const size_t aid = s_aid[lo];
+            const float* sr = s_out + lo * tc2::OUT_W + tc2::O_COV + 7 * o;
+            const float* sc = s_out + lo * tc2::OUT_W + tc2::O_COL + 3 * o;
+            const size_t orow = row_base + r;
+            const float* off = offset + (aid * NOFF + o) * 3;
+            // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
+            out_xyz[3 * orow] = rec[0] + __ldg(off) * rec[3];
+            out_xyz[3 * orow + 1] = rec[1] + __ldg(off + 1) * rec[4];
+            out_xyz[3 * orow + 2] = rec[2] + __ldg(off + 2) * rec[5];
+            out_scaling[3 * orow] = rec[6] * sigmoidf_(sr[0]);
+            out_scaling[3 * orow + 1] = rec[7] * sigmoidf_(sr[1]);
+            out_scaling[3 * orow + 2] = rec[8] * sigmoidf_(sr[2]);
+            const float q0 = sr[3], q1 = sr[4], q2 = sr[5], q3 = sr[6];
+            const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
+            *reinterpret_cast<float4*>(out_rot + 4 * orow) = make_float4(q0 / nrm, q1 / nrm, q2 / nrm, q3 / nrm);
+            out_opacity[orow] = rec[9 + o];
+#pragma unroll
+            for (int k = 0; k < 3; ++k) out_color[3 * orow + k] = sigmoidf_(sc[k]);
+        }
+        __syncthreads();                 // the tile is done with s_out / s_rec / s_row / s_aid / s_msk; next ticket is visible
+    }
+
+    // ---- teardown: the allocating warp frees TMEM once every warp is done with it ----
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, tc2::TMEM_COLS);
 }
 
 // =======================================================================================
@@ -1027,6 +1515,251 @@ decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs,
     }
 }
 
+// =======================================================================================
+// backward, kernel 2, variant 2 (round 2): the weight gradients on the tensor cores
+// =======================================================================================
+// dW[p][q] = sum over anchors k of U[k][p] V[k][q] is a contraction over the ANCHOR index, and kernel 1 already stores
+// every factor feature-major ([row][64 ordinals]) — K-major operands as they lie.  Per stage of 32 ordinals the rows
+// are loaded once (coalesced 16-byte loads, 100 % sector use), split hi / lo (3xTF32) in registers and stored as the
+// no-swizzle core-matrix tiles of three products that accumulate in TMEM over ALL stages of the persistent CTA:
+//   D1[128 x 48]  = [dpre_opacity | dpre_cov | dpre_colour](96 rows)  x  [x(36) | 1]      -> dW1 of the three MLPs, db1
+//   D2[128 x 112] = [d2_opacity(10) | d2_scale_rot(70) | d2_colour(30)] x [h_opacity | h_cov | h_colour | 1]
+//                                                      -> the diagonal blocks are dW2 of the three MLPs, the 1-column db2
+//   D3[128 x 48]  = [dpre_bank(32) | dlogit(3)]  x  [h_bank(32) | view,dist(4) | 1]        -> feature-bank dW1, dW2, biases
+// (a row of ones in the B operand turns the bias sums into one more output column).  36 tcgen05.mma per stage replace
+// ~2300 FFMA + 580 LDS.128 per thread; the next stage's rows are in flight (registers) while the MMAs run.  One flush
+// per CTA: tcgen05.ld + one atomic per needed element, as in variant 1.
+namespace wg2 {
+
+constexpr int THREADS = 512;
+constexpr int KS = 32;                          // ordinals per stage = MMA K per stage (4 instructions of K = 8)
+constexpr int KBS = KS / 4;                     // 16-byte K-blocks per operand row
+constexpr uint32_t SBO = KBS * tc::CORE;        // 1024
+constexpr int N1 = 48, N2 = 112, N3 = 48;
+constexpr int A_T = 128 * KS * 4;               // bytes of a 128-row operand tile (hi or lo)
+constexpr int OFF_A1 = 0;
+constexpr int OFF_B1 = OFF_A1 + A_T;
+constexpr int OFF_A2 = OFF_B1 + N1 * KS * 4;
+constexpr int OFF_B2 = OFF_A2 + A_T;
+constexpr int OFF_A3 = OFF_B2 + N2 * KS * 4;
+constexpr int OFF_B3 = OFF_A3 + A_T;
+constexpr int HALF = OFF_B3 + N3 * KS * 4;      // 75776: the lo tiles follow the hi tiles
+constexpr int SMEM = 2 * HALF;
+constexpr int COL_D1 = 0, COL_D2 = 64, COL_D3 = 192;
+constexpr int TMEM_COLS = 256;
+constexpr int ONES1 = XDIM, ONES2 = 3 * FEAT, ONES3 = FEAT + 4;       // B-tile rows that hold 1.0
+constexpr int MAX_LD = ((FACT_ROWS + 7) / 8 * 8 * KBS + THREADS - 1) / THREADS;   // 16-byte loads per thread and stage (13)
+static_assert(HALF % 1024 == 0 && SMEM <= 227 * 1024, "decode wgrad v2: shared memory");
+
+__device__ __forceinline__ uint32_t canon(int row, int k) {
+    return uint32_t(((row >> 3) * KBS + (k >> 2)) * tc::CORE + (row & 7) * 16 + (k & 3) * 4);
+}
+// factor row -> byte offset of its row 0 / column 0 element inside the hi half (tile base + row placement)
+__device__ __forceinline__ uint32_t place(int r) {
+    int base, trow;
+    if (r < F_H) { base = OFF_B1; trow = r - F_X; }
+    else if (r < F_DPRE) { base = OFF_B2; trow = r - F_H; }
+    else if (r < F_D2O) { base = OFF_A1; trow = r - F_DPRE; }
+    else if (r < F_HB) { base = OFF_A2; trow = r - F_D2O; }
+    else if (r < F_DPREB) { base = OFF_B3; trow = r - F_HB; }
+    else if (r < F_DLOG) { base = OFF_A3; trow = r - F_DPREB; }
+    else if (r < F_CAT) { base = OFF_A3; trow = FEAT + (r - F_DLOG); }
+    else { base = OFF_B3; trow = FEAT + (r - F_CAT); }
+    return uint32_t(base) + uint32_t(((trow >> 3) * KBS) * tc::CORE + (trow & 7) * 16);
+}
+
+}  // namespace wg2
+
+struct WGradOut {
+    float* w1[3]; float* b1[3]; int ld1[3]; int in1[3];     // first layers: dW1[j * ld + i], i < in
+    float* w2[3]; float* b2[3];                             // second layers: opacity [10,32], cov [70,32], colour [30,32]
+    float* bank_w1; float* bank_b1; float* bank_w2; float* bank_b2;   // NULL without the feature bank
+};
+
+__global__ void __launch_bounds__(wg2::THREADS, 1)
+decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut out, const int nrows_used)
+{
+    extern __shared__ __align__(1024) unsigned char s_op[];
+    __shared__ uint32_t s_tmem;
+    __shared__ __align__(8) uint64_t s_bar;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int nstages = (n_vis + wg2::KS - 1) / wg2::KS;
+    const bool bank = out.bank_w1 != nullptr;
+
+    if (warp == 0) tc::tmem_alloc(&s_tmem, wg2::TMEM_COLS);
+    if (tid == 0) tc::mbar_init(&s_bar, 1);
+    // padding rows stay zero for the whole kernel; the rows of ones are written once
+    for (int e = tid; e < wg2::SMEM / 16; e += wg2::THREADS) reinterpret_cast<float4*>(s_op)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
+    __syncthreads();
+    if (tid < 3 * wg2::KS) {
+        const int which = tid / wg2::KS, k = tid % wg2::KS;
+        const int base = which == 0 ? wg2::OFF_B1 : which == 1 ? wg2::OFF_B2 : wg2::OFF_B3;
+        const int row = which == 0 ? wg2::ONES1 : which == 1 ? wg2::ONES2 : wg2::ONES3;
+        *reinterpret_cast<float*>(s_op + base + wg2::canon(row, k)) = 1.0f;
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    tc::fence_after_sync();
+    const uint32_t tmem = s_tmem;
+
+    // this thread's 16-byte pieces of a stage: piece e -> factor row (e >> 6) * 8 + (e & 7), K-block ((e >> 3) & 3) + 4 * ((e >> 5) & 1)
+    // (8 rows x 4 K-blocks per warp instruction: 64 contiguous bytes per row from global memory, 128 contiguous bytes per
+    // quarter-warp in shared memory)
+    const int npieces = (nrows_used + 7) / 8 * 8 * wg2::KBS;
+    float4 buf[wg2::MAX_LD];
+    auto piece = [&](int e, int& row, int& kb) {
+        const int r3 = e & 7, c2 = (e >> 3) & 3, rest = e >> 5;
+        kb = c2 + 4 * (rest & 1);
+        row = ((rest >> 1) << 3) + r3;
+    };
+    // where this thread's pieces go in the operand tiles and come from inside a stage: the same for every stage
+    uint32_t dst_off[wg2::MAX_LD], src_off[wg2::MAX_LD];
+#pragma unroll
+    for (int it = 0; it < wg2::MAX_LD; ++it) {
+        const int e = tid + it * wg2::THREADS;
+        int row, kb;
+        piece(e, row, kb);
+        const bool ok = e < npieces && row < nrows_used;
+        dst_off[it] = ok ? wg2::place(row) + kb * tc::CORE : 0xFFFFFFFFu;
+        src_off[it] = ok ? uint32_t(row * FT + 4 * kb) : 0u;
+    }
+    auto load_stage = [&](int s) {
+        const float* src = fact + size_t(s >> 1) * FACT_ROWS * FT + (s & 1) * wg2::KS;
+        const int nk = min(wg2::KS, n_vis - s * wg2::KS);
+#pragma unroll
+        for (int it = 0; it < wg2::MAX_LD; ++it) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (dst_off[it] != 0xFFFFFFFFu) {
+                v = __ldg(reinterpret_cast<const float4*>(src + src_off[it]));
+                if (nk < wg2::KS) {
+                    // tail stage: the ordinals past n_vis hold whatever the scratch held
+                    const int k0 = int(src_off[it]) & (FT - 1);
+                    if (k0 + 0 >= nk) v.x = 0.f;
+                    if (k0 + 1 >= nk) v.y = 0.f;
+                    if (k0 + 2 >= nk) v.z = 0.f;
+                    if (k0 + 3 >= nk) v.w = 0.f;
+                }
+            }
+            buf[it] = v;
+        }
+    };
+    auto store_stage = [&]() {
+#pragma unroll
+        for (int it = 0; it < wg2::MAX_LD; ++it) {
+            if (dst_off[it] != 0xFFFFFFFFu) {
+                const float4 v = buf[it];
+                const tc::Split4 sp = tc::split4(v.x, v.y, v.z, v.w);
+                *reinterpret_cast<float4*>(s_op + dst_off[it]) = sp.hi;
+                *reinterpret_cast<float4*>(s_op + wg2::HALF + dst_off[it]) = sp.lo;
+            }
+        }
+    };
+
+    const uint64_t d_hi = tc2::make_desc(tc::smem_u32(s_op), wg2::SBO), d_lo = tc2::make_desc(tc::smem_u32(s_op) + wg2::HALF, wg2::SBO);
+    uint32_t phase = 0;
+    bool first = true;
+    int s = blockIdx.x;
+    if (s < nstages) load_stage(s);
+    for (; s < nstages; s += gridDim.x) {
+        if (!first) {                     // the previous stage's MMAs have read the tiles
+            tc::mbar_wait(&s_bar, phase);
+            phase ^= 1u;
+        }
+        store_stage();
+        tc::fence_async_smem();
+        tc::fence_before_sync();
+        __syncthreads();
+        if (tid == 0) {
+            tc::fence_after_sync();
+            const uint32_t acc0 = first ? 0u : 1u;
+#pragma unroll
+            for (int g = 0; g < 3; ++g) {
+                if (g == 2 && !bank) break;
+                const uint32_t a = g == 0 ? wg2::OFF_A1 : g == 1 ? wg2::OFF_A2 : wg2::OFF_A3;
+                const uint32_t b = g == 0 ? wg2::OFF_B1 : g == 1 ? wg2::OFF_B2 : wg2::OFF_B3;
+                const uint32_t d = tmem + (g == 0 ? wg2::COL_D1 : g == 1 ? wg2::COL_D2 : wg2::COL_D3);
+                const uint32_t id = g == 1 ? tc2::idesc(wg2::N2) : tc2::idesc(wg2::N1);
+#pragma unroll
+                for (int j = 0; j < wg2::KS / 8; ++j) {
+                    const uint64_t ka = (a + 2 * j * tc::CORE) >> 4, kb = (b + 2 * j * tc::CORE) >> 4;
+                    tc2::umma_tf32(d, d_hi + ka, d_hi + kb, id, j > 0 ? 1u : acc0);
+                    tc2::umma_tf32(d, d_hi + ka, d_lo + kb, id, 1u);
+                    tc2::umma_tf32(d, d_lo + ka, d_hi + kb, id, 1u);
+                }
+            }
+            tc::umma_commit(&s_bar);
+        }
+        first = false;
+        const int nxt = s + gridDim.x;
+        if (nxt < nstages) load_stage(nxt);          // in flight while the tensor core works
+    }
+    if (first) {                                      // no stage for this CTA (grid <= stages, so this does not happen)
+        tc::fence_before_sync();
+        __syncthreads();
+        if (warp == 0) tc::tmem_dealloc(tmem, wg2::TMEM_COLS);
+        return;
+    }
+    tc::mbar_wait(&s_bar, phase);
+    tc::fence_after_sync();
+
+    // ---- flush: thread = accumulator row (TMEM lane); one atomic per needed element ----
+    const int lq = warp & 3, part = warp >> 2;       // 16 warps: D1 | D2 | D3 | -
+    const int row = lq * 32 + lane;
+    const uint32_t lane_base = tmem + (uint32_t(lq * 32) << 16);
+    float v[32];
+    if (part == 0) {
+        // D1: row = 32 * mlp + hidden unit j; columns = input column i (36: the bias sum)
+        const int m = min(row >> 5, 2), j = row & 31;
+        tc::tmem_ld32(lane_base + wg2::COL_D1, v);
+        if (row < 3 * FEAT) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) atomicAdd(out.w1[m] + j * out.ld1[m] + i, v[i]);
+        }
+        tc::tmem_ld32(lane_base + wg2::COL_D1 + 32, v);       // columns 32..47 are D1's, the rest is not used
+        if (row < 3 * FEAT) {
+#pragma unroll
+            for (int i = 32; i < XDIM; ++i) if (i < out.in1[m]) atomicAdd(out.w1[m] + j * out.ld1[m] + i, v[i - 32]);
+            atomicAdd(out.b1[m] + j, v[wg2::ONES1 - 32]);
+        }
+    } else if (part == 2) {
+        if (bank) {
+            // D3: rows 0..31 = bank hidden unit j (columns 32..35 = [view, dist], 36 = bias), rows 32..34 = logit m (columns 0..31)
+            tc::tmem_ld32(lane_base + wg2::COL_D3, v);
+            if (row >= FEAT && row < FEAT + 3) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(out.bank_w2 + (row - FEAT) * FEAT + i, v[i]);
+            }
+            tc::tmem_ld32(lane_base + wg2::COL_D3 + 32, v);
+            if (row < FEAT) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) atomicAdd(out.bank_w1 + row * 4 + i, v[i]);
+                atomicAdd(out.bank_b1 + row, v[wg2::ONES3 - 32]);
+            } else if (row < FEAT + 3) {
+                atomicAdd(out.bank_b2 + (row - FEAT), v[wg2::ONES3 - 32]);
+            }
+        }
+    } else if (part == 1) {
+        // D2: rows = second-layer output units (opacity 0..9, scale_rot 10..79, colour 80..109); the block of 32 columns of
+        // the same MLP's hidden units is the weight gradient, column 96 the bias sum
+        const int m = row < NOFF ? 0 : row < NOFF + 7 * NOFF ? 1 : 2;
+        const int n = m == 0 ? row : m == 1 ? row - NOFF : row - NOFF - 7 * NOFF;
+        const bool used = row < NOFF + 7 * NOFF + 3 * NOFF;
+#pragma unroll
+        for (int blk = 0; blk < 3; ++blk) {
+            tc::tmem_ld32(lane_base + wg2::COL_D2 + 32 * blk, v);
+            if (used && blk == m) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) atomicAdd(out.w2[m] + n * FEAT + i, v[i]);
+            }
+        }
+        tc::tmem_ld32(lane_base + wg2::COL_D2 + wg2::ONES2, v);
+        if (used) atomicAdd(out.b2[m] + n, v[0]);
+    }
+    tc::fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc(tmem, wg2::TMEM_COLS);
+}
+
 // appearance path: the appearance vector is the same for all anchors, so its gradients follow from
 // db1_colour:  d_app = W1c[:, app cols]^T db1c ;  dW1c[:, app cols] = db1c (x) app ;
 // d app_w = d_app (x) pose ; d app_b = d_app
@@ -1089,6 +1822,27 @@ HostCounts decode_host_counts()
     return out;
 }
 
+// which forward kernel runs: 1 = thread-per-anchor kernel with the first layers on tcgen05, 2 = both layers on
+// tcgen05 over tiles of visible anchors.  SEGS_DECODE_VARIANT in the environment sets the initial value.
+std::atomic<int> g_decode_variant{0};
+int decode_variant()
+{
+    int v = g_decode_variant.load(std::memory_order_relaxed);
+    if (v == 0) {
+        const char* e = getenv("SEGS_DECODE_VARIANT");
+        v = (e && e[0] == '1') ? 1 : 2;
+        g_decode_variant.store(v, std::memory_order_relaxed);
+    }
+    return v;
+}
+
+// the weight-gradient kernel follows the forward variant unless SEGS_DECODE_WGRAD (1 | 2) says otherwise (development)
+int decode_wgrad_variant()
+{
+    static const int env = [] { const char* e = getenv("SEGS_DECODE_WGRAD"); return e ? (e[0] == '1' ? 1 : e[0] == '2' ? 2 : 0) : 0; }();
+    return env ? env : decode_variant();
+}
+
 int check_params(const segs_decode_params* p)
 {
     if (!p) { set_error("decode: params must not be NULL"); return SEGS_ERR_INVALID_ARG; }
@@ -1106,6 +1860,15 @@ int check_params(const segs_decode_params* p)
 }  // namespace segs
 
 using namespace segs;
+
+extern "C" int segs_decode_set_variant(int variant)
+{
+    if (variant != 1 && variant != 2) { set_error("decode: variant must be 1 or 2"); return SEGS_ERR_INVALID_ARG; }
+    g_decode_variant.store(variant, std::memory_order_relaxed);
+    return SEGS_OK;
+}
+
+extern "C" int segs_decode_get_variant(void) { return decode_variant(); }
 
 extern "C" size_t segs_decode_state_bytes(int A)
 {
@@ -1136,11 +1899,24 @@ extern "C" int segs_decode_forward(
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
     const int tiles = (A + DEC_THREADS - 1) / DEC_THREADS;
-    SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
-    decode_forward_kernel<<<std::min(tiles, SM_COUNT * 2), DEC_THREADS, FWD_SMEM, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
-                                                            camera_center, p7, *params, xyz, color, opacity, out_scaling,
-                                                            rot, neural_opacity, mask, st, hc.dev);
-    SEGS_LAUNCH_CHECK();
+    if (decode_variant() == 1) {
+        SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)FWD_SMEM));
+        decode_forward_kernel<<<std::min(tiles, SM_COUNT * 2), DEC_THREADS, FWD_SMEM, stream>>>(A, visible_mask, anchor, anchor_feat, offset, scaling,
+                                                                camera_center, p7, *params, xyz, color, opacity, out_scaling,
+                                                                rot, neural_opacity, mask, st, hc.dev);
+        SEGS_LAUNCH_CHECK();
+    } else {
+        // variant 2: list the visible anchors, then one persistent CTA per SM over tiles of 128 visible anchors
+        if (visible_mask != nullptr) {
+            decode_compact_kernel<<<(A + CMP_TILE - 1) / CMP_TILE, DEC_THREADS, 0, stream>>>(A, visible_mask, st);
+            SEGS_LAUNCH_CHECK();
+        }
+        SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_forward_v2_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)tc2::SMEM));
+        decode_forward_v2_kernel<<<std::min(tiles, SM_COUNT), tc2::THREADS, tc2::SMEM, stream>>>(
+            A, visible_mask == nullptr ? 1 : 0, anchor, anchor_feat, offset, scaling, camera_center, p7, *params, xyz, color,
+            opacity, out_scaling, rot, neural_opacity, mask, st, hc.dev);
+        SEGS_LAUNCH_CHECK();
+    }
     SEGS_CUDA_CHECK(cudaEventRecord(hc.ev, stream));
     SEGS_CUDA_CHECK(cudaEventSynchronize(hc.ev));
     counts[0] = (int)((volatile uint32_t*)hc.host)[0];
@@ -1218,6 +1994,28 @@ extern "C" int segs_decode_backward_ex(
         g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
     SEGS_LAUNCH_CHECK();
 
+    if (decode_wgrad_variant() == 2) {
+        WGradOut o;
+        o.w1[0] = dp->opacity_w1; o.w1[1] = dp->cov_w1; o.w1[2] = dp->color_w1;
+        o.b1[0] = dp->opacity_b1; o.b1[1] = dp->cov_b1; o.b1[2] = dp->color_b1;
+        o.ld1[0] = in_o; o.ld1[1] = in_s; o.ld1[2] = ld_c;
+        o.in1[0] = in_o; o.in1[1] = in_s; o.in1[2] = in_c;         // the appearance columns follow from db1 (appgrad kernel)
+        o.w2[0] = dp->opacity_w2; o.w2[1] = dp->cov_w2; o.w2[2] = dp->color_w2;
+        o.b2[0] = dp->opacity_b2; o.b2[1] = dp->cov_b2; o.b2[2] = dp->color_b2;
+        o.bank_w1 = p.use_feat_bank ? dp->bank_w1 : nullptr; o.bank_b1 = p.use_feat_bank ? dp->bank_b1 : nullptr;
+        o.bank_w2 = p.use_feat_bank ? dp->bank_w2 : nullptr; o.bank_b2 = p.use_feat_bank ? dp->bank_b2 : nullptr;
+        const int nstages = (n_vis + wg2::KS - 1) / wg2::KS;
+        // every CTA pays for zeroing its operand tiles and for one flush: at least four stages each
+        const int grid = std::max(1, std::min((nstages + 3) / 4, SM_COUNT));
+        SEGS_CUDA_CHECK(cudaFuncSetAttribute(decode_wgrad_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)wg2::SMEM));
+        decode_wgrad_tc_kernel<<<grid, wg2::THREADS, wg2::SMEM, stream>>>(fact, n_vis, o, p.use_feat_bank ? FACT_ROWS : F_HB);
+        SEGS_LAUNCH_CHECK();
+        if (p.appearance_dim > 0) {
+            decode_appgrad_kernel<<<1, 32, 0, stream>>>(p, *dp, p7);
+            SEGS_LAUNCH_CHECK();
+        }
+        return SEGS_OK;
+    }
     WJobs jobs;
     int n = 0;
     auto add = [&](int warp, int u0, int np, int v0, float* out, int ld, int nq, int tr = 0) {

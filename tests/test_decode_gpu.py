@@ -75,6 +75,17 @@ def _compare_forward(ref, mine):
     return both, idx_r, idx_m
 
 
+@pytest.fixture(params=[2, 1], ids=["v2_both_layers_tcgen05", "v1_thread_per_anchor"])
+def variant(request):
+    """Run a test on both forward kernels of segs_decode_forward (include/segs_raster.h: segs_decode_set_variant)."""
+    from segs_slam_b200 import _lib
+    lib = _lib.load()
+    before = lib.segs_decode_get_variant()
+    _lib.check(lib.segs_decode_set_variant(request.param))
+    yield request.param
+    _lib.check(lib.segs_decode_set_variant(before))
+
+
 CONFIGS = {
     "bank_app32": do.DecodeConfig(32, True, False, False, False),
     "plain": do.DecodeConfig(0, False, False, False, False),
@@ -85,13 +96,13 @@ CONFIGS = {
 
 @pytest.mark.parametrize("name", list(CONFIGS))
 @pytest.mark.parametrize("A,vis", [(1000, None), (5000, 0.6), (333, 0.1)])
-def test_decode_forward_parity(device, name, A, vis):
+def test_decode_forward_parity(device, variant, name, A, vis):
     _, ref, mine = _run_pair(A, CONFIGS[name], device, vis)
     _compare_forward(ref, mine)
 
 
 @pytest.mark.parametrize("name", list(CONFIGS))
-def test_decode_backward_parity(device, name):
+def test_decode_backward_parity(device, variant, name):
     A = 4000
     model, ref, mine = _run_pair(A, CONFIGS[name], device, 0.7)
     both, idx_r, idx_m = _compare_forward(ref, mine)
@@ -118,7 +129,45 @@ def test_decode_backward_parity(device, name):
         assert bad.float().mean().item() <= 1e-4, (n, bad.sum().item(), ((a - b).abs() / tol).max().item())
 
 
-def test_decode_empty_and_all_invisible(device):
+@pytest.mark.parametrize("A,vis", [(1, None), (127, None), (128, None), (129, None), (1025, None), (2048, 0.5),
+                                   (5000, 0.002), (40_000, 0.2), (1031, 1.1)])
+def test_decode_ragged_tiles(device, variant, A, vis):
+    """Tile edges of both kernels: one anchor, exactly / one over a 128-anchor tile and the 1024-anchor compaction tile,
+    a handful of visible anchors spread over many tiles, a mapping-view visibility (20 %), a mask that is all true."""
+    _, ref, mine = _run_pair(A, CONFIGS["bank_app32"], device, vis, seed=A)
+    _compare_forward(ref, mine)
+
+
+def test_decode_variants_agree(device):
+    """The two forward kernels on the same input: same mask (away from opacity = 0), same rows to 1e-5, and the state
+    they leave makes the backward produce the same gradients (the backward reads ordinals, row starts and masks)."""
+    from segs_slam_b200 import _lib
+    lib = _lib.load()
+    before = lib.segs_decode_get_variant()
+    outs = {}
+    try:
+        for v in (1, 2):
+            _lib.check(lib.segs_decode_set_variant(v))
+            model, _, mine = _run_pair(6000, CONFIGS["bank_app32"], device, 0.35, seed=21)
+            # fixed random weights per output element (a quadratic loss on the unit quaternions would have a zero
+            # gradient made of rounding noise)
+            g = torch.Generator(device="cpu").manual_seed(5)
+            loss = sum((t * torch.randn(t.shape, generator=g).to(device)).sum() for t in mine[:6])
+            grads = torch.autograd.grad(loss, [p for p in model.parameters()], allow_unused=True)
+            outs[v] = (mine, grads)
+    finally:
+        _lib.check(lib.segs_decode_set_variant(before))
+    (m1, g1), (m2, g2) = outs[1], outs[2]
+    _compare_forward(m1, m2)
+    if torch.equal(m1[6], m2[6]):
+        for a, b in zip(g1, g2):
+            if a is None:
+                assert b is None
+                continue
+            assert (a - b).abs().max().item() <= 1e-4 * (b.abs().max().item() + 1e-30)
+
+
+def test_decode_empty_and_all_invisible(device, variant):
     cfg = CONFIGS["bank_app32"]
     model = _adapt(do.synth_model(256, 1200, 680, 600.0, 600.0, 5, cfg, device=device))
     cam = Cam(device)
@@ -128,7 +177,7 @@ def test_decode_empty_and_all_invisible(device):
 
 
 @pytest.mark.slow
-def test_decode_C3_size(device):
+def test_decode_C3_size(device, variant):
     """BASELINE config 3: 200k anchors x 10 offsets; row count, order and values at full size."""
     _, ref, mine = _run_pair(200_000, CONFIGS["bank_app32"], device, None, seed=1003)
     _compare_forward(ref, mine)
