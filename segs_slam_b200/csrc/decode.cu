@@ -799,7 +799,7 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
     uint32_t* s_aid = reinterpret_cast<uint32_t*>(s_dec + tc2::OFF_AID);   // [128] anchor ids
     uint32_t* s_msk = reinterpret_cast<uint32_t*>(s_dec + tc2::OFF_MSK);   // [128] surviving-offset bits
     __shared__ uint32_t s_warp[4];
-    __shared__ uint32_t s_tile[2], s_row_base, s_tmem;
+    __shared__ uint32_t s_tile[2], s_look[tc2::THREADS / 32], s_tmem;
     __shared__ __align__(8) uint64_t s_bar;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lq = warp & 3, grp = warp >> 2;          // TMEM lane quarter this warp may read; column group
@@ -869,11 +869,38 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
     const uint64_t dA2_hi = tc2::make_desc(tc::smem_u32(sA2_hi), tc2::SBO2), dA2_lo = tc2::make_desc(tc::smem_u32(sA2_lo), tc2::SBO2);
     const uint64_t dB2_hi = tc2::make_desc(tc::smem_u32(sB2_hi), tc2::SBO2), dB2_lo = tc2::make_desc(tc::smem_u32(sB2_lo), tc2::SBO2);
 
+    // raw inputs of this thread's (anchor slot, quarter) for one tile: fetched one tile ahead, so their global-memory
+    // latency hides behind the previous tile's second layer and row assembly
+    struct Raw { size_t a; float ax, ay, az; float4 f0, f1; float fa[8], fb[8]; };
+    auto fetch = [&](uint32_t t) {
+        Raw r;
+        const int i = tid >> 2, q = tid & 3;
+        const uint32_t o0 = t * tc::TM, na = min((uint32_t)tc::TM, n_vis - o0);
+        const uint32_t oi = o0 + ((uint32_t)i < na ? (uint32_t)i : 0u);     // idle slots read the tile's first anchor
+        r.a = identity ? size_t(oi) : size_t(st.anchor_index[oi]);
+        r.ax = __ldg(anchor + 3 * r.a); r.ay = __ldg(anchor + 3 * r.a + 1); r.az = __ldg(anchor + 3 * r.a + 2);
+        const float* frow = anchor_feat + r.a * FEAT;
+        r.f0 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q);
+        r.f1 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q + 1);
+        if (use_bank) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                r.fa[jj] = __ldg(frow + 4 * jj);                      // feat[4 (j mod 8)],  j = 8q + jj
+                r.fb[jj] = __ldg(frow + 16 * (q & 1) + 2 * jj);       // feat[2 (j mod 16)]
+            }
+        }
+        return r;
+    };
+    Raw raw;
+    bool have_raw = false;
+
     for (int it = 0;; ++it) {
         const uint32_t tile = s_tile[it & 1];
         if (tile >= ntiles) break;
+        if (tid == 0) s_tile[(it + 1) & 1] = atomicAdd(st.counters, 1u);   // next ticket (read after the barriers below)
         const uint32_t ord0 = tile * tc::TM;                               // visible ordinal of row 0
         const uint32_t n_act = min((uint32_t)tc::TM, n_vis - ord0);
+        if (!have_raw) raw = fetch(tile);
 
         // ---- D1-D3: MLP input rows -> layer-1 A operand (hi / lo).  4 threads per anchor: thread q owns the
         //      feature columns / bank hidden units [8q, 8q + 8) ----
@@ -882,17 +909,14 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             const int i = tid >> 2, q = tid & 3;
             const bool act = (uint32_t)i < n_act;        // idle slots compute on the tile's first anchor (the shuffles
             {                                            // below need every lane) and store nothing
-                const uint32_t oi = ord0 + (act ? (uint32_t)i : 0u);
-                const size_t a = identity ? size_t(oi) : size_t(st.anchor_index[oi]);
-                const float ax = __ldg(anchor + 3 * a), ay = __ldg(anchor + 3 * a + 1), az = __ldg(anchor + 3 * a + 2);
+                const size_t a = raw.a;
+                const float ax = raw.ax, ay = raw.ay, az = raw.az;
                 const float vx = ax - __ldg(cam), vy = ay - __ldg(cam + 1), vz = az - __ldg(cam + 2);
                 const float dist = sqrtf(vx * vx + vy * vy + vz * vz);
                 const float ux = vx / dist, uy = vy / dist, uz = vz / dist;
-                const float* frow = anchor_feat + a * FEAT;
                 float x[8];
                 {
-                    const float4 t0 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q);
-                    const float4 t1 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q + 1);
+                    const float4 t0 = raw.f0, t1 = raw.f1;
                     x[0] = t0.x; x[1] = t0.y; x[2] = t0.z; x[3] = t0.w; x[4] = t1.x; x[5] = t1.y; x[6] = t1.z; x[7] = t1.w;
                 }
                 if (use_bank) {
@@ -917,11 +941,7 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
                     const float w0 = e0 / den, w1 = e1 / den, w2 = e2 / den;
                     // feat'[j] = feat[4 (j mod 8)] w0 + feat[2 (j mod 16)] w1 + feat[j] w2   (:241-248; repeat = tiling)
 #pragma unroll
-                    for (int jj = 0; jj < 8; ++jj) {
-                        const float fa = __ldg(frow + 4 * jj);                      // j mod 8 = jj
-                        const float fb = __ldg(frow + 16 * (q & 1) + 2 * jj);       // j mod 16 = 8 (q & 1) + jj
-                        x[jj] = fa * w0 + fb * w1 + x[jj] * w2;
-                    }
+                    for (int jj = 0; jj < 8; ++jj) x[jj] = raw.fa[jj] * w0 + raw.fb[jj] * w1 + x[jj] * w2;
                 }
                 auto put4 = [&](int kb, float v0, float v1, float v2, float v3) {
                     if (!act) return;
@@ -960,6 +980,12 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
                 tc2::umma_tf32(tmem, dA1_lo + ko, dB1_hi + ko, id, 1u);
             }
             tc::umma_commit(&s_bar);
+        }
+        {
+            // the next tile's raw inputs go out now; nothing reads them before the next iteration
+            const uint32_t nxt = s_tile[(it + 1) & 1];
+            have_raw = nxt < ntiles;
+            if (have_raw) raw = fetch(nxt);
         }
         tc::mbar_wait(&s_bar, phase);
         phase ^= 1u;
@@ -1005,7 +1031,6 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
                 }
             }
             tc::umma_commit(&s_bar);
-            s_tile[(it + 1) & 1] = atomicAdd(st.counters, 1u);   // next ticket: its latency hides behind the epilogue
         }
         tc::mbar_wait(&s_bar, phase);
         phase ^= 1u;
@@ -1067,61 +1092,102 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             s_row[tid] = woff + inc - cnt;
         }
         if (tid == 0) s_row[tc::TM] = n_rows;                 // sentinel for the search below
-        if (tid < 32) {
-            // ---- order across CTAs: exclusive prefix of the surviving rows (the visible prefix is ord0) ----
-            const uint32_t rb = lookback(st.look_row, tile, n_rows, lane);
-            if (lane == 0) {
-                s_row_base = rb;
-                if (tile == ntiles - 1 && host_counts != nullptr) {
-                    host_counts[0] = n_vis;
-                    host_counts[1] = rb + n_rows;
-                    __threadfence_system();
-                }
-            }
-        } else {
-            // ---- per-anchor outputs, coalesced over (ordinal, offset) ----
-            for (uint32_t e = tid - 32; e < n_act * NOFF; e += tc2::THREADS - 32) {
-                const uint32_t k = e / NOFF, o = e - k * NOFF;
-                neural_opacity[size_t(ord0) * NOFF + e] = s_rec[k * REC_W + 9 + o];
-                out_mask[size_t(ord0) * NOFF + e] = (unsigned char)((s_msk[k] >> o) & 1u);
-            }
+        // ---- order across CTAs: exclusive prefix of the surviving rows (the visible prefix is ord0).  The tiles of a
+        //      wave publish their aggregates at about the same time, so a look-back walks ~148 flags to the previous
+        //      wave's prefix: the 16 warps read 16 windows of 32 flags AT ONCE (one global-memory round trip instead of
+        //      five in a row) and every thread combines them ----
+        volatile uint32_t* look = st.look_row;
+        if (tid == 0) look[tile] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | n_rows;
+        // per-anchor outputs, coalesced over (ordinal, offset) — in flight while the flags are polled
+        for (uint32_t e = tid; e < n_act * NOFF; e += tc2::THREADS) {
+            const uint32_t k = e / NOFF, o = e - k * NOFF;
+            neural_opacity[size_t(ord0) * NOFF + e] = s_rec[k * REC_W + 9 + o];
+            out_mask[size_t(ord0) * NOFF + e] = (unsigned char)((s_msk[k] >> o) & 1u);
         }
-        __syncthreads();
-        const size_t row_base = s_row_base;
+        uint32_t excl = 0;
+        if (tile != 0) {
+            for (int newest = (int)tile - 1;; newest -= tc2::THREADS) {
+                const int t = newest - 32 * warp - lane;
+                uint32_t w = FLAG_PREFIX;                            // before tile 0: prefix 0
+                if (t >= 0) {
+                    do { w = look[t]; } while ((w & FLAG_MASK) == 0u);
+                }
+                const unsigned pref = __ballot_sync(FULL, (w & FLAG_MASK) == FLAG_PREFIX);
+                const int stop = __ffs(pref) - 1;
+                const uint32_t v = (stop < 0 || lane <= stop) ? (w & ~FLAG_MASK) : 0u;
+                const uint32_t sum = __reduce_add_sync(FULL, v);
+                if (lane == 0) s_look[warp] = sum | (stop >= 0 ? 0x80000000u : 0u);
+                __syncthreads();
+                bool done = false;
+#pragma unroll
+                for (int q = 0; q < tc2::THREADS / 32; ++q) {
+                    if (!done) {
+                        const uint32_t x = s_look[q];
+                        excl += x & 0x7FFFFFFFu;
+                        done = (x & 0x80000000u) != 0u;
+                    }
+                }
+                if (done) break;
+                __syncthreads();                                     // s_look is rewritten in the next round
+            }
+            if (tid == 0) look[tile] = FLAG_PREFIX | (excl + n_rows);
+        }
+        if (tid == 0 && tile == ntiles - 1 && host_counts != nullptr) {
+            host_counts[0] = n_vis;
+            host_counts[1] = excl + n_rows;
+            __threadfence_system();
+        }
+        const size_t row_base = excl;
+        __syncthreads();                 // s_row / s_msk of this tile are complete for every thread (tile 0 polls nothing)
         if ((uint32_t)tid < n_act) {
             if (identity) st.anchor_index[ord0 + tid] = s_aid[tid];
             st.row_start[ord0 + tid] = (uint32_t)(row_base + s_row[tid]);
             st.mask_bits[ord0 + tid] = s_msk[tid];
         }
 
-        // ---- D5: thread = output row; consecutive threads write consecutive rows ----
-        for (uint32_t r = tid; r < n_rows; r += tc2::THREADS) {
+        // ---- D5: thread = output row; consecutive threads write consecutive rows.  Two rows per thread are located
+        //      (binary search, offset load) before either is assembled, so their latencies overlap ----
+        struct RowRef { int lo, o; float ox, oy, oz; };
+        auto locate = [&](uint32_t r) {
+            RowRef rr;
             int lo = 0, hi = tc::TM;                     // s_row[lo] <= r < s_row[hi]
 #pragma unroll
             for (int step = 0; step < 7; ++step) {
                 const int mid = (lo + hi) >> 1;
                 if (mid > lo && s_row[mid] <= r) lo = mid; else if (mid > lo) hi = mid;
             }
-            const float* rec = s_rec + lo * REC_W;
-            const int o = __fns(s_msk[lo], 0, (int)(r - s_row[lo]) + 1);     // the (r - first)-th surviving offset
-            const size_t aid = s_aid[lo];
-            const float* sr = s_out + lo * tc2::OUT_W + tc2::O_COV + 7 * o;
-            const float* sc = s_out + lo * tc2::OUT_W + tc2::O_COL + 3 * o;
+            rr.lo = lo;
+            rr.o = __fns(s_msk[lo], 0, (int)(r - s_row[lo]) + 1);     // the (r - first)-th surviving offset
+            const float* off = offset + (size_t(s_aid[lo]) * NOFF + rr.o) * 3;
+            rr.ox = __ldg(off); rr.oy = __ldg(off + 1); rr.oz = __ldg(off + 2);
+            return rr;
+        };
+        auto emit = [&](uint32_t r, const RowRef& rr) {
+            const float* rec = s_rec + rr.lo * REC_W;
+            const float* sr = s_out + rr.lo * tc2::OUT_W + tc2::O_COV + 7 * rr.o;
+            const float* sc = s_out + rr.lo * tc2::OUT_W + tc2::O_COL + 3 * rr.o;
             const size_t orow = row_base + r;
-            const float* off = offset + (aid * NOFF + o) * 3;
             // xyz = anchor + offset * scaling[:3]; scaling = scaling[3:] * sigmoid(sr[:3]); rot = normalize(sr[3:7])
-            out_xyz[3 * orow] = rec[0] + __ldg(off) * rec[3];
-            out_xyz[3 * orow + 1] = rec[1] + __ldg(off + 1) * rec[4];
-            out_xyz[3 * orow + 2] = rec[2] + __ldg(off + 2) * rec[5];
+            out_xyz[3 * orow] = rec[0] + rr.ox * rec[3];
+            out_xyz[3 * orow + 1] = rec[1] + rr.oy * rec[4];
+            out_xyz[3 * orow + 2] = rec[2] + rr.oz * rec[5];
             out_scaling[3 * orow] = rec[6] * sigmoidf_(sr[0]);
             out_scaling[3 * orow + 1] = rec[7] * sigmoidf_(sr[1]);
             out_scaling[3 * orow + 2] = rec[8] * sigmoidf_(sr[2]);
             const float q0 = sr[3], q1 = sr[4], q2 = sr[5], q3 = sr[6];
             const float nrm = fmaxf(sqrtf(q0 * q0 + q1 * q1 + q2 * q2 + q3 * q3), 1e-12f);
             *reinterpret_cast<float4*>(out_rot + 4 * orow) = make_float4(q0 / nrm, q1 / nrm, q2 / nrm, q3 / nrm);
-            out_opacity[orow] = rec[9 + o];
+            out_opacity[orow] = rec[9 + rr.o];
 #pragma unroll
             for (int k = 0; k < 3; ++k) out_color[3 * orow + k] = sigmoidf_(sc[k]);
+        };
+        for (uint32_t r0 = tid; r0 < n_rows; r0 += 2 * tc2::THREADS) {
+            const uint32_t r1 = r0 + tc2::THREADS;
+            const bool two = r1 < n_rows;
+            const RowRef a0 = locate(r0);
+            const RowRef a1 = locate(two ? r1 : r0);
+            emit(r0, a0);
+            if (two) emit(r1, a1);
         }
         __syncthreads();                 // the tile is done with s_out / s_rec / s_row / s_aid / s_msk; next ticket is visible
     }
@@ -1606,7 +1672,7 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
     // (8 rows x 4 K-blocks per warp instruction: 64 contiguous bytes per row from global memory, 128 contiguous bytes per
     // quarter-warp in shared memory)
     const int npieces = (nrows_used + 7) / 8 * 8 * wg2::KBS;
-    float4 buf[wg2::MAX_LD];
+    float4 buf0[wg2::MAX_LD], buf1[wg2::MAX_LD];      // two stages of loads in flight
     auto piece = [&](int e, int& row, int& kb) {
         const int r3 = e & 7, c2 = (e >> 3) & 3, rest = e >> 5;
         kb = c2 + 4 * (rest & 1);
@@ -1623,7 +1689,7 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
         dst_off[it] = ok ? wg2::place(row) + kb * tc::CORE : 0xFFFFFFFFu;
         src_off[it] = ok ? uint32_t(row * FT + 4 * kb) : 0u;
     }
-    auto load_stage = [&](int s) {
+    auto load_stage = [&](float4 (&buf)[wg2::MAX_LD], int s) {
         const float* src = fact + size_t(s >> 1) * FACT_ROWS * FT + (s & 1) * wg2::KS;
         const int nk = min(wg2::KS, n_vis - s * wg2::KS);
 #pragma unroll
@@ -1643,7 +1709,7 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
             buf[it] = v;
         }
     };
-    auto store_stage = [&]() {
+    auto store_stage = [&](const float4 (&buf)[wg2::MAX_LD]) {
 #pragma unroll
         for (int it = 0; it < wg2::MAX_LD; ++it) {
             if (dst_off[it] != 0xFFFFFFFFu) {
@@ -1658,14 +1724,16 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
     const uint64_t d_hi = tc2::make_desc(tc::smem_u32(s_op), wg2::SBO), d_lo = tc2::make_desc(tc::smem_u32(s_op) + wg2::HALF, wg2::SBO);
     uint32_t phase = 0;
     bool first = true;
-    int s = blockIdx.x;
-    if (s < nstages) load_stage(s);
-    for (; s < nstages; s += gridDim.x) {
-        if (!first) {                     // the previous stage's MMAs have read the tiles
+    const int G = gridDim.x;
+    // one stage: wait for the previous stage's MMAs (they read the tiles), split + store this stage's rows, refill the
+    // register buffer with the stage two ahead, hand the tiles to the tensor core
+    auto stage = [&](float4 (&buf)[wg2::MAX_LD], int s) {
+        if (!first) {
             tc::mbar_wait(&s_bar, phase);
             phase ^= 1u;
         }
-        store_stage();
+        store_stage(buf);
+        if (s + 2 * G < nstages) load_stage(buf, s + 2 * G);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
@@ -1690,8 +1758,15 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
             tc::umma_commit(&s_bar);
         }
         first = false;
-        const int nxt = s + gridDim.x;
-        if (nxt < nstages) load_stage(nxt);          // in flight while the tensor core works
+    };
+    {
+        const int s0 = blockIdx.x;
+        if (s0 < nstages) load_stage(buf0, s0);
+        if (s0 + G < nstages) load_stage(buf1, s0 + G);
+        for (int s = s0; s < nstages; s += 2 * G) {
+            stage(buf0, s);
+            if (s + G < nstages) stage(buf1, s + G);
+        }
     }
     if (first) {                                      // no stage for this CTA (grid <= stages, so this does not happen)
         tc::fence_before_sync();
