@@ -66,6 +66,8 @@ struct SW : SWF {
     float w1[3][FEAT][XDIM];     // first 35(+dist) input columns, zero padded
 };
 
+constexpr int O2_W = NOFF + 7 * NOFF + 3 * NOFF;   // second-layer outputs per anchor: opacity(10) | scale_rot(70) | colour(30)
+
 // opaque state shared by forward and backward
 struct DecodeState {
     uint32_t* counters;       // [8]: 0 ticket
@@ -74,6 +76,8 @@ struct DecodeState {
     uint32_t* anchor_index;   // [A] anchor id of every visible ordinal
     uint32_t* row_start;      // [A] first output row of every visible ordinal
     uint32_t* mask_bits;      // [A] surviving-offset bits of every visible ordinal
+    float* hidden;            // [A][96]  relu(layer 1) of the three MLPs per visible ordinal   } written by forward variant 2
+    float* out2;              // [A][110] tanh(opacity) | scale_rot | colour pre-activations     } (counters[3] = 1), read by backward
     size_t zero_bytes;        // counters + look words
     static DecodeState carve(char* base, size_t A, size_t* bytes) {
         Carver c(base);
@@ -86,6 +90,8 @@ struct DecodeState {
         s.anchor_index = c.take<uint32_t>(A);
         s.row_start = c.take<uint32_t>(A);
         s.mask_bits = c.take<uint32_t>(A);
+        s.hidden = c.take<float>(A * size_t(3 * FEAT));
+        s.out2 = c.take<float>(A * size_t(O2_W));
         if (bytes) *bytes = c.used(base) + 128;
         return s;
     }
@@ -811,6 +817,7 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
     if (tid == 0) {
         tc::mbar_init(&s_bar, 1);
         s_tile[0] = atomicAdd(st.counters, 1u);
+        if (blockIdx.x == 0) st.counters[3] = 1u;                          // hidden / out2 are valid for the backward
         if (ntiles == 0 && blockIdx.x == 0 && host_counts != nullptr) {    // nothing visible: nobody else reports
             host_counts[0] = 0;
             host_counts[1] = 0;
@@ -1002,12 +1009,17 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             unsigned char* a_lo = sA2_lo + grp * tc2::A2_BYTES;
 #pragma unroll
             for (int kb = 0; kb < tc2::KB2; ++kb) {
-                const float v0 = fmaxf(h[4 * kb] + sw.b1[grp][4 * kb], 0.f), v1 = fmaxf(h[4 * kb + 1] + sw.b1[grp][4 * kb + 1], 0.f);
-                const float v2 = fmaxf(h[4 * kb + 2] + sw.b1[grp][4 * kb + 2], 0.f), v3 = fmaxf(h[4 * kb + 3] + sw.b1[grp][4 * kb + 3], 0.f);
+                const float p0 = h[4 * kb] + sw.b1[grp][4 * kb], p1 = h[4 * kb + 1] + sw.b1[grp][4 * kb + 1];
+                const float p2 = h[4 * kb + 2] + sw.b1[grp][4 * kb + 2], p3 = h[4 * kb + 3] + sw.b1[grp][4 * kb + 3];
+                const float v0 = fmaxf(p0, 0.f), v1 = fmaxf(p1, 0.f), v2 = fmaxf(p2, 0.f), v3 = fmaxf(p3, 0.f);
                 const tc::Split4 sp = tc::split4(v0, v1, v2, v3);
                 const uint32_t off = tc2::canon2(row, 4 * kb);
                 *reinterpret_cast<float4*>(a_hi + off) = sp.hi;
                 *reinterpret_cast<float4*>(a_lo + off) = sp.lo;
+                // the backward reads the PRE-activations back instead of recomputing the layer (128 contiguous bytes per
+                // thread); it redoes a unit in FP32 only where the sign of the ReLU argument is within the 3xTF32 error
+                if ((uint32_t)row < n_act)
+                    *reinterpret_cast<float4*>(st.hidden + size_t(ord0 + row) * (3 * FEAT) + grp * FEAT + 4 * kb) = make_float4(p0, p1, p2, p3);
             }
         }
         tc::fence_async_smem();
@@ -1066,6 +1078,7 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
         for (uint32_t e = tid; e < n_act * NOFF; e += tc2::THREADS) {
             const uint32_t k = e / NOFF, o = e - k * NOFF;
             const float t = tanhf(s_out[k * tc2::OUT_W + tc2::O_OP + o]);
+            s_out[k * tc2::OUT_W + tc2::O_OP + o] = t;
             s_rec[k * REC_W + 9 + o] = t;
             if (t > 0.0f) atomicOr(&s_msk[k], 1u << o);
         }
@@ -1103,6 +1116,11 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             const uint32_t k = e / NOFF, o = e - k * NOFF;
             neural_opacity[size_t(ord0) * NOFF + e] = s_rec[k * REC_W + 9 + o];
             out_mask[size_t(ord0) * NOFF + e] = (unsigned char)((s_msk[k] >> o) & 1u);
+        }
+        // second-layer outputs for the backward (which then has no dot product of the forward left to redo)
+        for (uint32_t e = tid; e < n_act * O2_W; e += tc2::THREADS) {
+            const uint32_t k = e / O2_W, c = e - k * O2_W;
+            st.out2[size_t(ord0) * O2_W + e] = s_out[k * tc2::OUT_W + c];
         }
         uint32_t excl = 0;
         if (tile != 0) {
@@ -1232,6 +1250,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     // SEGS_DECODE_ATOMIC: several views accumulate into the same arrays from concurrent streams
     const bool atomic_mode = (flags & SEGS_DECODE_ATOMIC) != 0;
     auto accum = [&](float* dst, float v) { if (atomic_mode) atomicAdd(dst, v); else *dst += v; };
+    const bool cached = st.counters[3] != 0u;
   for (size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x; ordinal < (size_t)n_vis;
        ordinal += size_t(gridDim.x) * DEC_THREADS) {
     const size_t a = st.anchor_index[ordinal];
@@ -1245,6 +1264,42 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     build_input(sw, p.use_feat_bank != 0, anchor_feat + a * FEAT, in, x, bankw);
 #pragma unroll
     for (int i = 0; i < XDIM; ++i) put(F_X + i, x[i]);
+    // forward variant 2 left relu(layer 1) and the second-layer outputs of every visible ordinal: read them back instead
+    // of redoing 3 x 32 x 36 + ~2600 FMAs per anchor
+    const float* hid = st.hidden + ordinal * size_t(3 * FEAT);
+    const float* o2 = st.out2 + ordinal * size_t(O2_W);
+    auto hidden_of = [&](int mlp, float (&h)[FEAT]) {
+        if (cached) {
+#pragma unroll
+            for (int q = 0; q < FEAT / 4; ++q) {
+                const float4 t = __ldg(reinterpret_cast<const float4*>(hid + mlp * FEAT) + q);
+                h[4 * q] = t.x; h[4 * q + 1] = t.y; h[4 * q + 2] = t.z; h[4 * q + 3] = t.w;
+            }
+            // ReLU'(0): a pre-activation within the tensor-core split's error of zero (~3e-6; a few units in 1e5 are
+            // inside this band) is redone as the FP32 FMA chain, so the derivative mask is the one an FP32 forward takes
+            uint32_t amb = 0;
+#pragma unroll
+            for (int j = 0; j < FEAT; ++j) if (fabsf(h[j]) < 2e-5f) amb |= 1u << j;
+            while (amb != 0u) {                              // rare: one iteration per ambiguous unit
+                const int j = __ffs(amb) - 1;
+                amb &= amb - 1u;
+                float acc = sw.b1[mlp][j];
+                const float4* wrow = reinterpret_cast<const float4*>(sw.w1[mlp][j]);
+#pragma unroll
+                for (int q = 0; q < XDIM / 4; ++q) {
+                    const float4 w4 = wrow[q];
+                    acc = fmaf(w4.x, x[4 * q], acc); acc = fmaf(w4.y, x[4 * q + 1], acc);
+                    acc = fmaf(w4.z, x[4 * q + 2], acc); acc = fmaf(w4.w, x[4 * q + 3], acc);
+                }
+#pragma unroll
+                for (int jj = 0; jj < FEAT; ++jj) h[jj] = jj == j ? acc : h[jj];
+            }
+#pragma unroll
+            for (int j = 0; j < FEAT; ++j) h[j] = fmaxf(h[j], 0.f);
+        } else {
+            layer1(sw.w1[mlp], sw.b1[mlp], x, h);
+        }
+    };
 
     float dx[XDIM];
 #pragma unroll
@@ -1274,13 +1329,13 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     // ---- opacity MLP ----
     {
         float h[FEAT], dh[FEAT];
-        layer1(sw.w1[0], sw.b1[0], x, h);
+        hidden_of(0, h);
 #pragma unroll
         for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
         size_t r = row0;
 #pragma unroll 1
         for (int o = 0; o < NOFF; ++o) {
-            const float t = tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+            const float t = cached ? __ldg(o2 + o) : tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
             float g = g_nop ? __ldg(g_nop + ordinal * NOFF + o) : 0.f;
             if ((m >> o) & 1u) { g += __ldg(g_opacity + r); ++r; }
             const float dz = g * (1.f - t * t);
@@ -1292,7 +1347,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     // ---- covariance MLP + geometry assembly ----
     {
         float h[FEAT], dh[FEAT];
-        layer1(sw.w1[1], sw.b1[1], x, h);
+        hidden_of(1, h);
 #pragma unroll
         for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
         size_t r = row0;
@@ -1307,7 +1362,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
             }
             float sr[7], dsr[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) sr[k] = dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+            for (int k = 0; k < 7; ++k) sr[k] = cached ? __ldg(o2 + NOFF + 7 * o + k) : dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
             const float gx = __ldg(g_xyz + 3 * r), gy = __ldg(g_xyz + 3 * r + 1), gz = __ldg(g_xyz + 3 * r + 2);
             const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
                         oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
@@ -1351,7 +1406,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     // ---- colour MLP ----
     {
         float h[FEAT], dh[FEAT];
-        layer1(sw.w1[2], sw.b1[2], x, h);
+        hidden_of(2, h);
 #pragma unroll
         for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
         size_t r = row0;
@@ -1364,7 +1419,7 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
             }
 #pragma unroll
             for (int k = 0; k < 3; ++k) {
-                const float c = sigmoidf_(dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
+                const float c = sigmoidf_(cached ? __ldg(o2 + 8 * NOFF + 3 * o + k) : dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
                 const float dz = __ldg(g_color + 3 * r + k) * c * (1.f - c);
                 put(F_D2C + 3 * o + k, dz);
                 axpy32(sw.w2c[3 * o + k], dz, dh);
