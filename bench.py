@@ -1001,9 +1001,24 @@ def _c3_decode_raster(impl, dev):
     for _ in range(5):
         run()
     ms = timed(run, 20, sync)
-    return {"workload": "200k anchors x 10 offsets (appearance 32, feature bank) at 1200x680: prefilter + decode + rasterize, "
-                        "forward + backward (tensor-level API)", "gaussians": info.get("P"), "ms": _stats(ms),
-            "mean_ms": round(float(np.mean(ms)), 4), "iterations_per_s": round(1e3 / float(np.mean(ms)), 2)}
+    out = {"workload": "200k anchors x 10 offsets (appearance 32, feature bank) at 1200x680: prefilter + decode + rasterize, "
+                       "forward + backward (tensor-level API)", "gaussians": info.get("P"), "ms": _stats(ms),
+           "mean_ms": round(float(np.mean(ms)), 4), "iterations_per_s": round(1e3 / float(np.mean(ms)), 2)}
+    if impl == "ours":
+        # the decode kernels of round 1 (thread = anchor, first layers on tcgen05 only) beside the default (variant 2: both
+        # layers and the weight gradients on tcgen05, tiles of visible anchors); include/segs_raster.h: segs_decode_set_variant
+        from segs_slam_b200 import _lib
+        lib = _lib.load()
+        out["decode_variant"] = int(lib.segs_decode_get_variant())
+        try:
+            _lib.check(lib.segs_decode_set_variant(1))
+            for _ in range(3):
+                run()
+            ms1 = timed(run, 20, sync)
+            out["decode_variant_1"] = {"ms": _stats(ms1), "mean_ms": round(float(np.mean(ms1)), 4)}
+        finally:
+            _lib.check(lib.segs_decode_set_variant(out["decode_variant"]))
+    return out
 
 
 def _bind_to_gpu_numa_node(local_rank):

@@ -3,6 +3,8 @@ bench.py on B200s) carry every key the measurement contract names, with consiste
 import json
 import os
 
+import pytest
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -10,8 +12,9 @@ def _line(name):
     return json.loads(open(os.path.join(ROOT, "profiles", name)).read().strip().splitlines()[-1])
 
 
-def test_ours_line_has_the_contract_keys():
-    d = _line("r2_bench_final.json")
+@pytest.mark.parametrize("name", ["r2_bench_final.json", "r2b_bench_final.json"])
+def test_ours_line_has_the_contract_keys(name):
+    d = _line(name)
     for k in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
               "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline", "mapping",
               "batch", "configs"):
@@ -45,8 +48,10 @@ def test_ours_line_has_the_contract_keys():
     assert d["batch"]["views_in_flight_per_gpu"] > 1 and d["batch"]["value"] > d["value"]
 
 
-def test_reference_line_is_marked_and_comparable():
-    o, r = _line("r2_bench_final.json"), _line("r2_bench_reference_final.json")
+@pytest.mark.parametrize("ours,ref", [("r2_bench_final.json", "r2_bench_reference_final.json"),
+                                      ("r2b_bench_final.json", "r2b_bench_reference_final.json")])
+def test_reference_line_is_marked_and_comparable(ours, ref):
+    o, r = _line(ours), _line(ref)
     assert r["impl"] == "reference" and r["gpu_launches"] == 0
     for k in ("metric", "unit", "higher_is_better", "steps", "warmup"):
         assert r[k] == o[k]
@@ -66,3 +71,12 @@ def test_eight_gpu_line_meets_the_scaling_target():
     assert e["n_gpus"] == 8 and e["scaling"] == "weak"
     assert e["value"] / (8 * o["value"]) >= 0.85                        # north_star: >= 0.85 at 8 GPUs
     assert e["mapping"]["value"] / (8 * o["mapping"]["value"]) >= 0.85
+
+
+def test_decode_variant_2_is_the_default_and_not_slower():
+    """Round 2b: the C3 sub-line is measured with the default decode kernels (variant 2: both MLP layers and the weight
+    gradients on tcgen05) and, beside it, with round 1's (variant 1); the mapping step moved with them."""
+    d, before = _line("r2b_bench_final.json"), _line("r2_bench_final.json")
+    c3 = d["configs"]["C3"]
+    assert c3["decode_variant"] == 2 and c3["mean_ms"] < c3["decode_variant_1"]["mean_ms"]
+    assert d["mapping"]["value"] > before["mapping"]["value"]

@@ -12,6 +12,7 @@ COLS = [
     ("dram__throughput.avg.pct_of_peak_sustained_elapsed", "dram %"),
     ("sm__throughput.avg.pct_of_peak_sustained_elapsed", "sm %"),
     ("smsp__issue_active.avg.pct_of_peak_sustained_active", "issue %"),
+    ("sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_elapsed", "tensor pipe %"),
     ("smsp__thread_inst_executed_per_inst_executed.ratio", "thr/inst"),
     ("sm__warps_active.avg.pct_of_peak_sustained_active", "occ %"),
     ("launch__registers_per_thread", "regs"),
