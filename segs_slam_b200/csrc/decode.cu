@@ -1233,6 +1233,11 @@ constexpr int F_DLOG = F_DPREB + FEAT;     // bank logit gradients [3]
 constexpr int F_CAT = F_DLOG + 3;          // bank input [view, dist] [4]
 constexpr int FACT_ROWS = F_CAT + 4;       // 409
 
+// CACHED: the forward left the layer activations in the state (variant 2).  Both instantiations are launched; the one
+// that does not match the flag the forward wrote returns at once (the host cannot read the flag without a sync).  The
+// split keeps each instantiation's code small: with both paths in one kernel the SASS was 820 KB and a quarter of the
+// warp-stall samples were instruction-cache misses.
+template <bool CACHED>
 __global__ void __launch_bounds__(DEC_THREADS, 4)
 decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float* __restrict__ anchor_feat,
                        const float* __restrict__ offset, const float* __restrict__ scaling,
@@ -1243,14 +1248,16 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
                        float* __restrict__ d_anchor, float* __restrict__ d_feat, float* __restrict__ d_offset,
                        float* __restrict__ d_scaling, float* __restrict__ fact, const int flags)
 {
+    if ((st.counters[3] != 0u) != CACHED) return;
+    constexpr bool cached = CACHED;
     __shared__ __align__(16) SW sw;
     stage_weights(sw, p, pose);
-    // SEGS_DECODE_ACCUMULATE: every anchor row is owned by exactly one thread, so `+=` needs no atomics
+    // SEGS_DECODE_ACCUMULATE: add to the caller's arrays.  Every anchor row is owned by exactly one thread of one view, so
+    // the sums do not depend on atomicity; RED.ADD is used either way because it does not wait for the old value
+    // (`*dst += v` stalled on a cold global load per element: 17 % of the kernel's stall samples in a mapping view).
+    // SEGS_DECODE_ATOMIC (several views accumulate concurrently) therefore needs nothing extra here.
     const bool acc_mode = (flags & SEGS_DECODE_ACCUMULATE) != 0;
-    // SEGS_DECODE_ATOMIC: several views accumulate into the same arrays from concurrent streams
-    const bool atomic_mode = (flags & SEGS_DECODE_ATOMIC) != 0;
-    auto accum = [&](float* dst, float v) { if (atomic_mode) atomicAdd(dst, v); else *dst += v; };
-    const bool cached = st.counters[3] != 0u;
+    auto accum = [&](float* dst, float v) { atomicAdd(dst, v); };
   for (size_t ordinal = size_t(blockIdx.x) * DEC_THREADS + threadIdx.x; ordinal < (size_t)n_vis;
        ordinal += size_t(gridDim.x) * DEC_THREADS) {
     const size_t a = st.anchor_index[ordinal];
@@ -1326,107 +1333,100 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
         }
     };
 
-    // ---- opacity MLP ----
-    {
+    // ---- the three MLPs, one after the other in ONE loop body: the code they share (activations, ReLU backward, the
+    //      first layer's transposed product) exists once in the instruction stream ----
+#pragma unroll 1
+    for (int mlp = 0; mlp < 3; ++mlp) {
         float h[FEAT], dh[FEAT];
-        hidden_of(0, h);
+        hidden_of(mlp, h);
 #pragma unroll
         for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
-        size_t r = row0;
+        if (mlp == 0) {
+            // opacity MLP
+            size_t r = row0;
 #pragma unroll 1
-        for (int o = 0; o < NOFF; ++o) {
-            const float t = cached ? __ldg(o2 + o) : tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
-            float g = g_nop ? __ldg(g_nop + ordinal * NOFF + o) : 0.f;
-            if ((m >> o) & 1u) { g += __ldg(g_opacity + r); ++r; }
-            const float dz = g * (1.f - t * t);
-            put(F_D2O + o, dz);
-            axpy32(sw.w2o[o], dz, dh);
-        }
-        finish_mlp(0, h, dh);
-    }
-    // ---- covariance MLP + geometry assembly ----
-    {
-        float h[FEAT], dh[FEAT];
-        hidden_of(1, h);
-#pragma unroll
-        for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
-        size_t r = row0;
+            for (int o = 0; o < NOFF; ++o) {
+                const float t = cached ? __ldg(o2 + o) : tanhf(dot32(sw.w2o[o], sw.b2o[o], h));
+                float g = g_nop ? __ldg(g_nop + ordinal * NOFF + o) : 0.f;
+                if ((m >> o) & 1u) { g += __ldg(g_opacity + r); ++r; }
+                const float dz = g * (1.f - t * t);
+                put(F_D2O + o, dz);
+                axpy32(sw.w2o[o], dz, dh);
+            }
+        } else if (mlp == 1) {
+            // covariance MLP + geometry assembly
+            size_t r = row0;
 #pragma unroll 1
-        for (int o = 0; o < NOFF; ++o) {
-            float* dof = d_offset + (a * NOFF + o) * 3;
-            if (!((m >> o) & 1u)) {
+            for (int o = 0; o < NOFF; ++o) {
+                float* dof = d_offset + (a * NOFF + o) * 3;
+                if (!((m >> o) & 1u)) {
 #pragma unroll
-                for (int k = 0; k < 7; ++k) put(F_D2S + 7 * o + k, 0.f);
-                if (!acc_mode) { dof[0] = 0.f; dof[1] = 0.f; dof[2] = 0.f; }
-                continue;
-            }
-            float sr[7], dsr[7];
-#pragma unroll
-            for (int k = 0; k < 7; ++k) sr[k] = cached ? __ldg(o2 + NOFF + 7 * o + k) : dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
-            const float gx = __ldg(g_xyz + 3 * r), gy = __ldg(g_xyz + 3 * r + 1), gz = __ldg(g_xyz + 3 * r + 2);
-            const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
-                        oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
-            // xyz = anchor + offset * s[:3]
-            dax += gx; day += gy; daz += gz;
-            if (acc_mode) { accum(dof, gx * in.s[0]); accum(dof + 1, gy * in.s[1]); accum(dof + 2, gz * in.s[2]); }
-            else { dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2]; }
-            ds[0] = fmaf(gx, ox, ds[0]); ds[1] = fmaf(gy, oy, ds[1]); ds[2] = fmaf(gz, oz, ds[2]);
-            // scaling = s[3:] * sigmoid(sr[:3])
-#pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float sg = sigmoidf_(sr[k]);
-                const float g = __ldg(g_scaling + 3 * r + k);
-                ds[3 + k] = fmaf(g, sg, ds[3 + k]);
-                dsr[k] = g * in.s[3 + k] * sg * (1.f - sg);
-            }
-            // rot = v / max(|v|, 1e-12)
-            {
-                const float4 g = __ldg(reinterpret_cast<const float4*>(g_rot + 4 * r));
-                const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
-                const float nrm = sqrtf(n2);
-                if (nrm > 1e-12f) {
-                    const float inv = 1.f / nrm;
-                    const float u0 = sr[3] * inv, u1 = sr[4] * inv, u2 = sr[5] * inv, u3 = sr[6] * inv;
-                    const float ug = u0 * g.x + u1 * g.y + u2 * g.z + u3 * g.w;
-                    dsr[3] = (g.x - u0 * ug) * inv; dsr[4] = (g.y - u1 * ug) * inv;
-                    dsr[5] = (g.z - u2 * ug) * inv; dsr[6] = (g.w - u3 * ug) * inv;
-                } else {
-                    dsr[3] = g.x * 1e12f; dsr[4] = g.y * 1e12f; dsr[5] = g.z * 1e12f; dsr[6] = g.w * 1e12f;
+                    for (int k = 0; k < 7; ++k) put(F_D2S + 7 * o + k, 0.f);
+                    if (!acc_mode) { dof[0] = 0.f; dof[1] = 0.f; dof[2] = 0.f; }
+                    continue;
                 }
-            }
+                float sr[7], dsr[7];
 #pragma unroll
-            for (int k = 0; k < 7; ++k) {
-                put(F_D2S + 7 * o + k, dsr[k]);
-                axpy32(sw.w2s[7 * o + k], dsr[k], dh);
-            }
-            ++r;
-        }
-        finish_mlp(1, h, dh);
-    }
-    // ---- colour MLP ----
-    {
-        float h[FEAT], dh[FEAT];
-        hidden_of(2, h);
+                for (int k = 0; k < 7; ++k) sr[k] = cached ? __ldg(o2 + NOFF + 7 * o + k) : dot32(sw.w2s[7 * o + k], sw.b2s[7 * o + k], h);
+                const float gx = __ldg(g_xyz + 3 * r), gy = __ldg(g_xyz + 3 * r + 1), gz = __ldg(g_xyz + 3 * r + 2);
+                const float ox = __ldg(offset + (a * NOFF + o) * 3), oy = __ldg(offset + (a * NOFF + o) * 3 + 1),
+                            oz = __ldg(offset + (a * NOFF + o) * 3 + 2);
+                // xyz = anchor + offset * s[:3]
+                dax += gx; day += gy; daz += gz;
+                if (acc_mode) { accum(dof, gx * in.s[0]); accum(dof + 1, gy * in.s[1]); accum(dof + 2, gz * in.s[2]); }
+                else { dof[0] = gx * in.s[0]; dof[1] = gy * in.s[1]; dof[2] = gz * in.s[2]; }
+                ds[0] = fmaf(gx, ox, ds[0]); ds[1] = fmaf(gy, oy, ds[1]); ds[2] = fmaf(gz, oz, ds[2]);
+                // scaling = s[3:] * sigmoid(sr[:3])
 #pragma unroll
-        for (int j = 0; j < FEAT; ++j) dh[j] = 0.f;
-        size_t r = row0;
+                for (int k = 0; k < 3; ++k) {
+                    const float sg = sigmoidf_(sr[k]);
+                    const float g = __ldg(g_scaling + 3 * r + k);
+                    ds[3 + k] = fmaf(g, sg, ds[3 + k]);
+                    dsr[k] = g * in.s[3 + k] * sg * (1.f - sg);
+                }
+                // rot = v / max(|v|, 1e-12)
+                {
+                    const float4 g = __ldg(reinterpret_cast<const float4*>(g_rot + 4 * r));
+                    const float n2 = sr[3] * sr[3] + sr[4] * sr[4] + sr[5] * sr[5] + sr[6] * sr[6];
+                    const float nrm = sqrtf(n2);
+                    if (nrm > 1e-12f) {
+                        const float inv = 1.f / nrm;
+                        const float u0 = sr[3] * inv, u1 = sr[4] * inv, u2 = sr[5] * inv, u3 = sr[6] * inv;
+                        const float ug = u0 * g.x + u1 * g.y + u2 * g.z + u3 * g.w;
+                        dsr[3] = (g.x - u0 * ug) * inv; dsr[4] = (g.y - u1 * ug) * inv;
+                        dsr[5] = (g.z - u2 * ug) * inv; dsr[6] = (g.w - u3 * ug) * inv;
+                    } else {
+                        dsr[3] = g.x * 1e12f; dsr[4] = g.y * 1e12f; dsr[5] = g.z * 1e12f; dsr[6] = g.w * 1e12f;
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 7; ++k) {
+                    put(F_D2S + 7 * o + k, dsr[k]);
+                    axpy32(sw.w2s[7 * o + k], dsr[k], dh);
+                }
+                ++r;
+            }
+        } else {
+            // colour MLP
+            size_t r = row0;
 #pragma unroll 1
-        for (int o = 0; o < NOFF; ++o) {
-            if (!((m >> o) & 1u)) {
+            for (int o = 0; o < NOFF; ++o) {
+                if (!((m >> o) & 1u)) {
 #pragma unroll
-                for (int k = 0; k < 3; ++k) put(F_D2C + 3 * o + k, 0.f);
-                continue;
-            }
+                    for (int k = 0; k < 3; ++k) put(F_D2C + 3 * o + k, 0.f);
+                    continue;
+                }
 #pragma unroll
-            for (int k = 0; k < 3; ++k) {
-                const float c = sigmoidf_(cached ? __ldg(o2 + 8 * NOFF + 3 * o + k) : dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
-                const float dz = __ldg(g_color + 3 * r + k) * c * (1.f - c);
-                put(F_D2C + 3 * o + k, dz);
-                axpy32(sw.w2c[3 * o + k], dz, dh);
+                for (int k = 0; k < 3; ++k) {
+                    const float c = sigmoidf_(cached ? __ldg(o2 + 8 * NOFF + 3 * o + k) : dot32(sw.w2c[3 * o + k], sw.b2c[3 * o + k], h));
+                    const float dz = __ldg(g_color + 3 * r + k) * c * (1.f - c);
+                    put(F_D2C + 3 * o + k, dz);
+                    axpy32(sw.w2c[3 * o + k], dz, dh);
+                }
+                ++r;
             }
-            ++r;
         }
-        finish_mlp(2, h, dh);
+        finish_mlp(mlp, h, dh);
     }
 
     // ---- inputs: dx = [d feat'(32), d view(3), d dist] ----
@@ -1479,12 +1479,11 @@ decode_backward_kernel(int n_vis, const float* __restrict__ anchor, const float*
     for (int q = 0; q < FEAT / 4; ++q) {
         float4* dst = reinterpret_cast<float4*>(d_feat + a * FEAT) + q;
         float4 v = make_float4(df[4 * q], df[4 * q + 1], df[4 * q + 2], df[4 * q + 3]);
-        if (acc_mode && atomic_mode) {
+        if (acc_mode) {
             float* d1 = reinterpret_cast<float*>(dst);
             atomicAdd(d1, v.x); atomicAdd(d1 + 1, v.y); atomicAdd(d1 + 2, v.z); atomicAdd(d1 + 3, v.w);
             continue;
         }
-        if (acc_mode) { const float4 o4 = *dst; v.x += o4.x; v.y += o4.y; v.z += o4.z; v.w += o4.w; }
         *dst = v;
     }
 
@@ -2119,10 +2118,18 @@ extern "C" int segs_decode_backward_ex(
     DecodeState st = DecodeState::carve(const_cast<char*>(state), A, nullptr);
     Pose7 p7;
     for (int i = 0; i < 7; ++i) p7.v[i] = pose[i];
-    decode_backward_kernel<<<std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 4), DEC_THREADS, 0, stream>>>(
-        n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
-        g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
-    SEGS_LAUNCH_CHECK();
+    {
+        // which of the two runs is decided on the device by the flag the forward left in the state; the other returns at once
+        const int grid = std::min((n_vis + DEC_THREADS - 1) / DEC_THREADS, SM_COUNT * 4);
+        decode_backward_kernel<true><<<grid, DEC_THREADS, 0, stream>>>(
+            n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
+            g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
+        SEGS_LAUNCH_CHECK();
+        decode_backward_kernel<false><<<grid, DEC_THREADS, 0, stream>>>(
+            n_vis, anchor, anchor_feat, offset, scaling, camera_center, p7, p, st, g_xyz, g_color, g_opacity, g_scaling, g_rot,
+            g_neural_opacity, d_anchor, d_anchor_feat, d_offset, d_scaling, fact, flags);
+        SEGS_LAUNCH_CHECK();
+    }
 
     if (decode_wgrad_variant() == 2) {
         WGradOut o;
