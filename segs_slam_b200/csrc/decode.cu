@@ -1640,51 +1640,55 @@ decode_wgrad_kernel(const float* __restrict__ fact, int n_vis, const WJobs jobs,
 // =======================================================================================
 // dW[p][q] = sum over anchors k of U[k][p] V[k][q] is a contraction over the ANCHOR index, and kernel 1 already stores
 // every factor feature-major ([row][64 ordinals]) — K-major operands as they lie.  Per stage of 32 ordinals the rows
-// are loaded once (coalesced 16-byte loads, 100 % sector use), split hi / lo (3xTF32) in registers and stored as the
-// no-swizzle core-matrix tiles of three products that accumulate in TMEM over ALL stages of the persistent CTA:
-//   D1[128 x 48]  = [dpre_opacity | dpre_cov | dpre_colour](96 rows)  x  [x(36) | 1]      -> dW1 of the three MLPs, db1
-//   D2[128 x 112] = [d2_opacity(10) | d2_scale_rot(70) | d2_colour(30)] x [h_opacity | h_cov | h_colour | 1]
-//                                                      -> the diagonal blocks are dW2 of the three MLPs, the 1-column db2
-//   D3[128 x 48]  = [dpre_bank(32) | dlogit(3)]  x  [h_bank(32) | view,dist(4) | 1]        -> feature-bank dW1, dW2, biases
-// (a row of ones in the B operand turns the bias sums into one more output column).  36 tcgen05.mma per stage replace
-// ~2300 FFMA + 580 LDS.128 per thread; the next stage's rows are in flight (registers) while the MMAs run.  One flush
-// per CTA: tcgen05.ld + one atomic per needed element, as in variant 1.
+// are loaded once (coalesced 16-byte loads, 100 % sector use, two stages in flight in registers), split hi / lo (3xTF32)
+// and stored as the no-swizzle core-matrix tiles of two products that accumulate in TMEM over ALL stages of the CTA:
+//   D1[128 x 48]  = [dpre_opacity | dpre_cov | dpre_colour (96) | dpre_bank (32)]  x  [x (36) | 1 | view,dist (4)]
+//                   rows < 96: dW1 of the three MLPs and (the 1-column) db1; rows 96..127: feature-bank dW1 / db1
+//   D2[128 x 144] = [d2_opacity (10) | d2_scale_rot (70) | d2_colour (30) | dlogit (3)]  x  [h_opacity | h_cov | h_colour | 1 | h_bank]
+//                   rows < 110: the diagonal blocks are dW2 of the three MLPs, the 1-column db2; rows 110..112: bank dW2 / db2
+// (a row of ones in the B operand turns the bias sums into one more output column; products nobody needs are computed
+// and ignored — the tensor pipe is far from busy).  The operand tiles are double-buffered (2 x 112 KB of shared memory):
+// the split + store of stage s+1 does not wait for the MMAs of stage s.
+// 24 tcgen05.mma per stage replace ~2300 FFMA + 580 LDS.128 per thread.  One flush per CTA: tcgen05.ld + one atomic
+// per needed element, as in variant 1.
 namespace wg2 {
 
 constexpr int THREADS = 512;
 constexpr int KS = 32;                          // ordinals per stage = MMA K per stage (4 instructions of K = 8)
 constexpr int KBS = KS / 4;                     // 16-byte K-blocks per operand row
 constexpr uint32_t SBO = KBS * tc::CORE;        // 1024
-constexpr int N1 = 48, N2 = 112, N3 = 48;
+constexpr int N1 = 48, N2 = 144;
 constexpr int A_T = 128 * KS * 4;               // bytes of a 128-row operand tile (hi or lo)
 constexpr int OFF_A1 = 0;
 constexpr int OFF_B1 = OFF_A1 + A_T;
 constexpr int OFF_A2 = OFF_B1 + N1 * KS * 4;
 constexpr int OFF_B2 = OFF_A2 + A_T;
-constexpr int OFF_A3 = OFF_B2 + N2 * KS * 4;
-constexpr int OFF_B3 = OFF_A3 + A_T;
-constexpr int HALF = OFF_B3 + N3 * KS * 4;      // 75776: the lo tiles follow the hi tiles
-constexpr int SMEM = 2 * HALF;
-constexpr int COL_D1 = 0, COL_D2 = 64, COL_D3 = 192;
+constexpr int HALF = OFF_B2 + N2 * KS * 4;      // 57344: the lo tiles follow the hi tiles
+constexpr int BUF = 2 * HALF;                   // one operand buffer (hi + lo)
+constexpr int SMEM = 2 * BUF;                   // two buffers
+constexpr int COL_D1 = 0, COL_D2 = 64;
 constexpr int TMEM_COLS = 256;
-constexpr int ONES1 = XDIM, ONES2 = 3 * FEAT, ONES3 = FEAT + 4;       // B-tile rows that hold 1.0
-constexpr int MAX_LD = ((FACT_ROWS + 7) / 8 * 8 * KBS + THREADS - 1) / THREADS;   // 16-byte loads per thread and stage (13)
-static_assert(HALF % 1024 == 0 && SMEM <= 227 * 1024, "decode wgrad v2: shared memory");
+// tile rows: B1 = x (0..35) | ones (36) | view,dist (37..40);  A1 = dpre (0..95) | dpre_bank (96..127)
+//            B2 = h (0..95) | ones (96) | h_bank (97..128);    A2 = d2 (0..109) | dlogit (110..112)
+constexpr int ONES1 = XDIM, CAT1 = XDIM + 1, ONES2 = 3 * FEAT, HB2 = 3 * FEAT + 1, BANK_A1 = 3 * FEAT, LOG_A2 = O2_W;
+constexpr int MAX_LD = ((FACT_ROWS + 7) / 8 * 8 * KBS + THREADS - 1) / THREADS;   // 16-byte loads per thread and stage (7)
+static_assert(HALF % 1024 == 0 && SMEM + 1024 <= 227 * 1024, "decode wgrad v2: shared memory");
+static_assert(CAT1 + 4 <= N1 && HB2 + FEAT <= N2 && LOG_A2 + 3 <= 128, "decode wgrad v2: tile rows");
 
 __device__ __forceinline__ uint32_t canon(int row, int k) {
     return uint32_t(((row >> 3) * KBS + (k >> 2)) * tc::CORE + (row & 7) * 16 + (k & 3) * 4);
 }
-// factor row -> byte offset of its row 0 / column 0 element inside the hi half (tile base + row placement)
+// factor row -> byte offset of its K-block 0 inside the hi half of a buffer (tile base + row placement)
 __device__ __forceinline__ uint32_t place(int r) {
     int base, trow;
     if (r < F_H) { base = OFF_B1; trow = r - F_X; }
     else if (r < F_DPRE) { base = OFF_B2; trow = r - F_H; }
     else if (r < F_D2O) { base = OFF_A1; trow = r - F_DPRE; }
     else if (r < F_HB) { base = OFF_A2; trow = r - F_D2O; }
-    else if (r < F_DPREB) { base = OFF_B3; trow = r - F_HB; }
-    else if (r < F_DLOG) { base = OFF_A3; trow = r - F_DPREB; }
-    else if (r < F_CAT) { base = OFF_A3; trow = FEAT + (r - F_DLOG); }
-    else { base = OFF_B3; trow = FEAT + (r - F_CAT); }
+    else if (r < F_DPREB) { base = OFF_B2; trow = HB2 + (r - F_HB); }
+    else if (r < F_DLOG) { base = OFF_A1; trow = BANK_A1 + (r - F_DPREB); }
+    else if (r < F_CAT) { base = OFF_A2; trow = LOG_A2 + (r - F_DLOG); }
+    else { base = OFF_B1; trow = CAT1 + (r - F_CAT); }
     return uint32_t(base) + uint32_t(((trow >> 3) * KBS) * tc::CORE + (trow & 7) * 16);
 }
 
@@ -1701,21 +1705,20 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
 {
     extern __shared__ __align__(1024) unsigned char s_op[];
     __shared__ uint32_t s_tmem;
-    __shared__ __align__(8) uint64_t s_bar;
+    __shared__ __align__(8) uint64_t s_bar[2];
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int nstages = (n_vis + wg2::KS - 1) / wg2::KS;
     const bool bank = out.bank_w1 != nullptr;
 
     if (warp == 0) tc::tmem_alloc(&s_tmem, wg2::TMEM_COLS);
-    if (tid == 0) tc::mbar_init(&s_bar, 1);
-    // padding rows stay zero for the whole kernel; the rows of ones are written once
+    if (tid == 0) { tc::mbar_init(&s_bar[0], 1); tc::mbar_init(&s_bar[1], 1); }
+    // padding rows stay zero for the whole kernel; the rows of ones are written once (hi halves of both buffers)
     for (int e = tid; e < wg2::SMEM / 16; e += wg2::THREADS) reinterpret_cast<float4*>(s_op)[e] = make_float4(0.f, 0.f, 0.f, 0.f);
     __syncthreads();
-    if (tid < 3 * wg2::KS) {
+    if (tid < 4 * wg2::KS) {
         const int which = tid / wg2::KS, k = tid % wg2::KS;
-        const int base = which == 0 ? wg2::OFF_B1 : which == 1 ? wg2::OFF_B2 : wg2::OFF_B3;
-        const int row = which == 0 ? wg2::ONES1 : which == 1 ? wg2::ONES2 : wg2::ONES3;
-        *reinterpret_cast<float*>(s_op + base + wg2::canon(row, k)) = 1.0f;
+        const int base = (which >> 1) * wg2::BUF + ((which & 1) ? wg2::OFF_B2 : wg2::OFF_B1);
+        *reinterpret_cast<float*>(s_op + base + wg2::canon((which & 1) ? wg2::ONES2 : wg2::ONES1, k)) = 1.0f;
     }
     tc::fence_before_sync();
     __syncthreads();
@@ -1724,25 +1727,19 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
 
     // this thread's 16-byte pieces of a stage: piece e -> factor row (e >> 6) * 8 + (e & 7), K-block ((e >> 3) & 3) + 4 * ((e >> 5) & 1)
     // (8 rows x 4 K-blocks per warp instruction: 64 contiguous bytes per row from global memory, 128 contiguous bytes per
-    // quarter-warp in shared memory)
+    // quarter-warp in shared memory).  Where a piece goes and where it comes from is the same for every stage.
     const int npieces = (nrows_used + 7) / 8 * 8 * wg2::KBS;
-    float4 buf0[wg2::MAX_LD], buf1[wg2::MAX_LD];      // two stages of loads in flight
-    auto piece = [&](int e, int& row, int& kb) {
-        const int r3 = e & 7, c2 = (e >> 3) & 3, rest = e >> 5;
-        kb = c2 + 4 * (rest & 1);
-        row = ((rest >> 1) << 3) + r3;
-    };
-    // where this thread's pieces go in the operand tiles and come from inside a stage: the same for every stage
     uint32_t dst_off[wg2::MAX_LD], src_off[wg2::MAX_LD];
 #pragma unroll
     for (int it = 0; it < wg2::MAX_LD; ++it) {
         const int e = tid + it * wg2::THREADS;
-        int row, kb;
-        piece(e, row, kb);
+        const int r3 = e & 7, c2 = (e >> 3) & 3, rest = e >> 5;
+        const int kb = c2 + 4 * (rest & 1), row = ((rest >> 1) << 3) + r3;
         const bool ok = e < npieces && row < nrows_used;
         dst_off[it] = ok ? wg2::place(row) + kb * tc::CORE : 0xFFFFFFFFu;
         src_off[it] = ok ? uint32_t(row * FT + 4 * kb) : 0u;
     }
+    float4 buf0[wg2::MAX_LD], buf1[wg2::MAX_LD];      // two stages of loads in flight
     auto load_stage = [&](float4 (&buf)[wg2::MAX_LD], int s) {
         const float* src = fact + size_t(s >> 1) * FACT_ROWS * FT + (s & 1) * wg2::KS;
         const int nk = min(wg2::KS, n_vis - s * wg2::KS);
@@ -1763,81 +1760,82 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
             buf[it] = v;
         }
     };
-    auto store_stage = [&](const float4 (&buf)[wg2::MAX_LD]) {
+    auto store_stage = [&](const float4 (&buf)[wg2::MAX_LD], unsigned char* dst) {
 #pragma unroll
         for (int it = 0; it < wg2::MAX_LD; ++it) {
             if (dst_off[it] != 0xFFFFFFFFu) {
                 const float4 v = buf[it];
                 const tc::Split4 sp = tc::split4(v.x, v.y, v.z, v.w);
-                *reinterpret_cast<float4*>(s_op + dst_off[it]) = sp.hi;
-                *reinterpret_cast<float4*>(s_op + wg2::HALF + dst_off[it]) = sp.lo;
+                *reinterpret_cast<float4*>(dst + dst_off[it]) = sp.hi;
+                *reinterpret_cast<float4*>(dst + wg2::HALF + dst_off[it]) = sp.lo;
             }
         }
     };
 
-    const uint64_t d_hi = tc2::make_desc(tc::smem_u32(s_op), wg2::SBO), d_lo = tc2::make_desc(tc::smem_u32(s_op) + wg2::HALF, wg2::SBO);
-    uint32_t phase = 0;
-    bool first = true;
+    const uint64_t d_base = tc2::make_desc(tc::smem_u32(s_op), wg2::SBO);
+    uint32_t ph0 = 0, ph1 = 0;
     const int G = gridDim.x;
-    // one stage: wait for the previous stage's MMAs (they read the tiles), split + store this stage's rows, refill the
-    // register buffer with the stage two ahead, hand the tiles to the tensor core
-    auto stage = [&](float4 (&buf)[wg2::MAX_LD], int s) {
-        if (!first) {
-            tc::mbar_wait(&s_bar, phase);
-            phase ^= 1u;
+    int nth = 0;                                          // stages this CTA has issued
+    // one stage: (the MMAs that read this operand buffer two stages ago have finished — checked, rarely waited for)
+    // split + store the rows, refill the register buffer with the stage two ahead, hand the tiles to the tensor core
+    auto stage = [&](float4 (&buf)[wg2::MAX_LD], int s, const int b) {
+        if (nth >= 2) {
+            if (b == 0) { tc::mbar_wait(&s_bar[0], ph0); ph0 ^= 1u; } else { tc::mbar_wait(&s_bar[1], ph1); ph1 ^= 1u; }
         }
-        store_stage(buf);
+        store_stage(buf, s_op + b * wg2::BUF);
         if (s + 2 * G < nstages) load_stage(buf, s + 2 * G);
         tc::fence_async_smem();
         tc::fence_before_sync();
         __syncthreads();
         if (tid == 0) {
             tc::fence_after_sync();
-            const uint32_t acc0 = first ? 0u : 1u;
+            const uint32_t acc0 = nth > 0 ? 1u : 0u;
+            const uint64_t d_hi = d_base + uint64_t((b * wg2::BUF) >> 4), d_lo = d_hi + uint64_t(wg2::HALF >> 4);
 #pragma unroll
-            for (int g = 0; g < 3; ++g) {
-                if (g == 2 && !bank) break;
-                const uint32_t a = g == 0 ? wg2::OFF_A1 : g == 1 ? wg2::OFF_A2 : wg2::OFF_A3;
-                const uint32_t b = g == 0 ? wg2::OFF_B1 : g == 1 ? wg2::OFF_B2 : wg2::OFF_B3;
-                const uint32_t d = tmem + (g == 0 ? wg2::COL_D1 : g == 1 ? wg2::COL_D2 : wg2::COL_D3);
-                const uint32_t id = g == 1 ? tc2::idesc(wg2::N2) : tc2::idesc(wg2::N1);
+            for (int g = 0; g < 2; ++g) {
+                const uint32_t a = g == 0 ? wg2::OFF_A1 : wg2::OFF_A2;
+                const uint32_t bb = g == 0 ? wg2::OFF_B1 : wg2::OFF_B2;
+                const uint32_t d = tmem + (g == 0 ? wg2::COL_D1 : wg2::COL_D2);
+                const uint32_t id = g == 0 ? tc2::idesc(wg2::N1) : tc2::idesc(wg2::N2);
 #pragma unroll
                 for (int j = 0; j < wg2::KS / 8; ++j) {
-                    const uint64_t ka = (a + 2 * j * tc::CORE) >> 4, kb = (b + 2 * j * tc::CORE) >> 4;
+                    const uint64_t ka = (a + 2 * j * tc::CORE) >> 4, kb = (bb + 2 * j * tc::CORE) >> 4;
                     tc2::umma_tf32(d, d_hi + ka, d_hi + kb, id, j > 0 ? 1u : acc0);
                     tc2::umma_tf32(d, d_hi + ka, d_lo + kb, id, 1u);
                     tc2::umma_tf32(d, d_lo + ka, d_hi + kb, id, 1u);
                 }
             }
-            tc::umma_commit(&s_bar);
+            tc::umma_commit(&s_bar[b]);
         }
-        first = false;
+        ++nth;
     };
     {
         const int s0 = blockIdx.x;
         if (s0 < nstages) load_stage(buf0, s0);
         if (s0 + G < nstages) load_stage(buf1, s0 + G);
         for (int s = s0; s < nstages; s += 2 * G) {
-            stage(buf0, s);
-            if (s + G < nstages) stage(buf1, s + G);
+            stage(buf0, s, 0);
+            if (s + G < nstages) stage(buf1, s + G, 1);
         }
     }
-    if (first) {                                      // no stage for this CTA (grid <= stages, so this does not happen)
+    if (nth == 0) {                                   // no stage for this CTA (grid <= stages, so this does not happen)
         tc::fence_before_sync();
         __syncthreads();
         if (warp == 0) tc::tmem_dealloc(tmem, wg2::TMEM_COLS);
         return;
     }
-    tc::mbar_wait(&s_bar, phase);
+    // the commit of the last stage covers every MMA issued before it
+    if ((nth - 1) & 1) tc::mbar_wait(&s_bar[1], ph1); else tc::mbar_wait(&s_bar[0], ph0);
     tc::fence_after_sync();
 
     // ---- flush: thread = accumulator row (TMEM lane); one atomic per needed element ----
-    const int lq = warp & 3, part = warp >> 2;       // 16 warps: D1 | D2 | D3 | -
+    const int lq = warp & 3, part = warp >> 2;       // 16 warps: D1 | D2 | - | -
     const int row = lq * 32 + lane;
     const uint32_t lane_base = tmem + (uint32_t(lq * 32) << 16);
     float v[32];
     if (part == 0) {
-        // D1: row = 32 * mlp + hidden unit j; columns = input column i (36: the bias sum)
+        // D1 rows < 96: row = 32 * mlp + hidden unit j, columns = input column i (36: the bias sum);
+        //    rows 96..127: bank hidden unit j = row - 96, columns 37..40 = [view, dist], 36 = the bias sum
         const int m = min(row >> 5, 2), j = row & 31;
         tc::tmem_ld32(lane_base + wg2::COL_D1, v);
         if (row < 3 * FEAT) {
@@ -1849,30 +1847,19 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
 #pragma unroll
             for (int i = 32; i < XDIM; ++i) if (i < out.in1[m]) atomicAdd(out.w1[m] + j * out.ld1[m] + i, v[i - 32]);
             atomicAdd(out.b1[m] + j, v[wg2::ONES1 - 32]);
-        }
-    } else if (part == 2) {
-        if (bank) {
-            // D3: rows 0..31 = bank hidden unit j (columns 32..35 = [view, dist], 36 = bias), rows 32..34 = logit m (columns 0..31)
-            tc::tmem_ld32(lane_base + wg2::COL_D3, v);
-            if (row >= FEAT && row < FEAT + 3) {
+        } else if (bank) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) atomicAdd(out.bank_w2 + (row - FEAT) * FEAT + i, v[i]);
-            }
-            tc::tmem_ld32(lane_base + wg2::COL_D3 + 32, v);
-            if (row < FEAT) {
-#pragma unroll
-                for (int i = 0; i < 4; ++i) atomicAdd(out.bank_w1 + row * 4 + i, v[i]);
-                atomicAdd(out.bank_b1 + row, v[wg2::ONES3 - 32]);
-            } else if (row < FEAT + 3) {
-                atomicAdd(out.bank_b2 + (row - FEAT), v[wg2::ONES3 - 32]);
-            }
+            for (int i = 0; i < 4; ++i) atomicAdd(out.bank_w1 + j * 4 + i, v[wg2::CAT1 - 32 + i]);
+            atomicAdd(out.bank_b1 + j, v[wg2::ONES1 - 32]);
         }
     } else if (part == 1) {
-        // D2: rows = second-layer output units (opacity 0..9, scale_rot 10..79, colour 80..109); the block of 32 columns of
-        // the same MLP's hidden units is the weight gradient, column 96 the bias sum
+        // D2 rows < 110 = second-layer output units (opacity 0..9, scale_rot 10..79, colour 80..109): the block of 32
+        //    columns of the same MLP's hidden units is the weight gradient, column 96 the bias sum;
+        //    rows 110..112 = bank logit m: columns 97..128 = bank hidden units, column 96 the bias sum
         const int m = row < NOFF ? 0 : row < NOFF + 7 * NOFF ? 1 : 2;
         const int n = m == 0 ? row : m == 1 ? row - NOFF : row - NOFF - 7 * NOFF;
-        const bool used = row < NOFF + 7 * NOFF + 3 * NOFF;
+        const bool used = row < O2_W;
+        const bool logit = bank && row >= wg2::LOG_A2 && row < wg2::LOG_A2 + 3;
 #pragma unroll
         for (int blk = 0; blk < 3; ++blk) {
             tc::tmem_ld32(lane_base + wg2::COL_D2 + 32 * blk, v);
@@ -1881,8 +1868,15 @@ decode_wgrad_tc_kernel(const float* __restrict__ fact, int n_vis, const WGradOut
                 for (int i = 0; i < 32; ++i) atomicAdd(out.w2[m] + n * FEAT + i, v[i]);
             }
         }
-        tc::tmem_ld32(lane_base + wg2::COL_D2 + wg2::ONES2, v);
+        tc::tmem_ld32(lane_base + wg2::COL_D2 + wg2::ONES2, v);        // columns 96..127: bias sum, bank hidden 0..30
         if (used) atomicAdd(out.b2[m] + n, v[0]);
+        if (logit) {
+            atomicAdd(out.bank_b2 + (row - wg2::LOG_A2), v[0]);
+#pragma unroll
+            for (int i = 0; i < FEAT - 1; ++i) atomicAdd(out.bank_w2 + (row - wg2::LOG_A2) * FEAT + i, v[1 + i]);
+        }
+        tc::tmem_ld32(lane_base + wg2::COL_D2 + wg2::ONES2 + 32, v);   // column 128: bank hidden 31
+        if (logit) atomicAdd(out.bank_w2 + (row - wg2::LOG_A2) * FEAT + FEAT - 1, v[0]);
     }
     tc::fence_before_sync();
     __syncthreads();
