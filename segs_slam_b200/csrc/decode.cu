@@ -403,11 +403,10 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
 __device__ __forceinline__ float tf32_hi(float v) { return __uint_as_float(__float_as_uint(v) & 0xFFFFE000u); }
 // round-to-nearest TF32 (the tensor core ignores the 13 low mantissa bits of its operands, i.e. truncates: rounding
 // both parts of a hi / lo split here halves the representation error of the split and removes its bias)
-__device__ __forceinline__ float tf32_rn(float v) {
-    uint32_t r;
-    asm("cvt.rna.tf32.f32 %0, %1;\n" : "=r"(r) : "f"(v));
-    return __uint_as_float(r);
-}
+// (cvt.rna.tf32.f32 does exactly this, but on the conversion pipe at a fraction of the ALU rate: with 56 - 64 conversions
+// per thread and tile it showed up as `math` throttle stalls; add-half-and-mask is two full-rate integer instructions.
+// Round to nearest, ties away from zero, as .rna.)
+__device__ __forceinline__ float tf32_rn(float v) { return __uint_as_float((__float_as_uint(v) + 0x1000u) & 0xFFFFE000u); }
 struct Split4 { float4 hi, lo; };
 __device__ __forceinline__ Split4 split4(float v0, float v1, float v2, float v3) {
     Split4 s;
