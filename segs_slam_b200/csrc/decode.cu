@@ -823,6 +823,33 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             __threadfence_system();
         }
     }
+    __syncthreads();                                   // s_tile[0]
+    const bool use_bank = p.use_feat_bank != 0;
+    // raw inputs of this thread's (anchor slot, quarter) for one tile: fetched one tile ahead, so their global-memory
+    // latency hides behind the previous tile's second layer and row assembly (the first tile's: behind the weight staging)
+    struct Raw { size_t a; float ax, ay, az; float4 f0, f1; float fa[8], fb[8]; };
+    auto fetch = [&](uint32_t t) {
+        Raw r;
+        const int i = tid >> 2, q = tid & 3;
+        const uint32_t o0 = t * tc::TM, na = min((uint32_t)tc::TM, n_vis - o0);
+        const uint32_t oi = o0 + ((uint32_t)i < na ? (uint32_t)i : 0u);     // idle slots read the tile's first anchor
+        r.a = identity ? size_t(oi) : size_t(st.anchor_index[oi]);
+        r.ax = __ldg(anchor + 3 * r.a); r.ay = __ldg(anchor + 3 * r.a + 1); r.az = __ldg(anchor + 3 * r.a + 2);
+        const float* frow = anchor_feat + r.a * FEAT;
+        r.f0 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q);
+        r.f1 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q + 1);
+        if (use_bank) {
+#pragma unroll
+            for (int jj = 0; jj < 8; ++jj) {
+                r.fa[jj] = __ldg(frow + 4 * jj);                      // feat[4 (j mod 8)],  j = 8q + jj
+                r.fb[jj] = __ldg(frow + 16 * (q & 1) + 2 * jj);       // feat[2 (j mod 16)]
+            }
+        }
+        return r;
+    };
+    Raw raw;
+    bool have_raw = s_tile[0] < ntiles;
+    if (have_raw) raw = fetch(s_tile[0]);
     {
         // B operands.  Layer 1: W1cat[n][k], n = 32 * mlp + hidden unit, k = input column (as in variant 1);
         // layer 2: one tile per MLP, row = output unit (zero rows pad N to 16 / 80 / 32), k = hidden unit.
@@ -866,7 +893,6 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
     __syncthreads();
     tc::fence_after_sync();
     const uint32_t tmem = s_tmem;
-    const bool use_bank = p.use_feat_bank != 0;
     uint32_t phase = 0;
     // descriptors of the operand tiles (the start address sits in the low bits in units of 16 bytes: stepping along K or to
     // another tile is an add)
@@ -874,31 +900,6 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
     const uint64_t dB1_hi = tc2::make_desc(tc::smem_u32(sB1_hi), tc2::SBO1), dB1_lo = tc2::make_desc(tc::smem_u32(sB1_lo), tc2::SBO1);
     const uint64_t dA2_hi = tc2::make_desc(tc::smem_u32(sA2_hi), tc2::SBO2), dA2_lo = tc2::make_desc(tc::smem_u32(sA2_lo), tc2::SBO2);
     const uint64_t dB2_hi = tc2::make_desc(tc::smem_u32(sB2_hi), tc2::SBO2), dB2_lo = tc2::make_desc(tc::smem_u32(sB2_lo), tc2::SBO2);
-
-    // raw inputs of this thread's (anchor slot, quarter) for one tile: fetched one tile ahead, so their global-memory
-    // latency hides behind the previous tile's second layer and row assembly
-    struct Raw { size_t a; float ax, ay, az; float4 f0, f1; float fa[8], fb[8]; };
-    auto fetch = [&](uint32_t t) {
-        Raw r;
-        const int i = tid >> 2, q = tid & 3;
-        const uint32_t o0 = t * tc::TM, na = min((uint32_t)tc::TM, n_vis - o0);
-        const uint32_t oi = o0 + ((uint32_t)i < na ? (uint32_t)i : 0u);     // idle slots read the tile's first anchor
-        r.a = identity ? size_t(oi) : size_t(st.anchor_index[oi]);
-        r.ax = __ldg(anchor + 3 * r.a); r.ay = __ldg(anchor + 3 * r.a + 1); r.az = __ldg(anchor + 3 * r.a + 2);
-        const float* frow = anchor_feat + r.a * FEAT;
-        r.f0 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q);
-        r.f1 = __ldg(reinterpret_cast<const float4*>(frow) + 2 * q + 1);
-        if (use_bank) {
-#pragma unroll
-            for (int jj = 0; jj < 8; ++jj) {
-                r.fa[jj] = __ldg(frow + 4 * jj);                      // feat[4 (j mod 8)],  j = 8q + jj
-                r.fb[jj] = __ldg(frow + 16 * (q & 1) + 2 * jj);       // feat[2 (j mod 16)]
-            }
-        }
-        return r;
-    };
-    Raw raw;
-    bool have_raw = false;
 
     for (int it = 0;; ++it) {
         const uint32_t tile = s_tile[it & 1];
@@ -987,12 +988,6 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
             }
             tc::umma_commit(&s_bar);
         }
-        {
-            // the next tile's raw inputs go out now; nothing reads them before the next iteration
-            const uint32_t nxt = s_tile[(it + 1) & 1];
-            have_raw = nxt < ntiles;
-            if (have_raw) raw = fetch(nxt);
-        }
         tc::mbar_wait(&s_bar, phase);
         phase ^= 1u;
         tc::fence_after_sync();
@@ -1042,6 +1037,13 @@ decode_forward_v2_kernel(int A, const int identity, const float* __restrict__ an
                 }
             }
             tc::umma_commit(&s_bar);
+        }
+        {
+            // the next tile's raw inputs go out now: behind the last proxy fence of this tile (fence.proxy.async is
+            // MEMBAR.ALL.CTA + FENCE.VIEW.ASYNC and would wait for them), ahead of everything that remains
+            const uint32_t nxt = s_tile[(it + 1) & 1];
+            have_raw = nxt < ntiles;
+            if (have_raw) raw = fetch(nxt);
         }
         tc::mbar_wait(&s_bar, phase);
         phase ^= 1u;
