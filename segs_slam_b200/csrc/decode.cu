@@ -6,25 +6,26 @@
 // MLPs, the opacity > 0 mask, repeat/cat into a [A*10, 22] temporary and a second boolean gather —
 // about 40 ATen kernels and ~1 GB of temporaries at 200k anchors.
 //
-// Forward (ONE kernel, thread = visible anchor, CTA = 128 consecutive anchors):
-//   * all weights (7.5k floats) live in shared memory, rows padded to float4 so that every
-//     weight fetch is one broadcast LDS.128 feeding four FFMAs; the appearance columns of the
-//     colour MLP are view-constant and are folded into its bias once per CTA;
-//   * both compactions (visible anchors, surviving offsets) are done in-kernel: CTA-local ballot
-//     scans plus a decoupled look-back over the preceding CTAs (atomic ticket => only running
-//     CTAs are waited for), so rows come out in the reference's (anchor, offset) order with no
-//     temporaries and no second pass.  The two totals are stored to mapped host memory by the last
-//     CTA (the host needs them to shape the outputs, as the reference's boolean indexing does).
-// Backward (two kernels):
-//   1. thread = visible anchor: recomputes the forward, back-propagates the row gradients to
-//      d_anchor / d_offset / d_anchor_feat / d_scaling and stores the per-anchor factors of the
-//      weight gradients (layer inputs and pre-activation gradients) feature-major in scratch;
-//   2. persistent CTAs turn those factors into the weight gradients: every job is
-//      dW[p][q] = sum_k U[k][p] * V[k][q] with q on the 32 lanes, accumulated in registers over
-//      all anchors and flushed once with atomics.
-// FP32 FFMA throughout (accumulation order differs from cuBLAS sgemm at the 1e-6 level).  The two
-// GEMM-shaped parts (layer products, weight-gradient sums) are the tcgen05 candidates of the path;
-// see DESIGN.md §decode.
+// Two kernel sets live behind segs_decode_forward / segs_decode_backward (segs_decode_set_variant):
+//
+// Variant 2 (default):
+//   forward   decode_compact_kernel lists the visible anchors; decode_forward_v2_kernel: persistent CTAs of 512 threads,
+//             tile = 128 visible anchors, BOTH layers of the three MLPs on tcgen05 (3xTF32, 51 MMAs per tile), rows
+//             assembled by thread = output row in the reference's (anchor, offset) order; the layer activations stay in
+//             the state buffer for the backward;
+//   backward  decode_backward_kernel<true> (thread = visible anchor) back-propagates the row gradients to d_anchor /
+//             d_offset / d_anchor_feat / d_scaling from those activations and stores the per-anchor factors of the weight
+//             gradients feature-major in scratch; decode_wgrad_tc_kernel turns them into dW on tcgen05 (K = anchor
+//             index, accumulators in TMEM over all stages of a persistent CTA).
+// Variant 1 (round 1):
+//   forward   decode_forward_kernel: thread = visible anchor, CTA = 128 consecutive anchors, first layers on tcgen05,
+//             second layers as FP32 FFMA chains out of shared memory (weights padded to float4: one broadcast LDS.128
+//             feeds four FFMAs); both compactions (visible anchors, surviving offsets) in-kernel with CTA-local ballot
+//             scans plus a decoupled look-back;
+//   backward  decode_backward_kernel<false> recomputes the forward; decode_wgrad_kernel: persistent CTAs,
+//             dW[p][q] = sum_k U[k][p] V[k][q] with q on the 32 lanes, FP32 FFMA, flushed once with atomics.
+// In both, the two totals (visible anchors, emitted rows) are stored to mapped host memory by the last tile (the host needs
+// them to shape the outputs, as the reference's boolean indexing does).
 #include <algorithm>
 #include <atomic>
 #include <cstdlib>

@@ -140,3 +140,21 @@ def test_header_is_plain_c(tmp_path):
     subprocess.check_call(["gcc", "-std=c99", f"-I{inc}", str(src), "-o", str(exe), f"-L{lib}", "-lsegs_raster",
                            f"-Wl,-rpath,{lib}", "-L/usr/local/cuda/lib64", "-Wl,-rpath,/usr/local/cuda/lib64"])
     assert subprocess.run([str(exe)]).returncode == 0          # segs_version() needs no GPU
+
+
+def test_decode_variant_switch():
+    """segs_decode_set_variant / segs_decode_get_variant (include/segs_raster.h): 2 is the default unless the environment
+    says otherwise, only 1 and 2 are accepted (no compute call: runs without a GPU)."""
+    from segs_slam_b200 import _lib
+    lib = _lib.load()
+    before = lib.segs_decode_get_variant()
+    assert before in (1, 2)
+    if "SEGS_DECODE_VARIANT" not in os.environ:
+        assert before == 2
+    try:
+        assert lib.segs_decode_set_variant(1) == 0 and lib.segs_decode_get_variant() == 1
+        assert lib.segs_decode_set_variant(2) == 0 and lib.segs_decode_get_variant() == 2
+        assert lib.segs_decode_set_variant(3) != 0 and lib.segs_decode_get_variant() == 2
+        assert lib.segs_decode_state_bytes(1000) >= 1000 * (12 + 4 * (96 + 110))      # the state carries the activations
+    finally:
+        lib.segs_decode_set_variant(before)
