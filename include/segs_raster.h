@@ -224,7 +224,8 @@ typedef struct segs_decode_grads {
 } segs_decode_grads;
 
 /* Bytes of caller-owned state that forward fills and backward reads (anchor ordinals, row starts,
- * masks, look-back words). */
+ * masks, look-back words and — left by the default forward kernel for the backward — the layer-1
+ * pre-activations [96] and second-layer outputs [110] of every visible anchor: 836 bytes per anchor). */
 size_t segs_decode_state_bytes(int A);
 
 /* visible_mask: [A] bytes (C++ bool) or NULL = all visible.  scaling = exp(_scaling) [A,6]
