@@ -75,7 +75,8 @@ coarse_emit_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict
     __shared__ uint32_t s_id[EMIT_TILE];
     __shared__ ushort4 s_rect[EMIT_TILE];
     __shared__ uint32_t s_warp[EMIT_THREADS / 32];
-    __shared__ uint32_t s_tile, s_base;
+    __shared__ uint32_t s_look[EMIT_THREADS / 32];
+    __shared__ uint32_t s_tile;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     if (threadIdx.x == 0) s_tile = atomicAdd(ticket, 1u);
     __syncthreads();
@@ -119,32 +120,44 @@ coarse_emit_kernel(const uint32_t* __restrict__ order, const ushort4* __restrict
         s_rect[slot] = rc[i];
         run += c[i];
     }
-    if (warp == 0) {
-        // decoupled look-back over the preceding CTAs' totals (one word per CTA), 32 tiles per
-        // round: lane l polls tile (t - l); the nearest lane holding an inclusive prefix ends the walk
-        if (lane == 0) {
-            s_off[EMIT_TILE] = total;
-            look[tile] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | total;
-        }
-        uint32_t excl = 0;
-        if (tile != 0) {
-            for (int t = (int)tile - 1;; t -= 32) {
-                uint32_t w = FLAG_PREFIX;                       // tiles before 0: an empty prefix
-                if (t - lane >= 0) {
-                    do { w = look[t - lane]; } while ((w & FLAG_MASK) == 0u);
-                }
-                const unsigned pref = __ballot_sync(FULL, (w & FLAG_MASK) == FLAG_PREFIX);
-                const int stop = __ffs(pref) - 1;               // nearest published prefix (-1: none)
-                const uint32_t v = (stop < 0 || lane <= stop) ? (w & ~FLAG_MASK) : 0u;
-                excl += __reduce_add_sync(FULL, v);
-                if (stop >= 0) break;
-            }
-            if (lane == 0) look[tile] = FLAG_PREFIX | (excl + total);
-        }
-        if (lane == 0) s_base = excl;
+    // decoupled look-back over the preceding CTAs' totals (one word per CTA).  The CTAs of this single-wave kernel publish
+    // their aggregates at about the same time, so a 32-wide walk meets a published prefix only after many dependent
+    // global round trips (tile 488 of 489 at C2: up to 15); the 8 warps poll 8 windows of 32 tiles AT ONCE and every
+    // thread combines them: the nearest window holding an inclusive prefix ends the walk.
+    if (threadIdx.x == 0) {
+        s_off[EMIT_TILE] = total;
+        look[tile] = (tile == 0 ? FLAG_PREFIX : FLAG_AGG) | total;
     }
-    __syncthreads();
-    const uint32_t base = s_base;
+    uint32_t excl = 0;
+    if (tile != 0) {
+        for (int newest = (int)tile - 1;; newest -= EMIT_THREADS) {
+            const int t = newest - 32 * warp - lane;
+            uint32_t w = FLAG_PREFIX;                           // tiles before 0: an empty prefix
+            if (t >= 0) {
+                do { w = look[t]; } while ((w & FLAG_MASK) == 0u);
+            }
+            const unsigned pref = __ballot_sync(FULL, (w & FLAG_MASK) == FLAG_PREFIX);
+            const int stop = __ffs(pref) - 1;                   // nearest published prefix of this window (-1: none)
+            const uint32_t v = (stop < 0 || lane <= stop) ? (w & ~FLAG_MASK) : 0u;
+            const uint32_t sum = __reduce_add_sync(FULL, v);
+            if (lane == 0) s_look[warp] = sum | (stop >= 0 ? 0x80000000u : 0u);     // sums stay below 2^30
+            __syncthreads();
+            bool done = false;
+#pragma unroll
+            for (int q = 0; q < EMIT_THREADS / 32; ++q) {
+                if (!done) {
+                    const uint32_t x = s_look[q];
+                    excl += x & 0x7FFFFFFFu;
+                    done = (x & 0x80000000u) != 0u;
+                }
+            }
+            if (done) break;
+            __syncthreads();                                    // s_look is rewritten in the next round
+        }
+        if (threadIdx.x == 0) look[tile] = FLAG_PREFIX | (excl + total);
+    }
+    __syncthreads();                                            // s_off / s_id / s_rect are complete
+    const uint32_t base = excl;
 
     // load-balanced expansion: output slot j belongs to the last item whose offset is <= j
     for (uint32_t j = threadIdx.x; j < total; j += EMIT_THREADS) {
