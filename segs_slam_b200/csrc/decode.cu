@@ -682,8 +682,8 @@ decode_forward_kernel(int A, const unsigned char* __restrict__ visible_mask, con
 //     back to shared memory as the K-major A operands of
 //   * layer 2:  O_m[128 x N_m] = relu(H_m)[128 x 32] W2_m^T    3 x 12 tcgen05.mma, N = 16 / 80 / 32 (opacity / cov /
 //     colour, zero-padded rows) -> TMEM cols 128.. / 160.. / 96..
-//     epilogue 2 (16 warps x 32 columns): bias, tanh + mask for the opacity columns, everything else to a
-//     [128][113]-float tile in shared memory (it overlays the dead A operands);
+//     epilogue 2 (16 warps x 32 columns): + bias, into a [128][113]-float tile in shared memory (it overlays the dead
+//     A operands); tanh + mask of the opacity columns then run one (anchor, offset) pair per thread;
 //   * the compacted rows are then assembled by thread = output row exactly as in variant 1 (activation, quaternion
 //     normalisation, coalesced stores), now with no dot products left in the loop.
 // 51 UTCHMMA per tile; every scalar FMA chain of the MLPs is gone from the forward.
